@@ -1,0 +1,92 @@
+"""ctypes binding of libcape_msda.so (C ABI in include/cape_msda.h).
+
+There is deliberately no fallback: if the shared object is missing or fails to load, every op raises
+``CapeLibraryError`` telling the user to run ``python __graft_entry__.py build`` — nothing silently routes to
+PyTorch eager, the CPU or the test oracle.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libcape_msda.so")
+ABI_VERSION = 1
+
+DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
+
+
+class CapeLibraryError(RuntimeError):
+    pass
+
+
+class Dims(ctypes.Structure):
+    """``cape_msda_dims`` (include/cape_msda.h)."""
+    _fields_ = [("N", ctypes.c_int32), ("S", ctypes.c_int32), ("M", ctypes.c_int32), ("D", ctypes.c_int32),
+                ("Lq", ctypes.c_int32), ("L", ctypes.c_int32), ("P", ctypes.c_int32)]
+
+
+_lock = threading.Lock()
+_lib = None
+_load_error = None
+
+_vp, _i = ctypes.c_void_p, ctypes.c_int
+_SIGNATURES = {
+    "cape_abi_version": (ctypes.c_int, []),
+    "cape_last_error": (ctypes.c_char_p, []),
+    "cape_launch_count": (ctypes.c_uint64, []),
+    "cape_msda_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(Dims), _i, _i, _vp]),
+    "cape_msda_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(Dims), _i, _i, _i, _vp]),
+    "cape_msda_decode": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(Dims), _i, _vp]),
+    "cape_msda_host_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(Dims), _i]),
+    "cape_msda_forward_backward_host": (_i, [_vp] * 10 + [ctypes.POINTER(Dims), _vp, ctypes.c_size_t, _vp]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def load():
+    """Load (once) and return the ctypes handle; raises CapeLibraryError when the library is unavailable."""
+    global _lib, _load_error
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            _load_error = (f"{LIB_PATH} not found: build it with `python __graft_entry__.py build` "
+                           f"(nvcc, sm_100a). There is no CPU or eager fallback.")
+            raise CapeLibraryError(_load_error)
+        try:
+            lib = ctypes.CDLL(LIB_PATH)
+        except OSError as e:                                    # pragma: no cover - depends on the box
+            _load_error = f"cannot load {LIB_PATH}: {e}"
+            raise CapeLibraryError(_load_error) from e
+        for name, (restype, argtypes) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        got = lib.cape_abi_version()
+        if got != ABI_VERSION:
+            raise CapeLibraryError(f"{LIB_PATH} has ABI version {got}, this package expects {ABI_VERSION}: rebuild")
+        _lib = lib
+    return _lib
+
+
+def available() -> bool:
+    try:
+        load()
+        return True
+    except CapeLibraryError:
+        return False
+
+
+def check(rc: int, what: str) -> None:
+    """Turn a non-zero ABI return code into a RuntimeError carrying cape_last_error()."""
+    if rc != 0:
+        msg = load().cape_last_error()
+        raise RuntimeError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")
+
+
+def launch_count() -> int:
+    return int(load().cape_launch_count())

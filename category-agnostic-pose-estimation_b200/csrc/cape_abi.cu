@@ -1,0 +1,284 @@
+// C ABI of libcape_msda.so (declared in include/cape_msda.h).  Validation, dtype dispatch and stream plumbing only —
+// the kernels live in msda_forward.cu / msda_backward.cu.  No allocation, no device synchronisation, no CPU path.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "msda_launch.h"
+
+namespace cape {
+
+namespace {
+
+std::atomic<uint64_t> g_launches{0};
+thread_local char t_error[512] = "";
+
+int fail(int code, const char* fmt, ...) __attribute__((format(printf, 2, 3)));
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_error, sizeof(t_error), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int fail_cuda(cudaError_t e, const char* what) {
+    snprintf(t_error, sizeof(t_error), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    return static_cast<int>(e);
+}
+
+size_t dtype_size(int dt) {
+    switch (dt) {
+        case CAPE_DTYPE_F32: return 4;
+        case CAPE_DTYPE_BF16:
+        case CAPE_DTYPE_F16: return 2;
+    }
+    return 0;
+}
+
+int check_dims(const cape_msda_dims* d) {
+    if (!d) return fail(CAPE_ERR_NULL_PTR, "dims is NULL");
+    if (d->N < 0 || d->S < 0 || d->Lq < 0 || d->M <= 0 || d->D <= 0 || d->L <= 0 || d->P <= 0)
+        return fail(CAPE_ERR_BAD_DIMS, "negative or zero dimension (N=%d S=%d M=%d D=%d Lq=%d L=%d P=%d)", d->N, d->S, d->M,
+                    d->D, d->Lq, d->L, d->P);
+    if (d->L > kMaxLevels || d->P > kMaxPoints)
+        return fail(CAPE_ERR_BAD_DIMS, "L=%d (max %d) or P=%d (max %d) out of range", d->L, kMaxLevels, d->P, kMaxPoints);
+    if (d->D > 256 || d->D % 4 != 0)
+        return fail(CAPE_ERR_BAD_DIMS, "D=%d must be a multiple of 4 and <= 256", d->D);
+    if (static_cast<int64_t>(d->S) * d->M * d->D > 0x7fffffffLL)
+        return fail(CAPE_ERR_BAD_DIMS, "S*M*D=%lld exceeds 2^31-1", static_cast<long long>(d->S) * d->M * d->D);
+    return 0;
+}
+
+int check_dtypes(int value_dtype, int aux_dtype) {
+    if (dtype_size(value_dtype) == 0) return fail(CAPE_ERR_BAD_DTYPE, "unknown value dtype %d", value_dtype);
+    if (aux_dtype != CAPE_DTYPE_F32 && aux_dtype != value_dtype)
+        return fail(CAPE_ERR_BAD_DTYPE, "aux dtype %d must be fp32 or equal to the value dtype %d", aux_dtype, value_dtype);
+    return 0;
+}
+
+// Device pointer check: NULL, alignment, and that CUDA knows the allocation as device (or managed) memory.
+int check_ptr(const void* p, const char* name, bool empty_ok, unsigned align = 16) {
+    if (!p) return empty_ok ? 0 : fail(CAPE_ERR_NULL_PTR, "%s is NULL", name);
+    if (reinterpret_cast<uintptr_t>(p) % align != 0)
+        return fail(CAPE_ERR_MISALIGNED, "%s (%p) is not %u-byte aligned", name, p, align);
+    cudaPointerAttributes attr;
+    const cudaError_t e = cudaPointerGetAttributes(&attr, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(CAPE_ERR_NOT_DEVICE_PTR, "%s (%p): %s", name, p, cudaGetErrorString(e));
+    }
+    if (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged)
+        return fail(CAPE_ERR_NOT_DEVICE_PTR, "%s (%p) is host memory; this library has no CPU path", name, p);
+    return 0;
+}
+
+}  // namespace
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+}  // namespace cape
+
+using namespace cape;
+
+extern "C" {
+
+int cape_abi_version(void) { return CAPE_ABI_VERSION; }
+
+const char* cape_last_error(void) { return t_error; }
+
+uint64_t cape_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int cape_msda_forward(const void* value, const int64_t* spatial_shapes_dev, const int64_t* level_start_index_dev,
+                      const void* sampling_locations, const void* attention_weights, void* out,
+                      const cape_msda_dims* dims, int value_dtype, int aux_dtype, void* stream) {
+    int rc;
+    if ((rc = check_dims(dims)) || (rc = check_dtypes(value_dtype, aux_dtype))) return rc;
+    const bool empty = dims->N == 0 || dims->Lq == 0;
+    if ((rc = check_ptr(value, "value", empty || dims->S == 0)) || (rc = check_ptr(spatial_shapes_dev, "spatial_shapes", false, 8)) ||
+        (rc = check_ptr(level_start_index_dev, "level_start_index", false, 8)) ||
+        (rc = check_ptr(sampling_locations, "sampling_locations", empty)) ||
+        (rc = check_ptr(attention_weights, "attention_weights", empty)) || (rc = check_ptr(out, "out", empty)))
+        return rc;
+    if (empty) return 0;
+    FwdArgs a{};
+    a.value = value;
+    a.shapes = spatial_shapes_dev;
+    a.starts = level_start_index_dev;
+    a.loc = sampling_locations;
+    a.attn = attention_weights;
+    a.ref_points = nullptr;
+    a.out = out;
+    a.d = *dims;
+    a.value_dtype = value_dtype;
+    a.aux_dtype = aux_dtype;
+    a.fused = false;
+    const cudaError_t e = launch_forward(a, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? 0 : fail_cuda(e, "cape_msda_forward launch");
+}
+
+int cape_msda_backward(const void* grad_out, const void* value, const int64_t* spatial_shapes_dev,
+                       const int64_t* level_start_index_dev, const void* sampling_locations,
+                       const void* attention_weights, float* grad_value, void* grad_loc, void* grad_attn,
+                       const cape_msda_dims* dims, int value_dtype, int aux_dtype, int zero_grad_value, void* stream) {
+    int rc;
+    if ((rc = check_dims(dims)) || (rc = check_dtypes(value_dtype, aux_dtype))) return rc;
+    const bool empty = dims->N == 0 || dims->Lq == 0;
+    const bool no_value = dims->N == 0 || dims->S == 0;
+    if ((rc = check_ptr(grad_out, "grad_out", empty)) || (rc = check_ptr(value, "value", empty || no_value)) ||
+        (rc = check_ptr(spatial_shapes_dev, "spatial_shapes", false, 8)) ||
+        (rc = check_ptr(level_start_index_dev, "level_start_index", false, 8)) ||
+        (rc = check_ptr(sampling_locations, "sampling_locations", empty)) ||
+        (rc = check_ptr(attention_weights, "attention_weights", empty)) || (rc = check_ptr(grad_value, "grad_value", no_value)) ||
+        (rc = check_ptr(grad_loc, "grad_loc", empty)) || (rc = check_ptr(grad_attn, "grad_attn", empty)))
+        return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (zero_grad_value && !no_value) {
+        const size_t bytes = static_cast<size_t>(dims->N) * dims->S * dims->M * dims->D * sizeof(float);
+        const cudaError_t e = cudaMemsetAsync(grad_value, 0, bytes, s);
+        if (e != cudaSuccess) return fail_cuda(e, "cape_msda_backward memset(grad_value)");
+    }
+    if (empty) return 0;
+    BwdArgs a{};
+    a.grad_out = grad_out;
+    a.value = value;
+    a.shapes = spatial_shapes_dev;
+    a.starts = level_start_index_dev;
+    a.loc = sampling_locations;
+    a.attn = attention_weights;
+    a.grad_value = grad_value;
+    a.grad_loc = grad_loc;
+    a.grad_attn = grad_attn;
+    a.d = *dims;
+    a.value_dtype = value_dtype;
+    a.aux_dtype = aux_dtype;
+    const cudaError_t e = launch_backward(a, s);
+    return e == cudaSuccess ? 0 : fail_cuda(e, "cape_msda_backward launch");
+}
+
+int cape_msda_decode(const void* value_cache, const int64_t* spatial_shapes_dev, const int64_t* level_start_index_dev,
+                     const float* reference_points, const float* sampling_offsets, const float* attention_logits,
+                     void* out, const cape_msda_dims* dims, int value_dtype, void* stream) {
+    int rc;
+    if ((rc = check_dims(dims)) || (rc = check_dtypes(value_dtype, CAPE_DTYPE_F32))) return rc;
+    const bool empty = dims->N == 0 || dims->Lq == 0;
+    if ((rc = check_ptr(value_cache, "value_cache", empty || dims->S == 0)) ||
+        (rc = check_ptr(spatial_shapes_dev, "spatial_shapes", false, 8)) ||
+        (rc = check_ptr(level_start_index_dev, "level_start_index", false, 8)) ||
+        (rc = check_ptr(reference_points, "reference_points", empty)) ||
+        (rc = check_ptr(sampling_offsets, "sampling_offsets", empty)) ||
+        (rc = check_ptr(attention_logits, "attention_logits", empty)) || (rc = check_ptr(out, "out", empty)))
+        return rc;
+    if (empty) return 0;
+    FwdArgs a{};
+    a.value = value_cache;
+    a.shapes = spatial_shapes_dev;
+    a.starts = level_start_index_dev;
+    a.loc = sampling_offsets;
+    a.attn = attention_logits;
+    a.ref_points = reference_points;
+    a.out = out;
+    a.d = *dims;
+    a.value_dtype = value_dtype;
+    a.aux_dtype = CAPE_DTYPE_F32;
+    a.fused = true;
+    const cudaError_t e = launch_forward(a, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? 0 : fail_cuda(e, "cape_msda_decode launch");
+}
+
+// ---- host-buffer round trip ------------------------------------------------------------------------------------
+
+namespace {
+struct HostPlan {
+    size_t value, loc, attn, out, gout, gvalue, gloc, gattn, shapes, starts, total;
+};
+size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
+HostPlan plan_host(const cape_msda_dims& d, bool bwd) {
+    HostPlan p{};
+    const size_t nv = static_cast<size_t>(d.N) * d.S * d.M * d.D * 4;
+    const size_t no = static_cast<size_t>(d.N) * d.Lq * d.M * d.D * 4;
+    const size_t na = static_cast<size_t>(d.N) * d.Lq * d.M * d.L * d.P * 4;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        const size_t at = off;
+        off += align256(bytes);
+        return at;
+    };
+    p.shapes = take(static_cast<size_t>(d.L) * 2 * 8);
+    p.starts = take(static_cast<size_t>(d.L) * 8);
+    p.value = take(nv);
+    p.loc = take(na * 2);
+    p.attn = take(na);
+    p.out = take(no);
+    if (bwd) {
+        p.gout = take(no);
+        p.gvalue = take(nv);
+        p.gloc = take(na * 2);
+        p.gattn = take(na);
+    }
+    p.total = off;
+    return p;
+}
+}  // namespace
+
+size_t cape_msda_host_workspace_bytes(const cape_msda_dims* dims, int with_backward) {
+    if (check_dims(dims)) return 0;
+    return plan_host(*dims, with_backward != 0).total;
+}
+
+int cape_msda_forward_backward_host(const float* value_host, const int64_t* spatial_shapes_host,
+                                    const int64_t* level_start_index_host, const float* loc_host,
+                                    const float* attn_host, const float* grad_out_host, float* out_host,
+                                    float* grad_value_host, float* grad_loc_host, float* grad_attn_host,
+                                    const cape_msda_dims* dims, void* workspace_dev, size_t workspace_bytes,
+                                    void* stream) {
+    int rc;
+    if ((rc = check_dims(dims))) return rc;
+    const bool bwd = grad_out_host != nullptr;
+    if (!value_host || !spatial_shapes_host || !level_start_index_host || !loc_host || !attn_host || !out_host)
+        return fail(CAPE_ERR_NULL_PTR, "a required host pointer is NULL");
+    if (bwd && (!grad_value_host || !grad_loc_host || !grad_attn_host))
+        return fail(CAPE_ERR_NULL_PTR, "grad_out_host given but a gradient output pointer is NULL");
+    const HostPlan p = plan_host(*dims, bwd);
+    if ((rc = check_ptr(workspace_dev, "workspace_dev", false))) return rc;
+    if (workspace_bytes < p.total)
+        return fail(CAPE_ERR_WORKSPACE, "workspace %zu B < required %zu B", workspace_bytes, p.total);
+    const cape_msda_dims& d = *dims;
+    const size_t nv = static_cast<size_t>(d.N) * d.S * d.M * d.D * 4;
+    const size_t no = static_cast<size_t>(d.N) * d.Lq * d.M * d.D * 4;
+    const size_t na = static_cast<size_t>(d.N) * d.Lq * d.M * d.L * d.P * 4;
+    char* ws = static_cast<char*>(workspace_dev);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaError_t e;
+#define CAPE_COPY(dst, src, bytes, kind)                                                    \
+    if ((bytes) && (e = cudaMemcpyAsync((dst), (src), (bytes), (kind), s)) != cudaSuccess)  \
+        return fail_cuda(e, "cape_msda_forward_backward_host copy");
+    CAPE_COPY(ws + p.shapes, spatial_shapes_host, static_cast<size_t>(d.L) * 16, cudaMemcpyHostToDevice)
+    CAPE_COPY(ws + p.starts, level_start_index_host, static_cast<size_t>(d.L) * 8, cudaMemcpyHostToDevice)
+    CAPE_COPY(ws + p.value, value_host, nv, cudaMemcpyHostToDevice)
+    CAPE_COPY(ws + p.loc, loc_host, na * 2, cudaMemcpyHostToDevice)
+    CAPE_COPY(ws + p.attn, attn_host, na, cudaMemcpyHostToDevice)
+    if (bwd) CAPE_COPY(ws + p.gout, grad_out_host, no, cudaMemcpyHostToDevice)
+    rc = cape_msda_forward(ws + p.value, reinterpret_cast<const int64_t*>(ws + p.shapes),
+                           reinterpret_cast<const int64_t*>(ws + p.starts), ws + p.loc, ws + p.attn, ws + p.out, dims,
+                           CAPE_DTYPE_F32, CAPE_DTYPE_F32, stream);
+    if (rc) return rc;
+    if (bwd) {
+        rc = cape_msda_backward(ws + p.gout, ws + p.value, reinterpret_cast<const int64_t*>(ws + p.shapes),
+                                reinterpret_cast<const int64_t*>(ws + p.starts), ws + p.loc, ws + p.attn,
+                                reinterpret_cast<float*>(ws + p.gvalue), ws + p.gloc, ws + p.gattn, dims, CAPE_DTYPE_F32,
+                                CAPE_DTYPE_F32, /*zero_grad_value=*/1, stream);
+        if (rc) return rc;
+    }
+    CAPE_COPY(out_host, ws + p.out, no, cudaMemcpyDeviceToHost)
+    if (bwd) {
+        CAPE_COPY(grad_value_host, ws + p.gvalue, nv, cudaMemcpyDeviceToHost)
+        CAPE_COPY(grad_loc_host, ws + p.gloc, na * 2, cudaMemcpyDeviceToHost)
+        CAPE_COPY(grad_attn_host, ws + p.gattn, na, cudaMemcpyDeviceToHost)
+    }
+#undef CAPE_COPY
+    return 0;
+}
+
+}  // extern "C"

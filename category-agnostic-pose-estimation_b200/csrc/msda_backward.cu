@@ -1,0 +1,250 @@
+// MSDeformAttn backward (scatter of grad_value + grad_sampling_loc + grad_attn_weight in one pass) for sm_100a.
+//
+// Derivative of ms_deform_attn_core_pytorch, /root/reference/models/deformable_transformer.py:129-141, i.e. what
+// autograd produces through grid_sampler_2d_backward.  Per sample with weight A, corner weights w_c = wx_c*wy_c and
+// G = grad_out[n, q, m, :]:
+//     grad_attn      = sum_c w_c <G, v_c>
+//     grad_loc.x     = A * W_l * sum_c (dx ? +wy_c : -wy_c) <G, v_c>
+//     grad_loc.y     = A * H_l * sum_c (dy ? +wx_c : -wx_c) <G, v_c>
+//     grad_value[c] += A * w_c * G                 (in-bounds corners only)
+//
+// Fast path (D = 32, P = 4, L <= 4): same CTA / warp / lane mapping as the forward (lane = (point p, channel quad k)).
+// The three dot-product partials are folded over the 8 lanes of a point with xor-shuffles; every lane of a point then
+// holds the sums, lane k == l keeps level l's result, and after the level loop lanes k < L write the grad_loc /
+// grad_attn entries of the (q, m).  grad_value is scattered with 16-byte vector reductions (REDG.E.ADD.F32x4): 8 lanes
+// cover one 128 B corner row.
+#include "msda_common.cuh"
+#include "msda_launch.h"
+
+namespace cape {
+
+namespace {
+
+constexpr int kBwdWarps = 8;
+
+template <typename VT>
+__device__ __forceinline__ void scatter_level(const VT* __restrict__ vbase, float* __restrict__ gbase, int rowStride,
+                                              int H, int W, int start, float locx, float locy, float a,
+                                              const float4& g, float& ga, float& gx, float& gy) {
+    ga = 0.f;
+    gx = 0.f;
+    gy = 0.f;
+    int x0, y0;
+    float lx, ly;
+    if (!sample_coords(locx, locy, H, W, x0, y0, lx, ly)) return;
+    const float hx = 1.f - lx, hy = 1.f - ly;
+    const bool x0ok = x0 >= 0, x1ok = x0 + 1 < W, y0ok = y0 >= 0, y1ok = y0 + 1 < H;
+    const int64_t off00 = static_cast<int64_t>(start + y0 * W + x0) * rowStride;
+    const int64_t offRow = static_cast<int64_t>(W) * rowStride;
+    float4 v00 = make_float4(0.f, 0.f, 0.f, 0.f), v01 = v00, v10 = v00, v11 = v00;
+    if (y0ok && x0ok) v00 = ld4(vbase + off00);
+    if (y0ok && x1ok) v01 = ld4(vbase + off00 + rowStride);
+    if (y1ok && x0ok) v10 = ld4(vbase + off00 + offRow);
+    if (y1ok && x1ok) v11 = ld4(vbase + off00 + offRow + rowStride);
+    if (y0ok && x0ok) {
+        const float c = a * hy * hx;
+        red_add4(gbase + off00, c * g.x, c * g.y, c * g.z, c * g.w);
+    }
+    if (y0ok && x1ok) {
+        const float c = a * hy * lx;
+        red_add4(gbase + off00 + rowStride, c * g.x, c * g.y, c * g.z, c * g.w);
+    }
+    if (y1ok && x0ok) {
+        const float c = a * ly * hx;
+        red_add4(gbase + off00 + offRow, c * g.x, c * g.y, c * g.z, c * g.w);
+    }
+    if (y1ok && x1ok) {
+        const float c = a * ly * lx;
+        red_add4(gbase + off00 + offRow + rowStride, c * g.x, c * g.y, c * g.z, c * g.w);
+    }
+    const float d00 = dot4(g, v00), d01 = dot4(g, v01), d10 = dot4(g, v10), d11 = dot4(g, v11);   // 0 for OOB corners
+    ga = hy * (hx * d00 + lx * d01) + ly * (hx * d10 + lx * d11);
+    gx = hy * (d01 - d00) + ly * (d11 - d10);
+    gy = hx * (d10 - d00) + lx * (d11 - d01);
+}
+
+template <typename VT, typename AT, int L>
+__global__ void __launch_bounds__(kBwdWarps * 32)
+msda_bwd_fast_kernel(const VT* __restrict__ gout, const VT* __restrict__ value, const int64_t* __restrict__ shapes,
+                     const int64_t* __restrict__ starts, const AT* __restrict__ locp, const AT* __restrict__ attnp,
+                     float* __restrict__ gvalue, AT* __restrict__ gloc, AT* __restrict__ gattn, int N, int S, int M,
+                     int Lq, int q_per_cta, int q_tiles) {
+    constexpr int D = 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int p = lane >> 3, k = lane & 7;
+    int bid = blockIdx.x;
+    const int qt = bid % q_tiles;
+    bid /= q_tiles;
+    const int m = bid % M, n = bid / M;
+    Levels<L> lv;
+    lv.load(shapes, starts);
+    const int rowStride = M * D;
+    const int64_t headOff = (static_cast<int64_t>(n) * S * M + m) * D + k * 4;
+    const VT* vbase = value + headOff;
+    float* gbase = gvalue + headOff;
+    const int q_end = min(Lq, (qt + 1) * q_per_cta);
+    for (int q = qt * q_per_cta + warp; q < q_end; q += nwarps) {
+        const int64_t qm = (static_cast<int64_t>(n) * Lq + q) * M + m;
+        float locv = 0.f, attnv = 0.f;
+        if (lane < L * 8) locv = to_f32(locp[qm * (L * 8) + lane]);
+        if (lane < L * 4) attnv = to_f32(attnp[qm * (L * 4) + lane]);
+        const float4 g = ld4(gout + qm * D + k * 4);
+        float r_ga = 0.f, r_gx = 0.f, r_gy = 0.f;
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+            const float locx = __shfl_sync(kFullMask, locv, l * 8 + p * 2);
+            const float locy = __shfl_sync(kFullMask, locv, l * 8 + p * 2 + 1);
+            const float a = __shfl_sync(kFullMask, attnv, l * 4 + p);
+            float ga, gx, gy;
+            scatter_level(vbase, gbase, rowStride, lv.H[l], lv.W[l], lv.start[l], locx, locy, a, g, ga, gx, gy);
+#pragma unroll
+            for (int s = 1; s <= 4; s <<= 1) {
+                ga += __shfl_xor_sync(kFullMask, ga, s);
+                gx += __shfl_xor_sync(kFullMask, gx, s);
+                gy += __shfl_xor_sync(kFullMask, gy, s);
+            }
+            if (k == l) {
+                r_ga = ga;
+                r_gx = a * static_cast<float>(lv.W[l]) * gx;
+                r_gy = a * static_cast<float>(lv.H[l]) * gy;
+            }
+        }
+        if (k < L) {   // lane (p, k) owns sample (level k, point p)
+            const int si = k * 4 + p;
+            gattn[qm * (L * 4) + si] = from_f32<AT>(r_ga);
+            gloc[(qm * (L * 4) + si) * 2] = from_f32<AT>(r_gx);
+            gloc[(qm * (L * 4) + si) * 2 + 1] = from_f32<AT>(r_gy);
+        }
+    }
+}
+
+// Generic path: one warp per (n, q, m); lanes stride over channels; scalar atomics.
+template <typename VT, typename AT>
+__global__ void __launch_bounds__(128)
+msda_bwd_generic_kernel(const VT* __restrict__ gout, const VT* __restrict__ value, const int64_t* __restrict__ shapes,
+                        const int64_t* __restrict__ starts, const AT* __restrict__ locp, const AT* __restrict__ attnp,
+                        float* __restrict__ gvalue, AT* __restrict__ gloc, AT* __restrict__ gattn, int64_t total_qm,
+                        int S, int M, int D, int Lq, int L, int P) {
+    const int lane = threadIdx.x & 31;
+    const int64_t qm = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (qm >= total_qm) return;
+    const int m = static_cast<int>(qm % M);
+    const int64_t n = (qm / M) / Lq;
+    const int LP = L * P;
+    constexpr int kChunks = 8;
+    float g[kChunks];
+#pragma unroll
+    for (int ch = 0; ch < kChunks; ++ch) {
+        const int d = lane + ch * 32;
+        g[ch] = d < D ? to_f32(gout[qm * D + d]) : 0.f;
+    }
+    for (int l = 0; l < L; ++l) {
+        const int H = static_cast<int>(__ldg(shapes + 2 * l)), W = static_cast<int>(__ldg(shapes + 2 * l + 1));
+        const int start = static_cast<int>(__ldg(starts + l));
+        for (int p = 0; p < P; ++p) {
+            const int64_t si = qm * LP + l * P + p;
+            const float locx = to_f32(locp[si * 2]), locy = to_f32(locp[si * 2 + 1]), a = to_f32(attnp[si]);
+            float ga = 0.f, gx = 0.f, gy = 0.f;
+            int x0, y0;
+            float lx, ly;
+            if (sample_coords(locx, locy, H, W, x0, y0, lx, ly)) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int xi = x0 + (c & 1), yi = y0 + (c >> 1);
+                    if (xi < 0 || xi >= W || yi < 0 || yi >= H) continue;
+                    const float wx = (c & 1) ? lx : 1.f - lx, wy = (c >> 1) ? ly : 1.f - ly;
+                    const int64_t row = ((n * S + start + yi * W + xi) * M + m) * D;
+                    float dot = 0.f;
+#pragma unroll
+                    for (int ch = 0; ch < kChunks; ++ch) {
+                        const int d = lane + ch * 32;
+                        if (d < D) {
+                            dot = fmaf(g[ch], to_f32(value[row + d]), dot);
+                            atomicAdd(gvalue + row + d, a * wx * wy * g[ch]);
+                        }
+                    }
+                    ga = fmaf(wx * wy, dot, ga);
+                    gx += ((c & 1) ? wy : -wy) * dot;
+                    gy += ((c >> 1) ? wx : -wx) * dot;
+                }
+            }
+#pragma unroll
+            for (int s = 16; s >= 1; s >>= 1) {
+                ga += __shfl_xor_sync(kFullMask, ga, s);
+                gx += __shfl_xor_sync(kFullMask, gx, s);
+                gy += __shfl_xor_sync(kFullMask, gy, s);
+            }
+            if (lane == 0) {
+                gattn[si] = from_f32<AT>(ga);
+                gloc[si * 2] = from_f32<AT>(a * static_cast<float>(W) * gx);
+                gloc[si * 2 + 1] = from_f32<AT>(a * static_cast<float>(H) * gy);
+            }
+        }
+    }
+}
+
+template <typename VT, typename AT>
+cudaError_t launch_typed(const BwdArgs& a, cudaStream_t stream) {
+    const cape_msda_dims& d = a.d;
+    const int64_t total_qm = static_cast<int64_t>(d.N) * d.Lq * d.M;
+    if (total_qm == 0) return cudaSuccess;
+    const VT* gout = static_cast<const VT*>(a.grad_out);
+    const VT* value = static_cast<const VT*>(a.value);
+    const AT* loc = static_cast<const AT*>(a.loc);
+    const AT* attn = static_cast<const AT*>(a.attn);
+    AT* gloc = static_cast<AT*>(a.grad_loc);
+    AT* gattn = static_cast<AT*>(a.grad_attn);
+    if (d.D == 32 && d.P == 4 && d.L >= 1 && d.L <= 4) {
+        int q_per_cta = 64;
+        while (q_per_cta > 8 &&
+               static_cast<int64_t>(d.N) * d.M * ((d.Lq + q_per_cta - 1) / q_per_cta) < 148 * 8)
+            q_per_cta >>= 1;
+        if (q_per_cta > d.Lq) q_per_cta = d.Lq;
+        const int q_tiles = (d.Lq + q_per_cta - 1) / q_per_cta;
+        const int warps = q_per_cta < kBwdWarps ? q_per_cta : kBwdWarps;
+        const int64_t grid = static_cast<int64_t>(d.N) * d.M * q_tiles;
+        if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+        const dim3 gdim(static_cast<unsigned>(grid)), b(warps * 32);
+#define CAPE_BWD_CASE(LL)                                                                                          \
+    case LL:                                                                                                       \
+        msda_bwd_fast_kernel<VT, AT, LL><<<gdim, b, 0, stream>>>(gout, value, a.shapes, a.starts, loc, attn,        \
+                                                                 a.grad_value, gloc, gattn, d.N, d.S, d.M, d.Lq,   \
+                                                                 q_per_cta, q_tiles);                              \
+        break;
+        switch (d.L) {
+            CAPE_BWD_CASE(1)
+            CAPE_BWD_CASE(2)
+            CAPE_BWD_CASE(3)
+            CAPE_BWD_CASE(4)
+        }
+#undef CAPE_BWD_CASE
+    } else {
+        const int warps = 4;
+        const int64_t grid = (total_qm + warps - 1) / warps;
+        if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+        msda_bwd_generic_kernel<VT, AT><<<static_cast<unsigned>(grid), warps * 32, 0, stream>>>(
+            gout, value, a.shapes, a.starts, loc, attn, a.grad_value, gloc, gattn, total_qm, d.S, d.M, d.D, d.Lq, d.L,
+            d.P);
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+
+template <typename VT>
+cudaError_t launch_value_typed(const BwdArgs& a, cudaStream_t stream) {
+    if (a.aux_dtype == CAPE_DTYPE_F32) return launch_typed<VT, float>(a, stream);
+    return launch_typed<VT, VT>(a, stream);
+}
+
+}  // namespace
+
+cudaError_t launch_backward(const BwdArgs& a, cudaStream_t stream) {
+    switch (a.value_dtype) {
+        case CAPE_DTYPE_F32: return launch_value_typed<float>(a, stream);
+        case CAPE_DTYPE_BF16: return launch_value_typed<__nv_bfloat16>(a, stream);
+        case CAPE_DTYPE_F16: return launch_value_typed<__half>(a, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace cape

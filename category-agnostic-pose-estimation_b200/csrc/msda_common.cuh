@@ -1,0 +1,102 @@
+// Shared device helpers for the MSDeformAttn kernels (sm_100a).
+//
+// Arithmetic contract (what the parity tests pin): for one sample at normalised location (locx, locy) on a level
+// of size (H, W), following /root/reference/models/deformable_transformer.py:129,136-137
+//     g = 2*loc - 1                           (:129)
+//     x = (g + 1) * (W/2) - 0.5               (grid_sample, align_corners=False; separate mul and sub, like ATen's CPU path)
+//     x0 = floor(x), lx = x - x0, weights (1-lx, lx); same for y
+//     corners (y0,x0) (y0,x0+1) (y0+1,x0) (y0+1,x0+1); a corner outside the map contributes nothing (zeros padding)
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "msda_launch.h"
+
+namespace cape {
+
+constexpr unsigned kFullMask = 0xffffffffu;
+
+// ---- element access: 4 consecutive channels <-> float4 ------------------------------------------------------
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {
+    const uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
+    float4 f;
+    f.x = __uint_as_float(r.x << 16);
+    f.y = __uint_as_float(r.x & 0xffff0000u);
+    f.z = __uint_as_float(r.y << 16);
+    f.w = __uint_as_float(r.y & 0xffff0000u);
+    return f;
+}
+__device__ __forceinline__ float4 ld4(const __half* p) {
+    const uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4(__nv_bfloat16* p, const float4& v) {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 r;
+    r.x = *reinterpret_cast<const uint32_t*>(&a);
+    r.y = *reinterpret_cast<const uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = r;
+}
+__device__ __forceinline__ void st4(__half* p, const float4& v) {
+    const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    uint2 r;
+    r.x = *reinterpret_cast<const uint32_t*>(&a);
+    r.y = *reinterpret_cast<const uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = r;
+}
+
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+
+// fp32 vector reduction into global memory (REDG.E.ADD.F32x4 on sm_90+); p must be 16-byte aligned.
+__device__ __forceinline__ void red_add4(float* p, float x, float y, float z, float w) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+
+// ---- per-level metadata held in registers --------------------------------------------------------------------
+template <int L>
+struct Levels {
+    int H[L], W[L], start[L];
+    __device__ __forceinline__ void load(const int64_t* __restrict__ shapes, const int64_t* __restrict__ starts) {
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+            H[l] = static_cast<int>(__ldg(shapes + 2 * l));
+            W[l] = static_cast<int>(__ldg(shapes + 2 * l + 1));
+            start[l] = static_cast<int>(__ldg(starts + l));
+        }
+    }
+};
+
+// Pixel coordinates of one sample.  Returns false when no corner can be in bounds (also for NaN / inf locations),
+// in which case x0/y0/lx/ly are not written.
+__device__ __forceinline__ bool sample_coords(float locx, float locy, int H, int W, int& x0, int& y0, float& lx, float& ly) {
+    const float gx = fmaf(2.f, locx, -1.f);            // exact product, one rounding: same as mul then sub
+    const float gy = fmaf(2.f, locy, -1.f);
+    const float x = __fsub_rn(__fmul_rn(__fadd_rn(gx, 1.f), 0.5f * static_cast<float>(W)), 0.5f);
+    const float y = __fsub_rn(__fmul_rn(__fadd_rn(gy, 1.f), 0.5f * static_cast<float>(H)), 0.5f);
+    if (!(x >= -1.f && x < static_cast<float>(W) && y >= -1.f && y < static_cast<float>(H))) return false;
+    const float xf = floorf(x), yf = floorf(y);
+    lx = x - xf;
+    ly = y - yf;
+    x0 = static_cast<int>(xf);
+    y0 = static_cast<int>(yf);
+    return true;
+}
+
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) {
+    return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+
+}  // namespace cape

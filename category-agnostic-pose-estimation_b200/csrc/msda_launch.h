@@ -1,0 +1,53 @@
+// Internal launch interface between the C ABI (cape_abi.cu) and the kernel translation units.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/cape_msda.h"
+
+namespace cape {
+
+constexpr int kMaxLevels = 8;
+constexpr int kMaxPoints = 8;
+
+// What the sampling kernels read their per-sample (x, y, weight) from.
+//   direct: sampling_locations + attention_weights (aux dtype)          — cape_msda_forward / backward
+//   fused : reference_points + raw offsets + raw logits (fp32), softmax and the location arithmetic of
+//           MSDeformAttn.forward (deformable_transformer.py:99-105) done in the kernel — cape_msda_decode
+struct FwdArgs {
+    const void* value;
+    const int64_t* shapes;
+    const int64_t* starts;
+    const void* loc;          // direct: sampling_locations; fused: sampling_offsets
+    const void* attn;         // direct: attention_weights;  fused: attention_logits
+    const float* ref_points;  // fused only
+    void* out;
+    cape_msda_dims d;
+    int value_dtype;
+    int aux_dtype;
+    bool fused;
+};
+
+struct BwdArgs {
+    const void* grad_out;
+    const void* value;
+    const int64_t* shapes;
+    const int64_t* starts;
+    const void* loc;
+    const void* attn;
+    float* grad_value;
+    void* grad_loc;
+    void* grad_attn;
+    cape_msda_dims d;
+    int value_dtype;
+    int aux_dtype;
+};
+
+// Each returns cudaGetLastError() after the launch and bumps the launch counter.
+cudaError_t launch_forward(const FwdArgs& a, cudaStream_t stream);
+cudaError_t launch_backward(const BwdArgs& a, cudaStream_t stream);
+
+void count_launch();
+
+}  // namespace cape

@@ -1,0 +1,118 @@
+"""Episode-level data parallelism (one process per GPU, ``torch.distributed``; NCCL on B200, gloo in CPU tests).
+
+The MSDeformAttn path has no cross-sample term: episodes are sharded across ranks and the op itself
+needs no collective.  The only exchange in training is one gradient all-reduce per optimizer step, which the
+reference never had (its ``util/misc.py:341-377`` bootstrap is never called).  ``FlatGradAllreduce`` does it over a
+single flat bucket with fixed slots, so parameters that never receive a gradient (38 tensors in ``CAPEModel``,
+SURVEY.md §5) contribute zeros instead of breaking the collective the way stock DDP does without
+``find_unused_parameters``.
+"""
+from __future__ import annotations
+
+import os
+from typing import Iterable, List, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend: str | None = None):
+    """Initialise the default process group from RANK / WORLD_SIZE / LOCAL_RANK / MASTER_* (torchrun's contract).
+    Returns (rank, world_size, local_rank).  Single-process runs (no WORLD_SIZE) return (0, 1, 0) without a group."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", str(rank)))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group(backend, rank=rank, world_size=world,
+                                    device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group(backend, rank=rank, world_size=world)
+    return rank, world, local_rank
+
+
+def world_size() -> int:
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def shard_episodes(n_episodes: int, rank: int, world: int) -> List[int]:
+    """Episodes owned by ``rank``: ``rank, rank + world, ...`` (round robin, so ragged tails spread evenly)."""
+    if not 0 <= rank < world:
+        raise ValueError(f"rank {rank} outside world of {world}")
+    return list(range(rank, n_episodes, world))
+
+
+def max_over_ranks(value: float, device="cpu") -> float:
+    """The slowest rank's time — how every multi-GPU number here is reported."""
+    if world_size() == 1:
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(value: float, device="cpu") -> float:
+    if world_size() == 1:
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def barrier(device=None):
+    if world_size() > 1:
+        if device is not None and torch.device(device).type == "cuda":
+            dist.barrier(device_ids=[torch.device(device).index])
+        else:
+            dist.barrier()
+
+
+class FlatGradAllreduce:
+    """One all-reduce (sum, then / world) of every trainable parameter's gradient through a flat fp32 bucket.
+
+    Slots are fixed at construction from ``params`` order, so every rank reduces the same layout whether or not a
+    given parameter produced a gradient this step (``grad is None`` -> zeros in, and the averaged slot is written
+    back only if some rank had a gradient, mirroring what a single-process run would leave as ``None``).
+    """
+
+    def __init__(self, params: Iterable[torch.nn.Parameter]):
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        self.offsets: List[int] = []
+        total = 0
+        for p in self.params:
+            self.offsets.append(total)
+            total += p.numel()
+        self.numel = total
+        device = self.params[0].device if self.params else torch.device("cpu")
+        self.flat = torch.zeros(total + len(self.params), dtype=torch.float32, device=device)
+
+    def __call__(self) -> None:
+        world = world_size()
+        n = self.numel
+        flags = self.flat[n:]
+        self.flat.zero_()
+        for i, (p, off) in enumerate(zip(self.params, self.offsets)):
+            if p.grad is not None:
+                self.flat[off:off + p.numel()].copy_(p.grad.reshape(-1))
+                flags[i] = 1.0
+        if world > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            self.flat[:n].div_(world)
+        has_grad = flags.tolist()
+        for i, (p, off) in enumerate(zip(self.params, self.offsets)):
+            if has_grad[i] > 0:
+                g = self.flat[off:off + p.numel()].view_as(p).to(p.dtype)
+                if p.grad is None:
+                    p.grad = g.clone()
+                else:
+                    p.grad.copy_(g)
+
+
+def shard_sizes(total: int, world: int) -> Sequence[int]:
+    """Per-rank item counts of a round-robin shard of ``total`` items."""
+    return [len(range(r, total, world)) for r in range(world)]

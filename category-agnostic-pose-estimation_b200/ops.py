@@ -1,0 +1,181 @@
+"""torch.library registration of the MSDeformAttn ops (namespace ``cape``).
+
+    cape::ms_deform_attn(value, spatial_shapes, level_start_index, sampling_locations, attention_weights) -> out
+    cape::ms_deform_attn_backward(grad_out, value, spatial_shapes, level_start_index, sampling_locations,
+                                  attention_weights) -> (grad_value, grad_sampling_loc, grad_attn_weight)
+    cape::ms_deform_attn_decode(value_cache, spatial_shapes, level_start_index, reference_points,
+                                sampling_offsets, attention_logits) -> out
+
+The argument order is upstream Deformable-DETR's ``MSDeformAttnFunction`` (what the reference's vestigial
+``im2col_step`` at ``/root/reference/models/deformable_transformer.py:51`` was for); semantics are those of
+``ms_deform_attn_core_pytorch`` (``:115-141``).  CUDA only: the ops are registered for the CUDA dispatch key alone,
+so CPU tensors raise ``NotImplementedError`` from the dispatcher, and a missing shared library raises
+``CapeLibraryError`` — there is no fallback path.
+
+Host work per call: one ctypes call on the current torch stream.  No device synchronisation (``spatial_shapes`` and
+``level_start_index`` are read on the device, unlike the reference which iterates the CUDA tensor in Python,
+``:130,133``).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Tuple
+
+import torch
+
+from . import _lib
+
+_DTYPE_CODE = {torch.float32: _lib.DTYPE_F32, torch.bfloat16: _lib.DTYPE_BF16, torch.float16: _lib.DTYPE_F16}
+
+
+def _dims(value, loc) -> "_lib.Dims":
+    n, s, m, d = value.shape
+    lq, l, p = loc.shape[1], loc.shape[3], loc.shape[4]
+    return _lib.Dims(n, s, m, d, lq, l, p)
+
+
+def _check_shapes(value, spatial_shapes, level_start_index, loc, attn):
+    if value.dim() != 4:
+        raise ValueError(f"value must be (N, S, M, D), got {tuple(value.shape)}")
+    if loc.dim() != 6 or loc.shape[-1] != 2:
+        raise ValueError(f"sampling_locations must be (N, Lq, M, L, P, 2), got {tuple(loc.shape)}")
+    n, _, m, _ = value.shape
+    if loc.shape[0] != n or loc.shape[2] != m:
+        raise ValueError(f"sampling_locations {tuple(loc.shape)} does not match value {tuple(value.shape)}")
+    if tuple(attn.shape) != tuple(loc.shape[:5]):
+        raise ValueError(f"attention_weights must be {tuple(loc.shape[:5])}, got {tuple(attn.shape)}")
+    l = loc.shape[3]
+    if tuple(spatial_shapes.shape) != (l, 2) or tuple(level_start_index.shape) != (l,):
+        raise ValueError(f"spatial_shapes must be ({l}, 2) and level_start_index ({l},), got "
+                         f"{tuple(spatial_shapes.shape)} and {tuple(level_start_index.shape)}")
+
+
+def _meta(t: torch.Tensor, device) -> torch.Tensor:
+    """int64, contiguous, on the op's device (spatial_shapes / level_start_index)."""
+    if t.dtype != torch.int64 or t.device != device or not t.is_contiguous():
+        t = t.to(device=device, dtype=torch.int64, non_blocking=True).contiguous()
+    return t
+
+
+def _aux(loc, attn, value_dtype):
+    """The kernels take loc/attn either both fp32 or both in the value dtype."""
+    if loc.dtype == attn.dtype and (loc.dtype == torch.float32 or loc.dtype == value_dtype):
+        return loc.contiguous(), attn.contiguous()
+    return loc.float().contiguous(), attn.float().contiguous()
+
+
+def _ptr(t) -> ctypes.c_void_p:
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+@torch.library.custom_op("cape::ms_deform_attn", mutates_args=(), device_types="cuda")
+def ms_deform_attn(value: torch.Tensor, spatial_shapes: torch.Tensor, level_start_index: torch.Tensor,
+                   sampling_locations: torch.Tensor, attention_weights: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    _check_shapes(value, spatial_shapes, level_start_index, sampling_locations, attention_weights)
+    if value.dtype not in _DTYPE_CODE:
+        raise TypeError(f"unsupported value dtype {value.dtype}")
+    value = value.contiguous()
+    loc, attn = _aux(sampling_locations, attention_weights, value.dtype)
+    shapes = _meta(spatial_shapes, value.device)
+    starts = _meta(level_start_index, value.device)
+    dims = _dims(value, loc)
+    out = torch.empty((dims.N, dims.Lq, dims.M * dims.D), dtype=value.dtype, device=value.device)
+    with torch.cuda.device(value.device):
+        rc = lib.cape_msda_forward(_ptr(value), _ptr(shapes), _ptr(starts), _ptr(loc), _ptr(attn), _ptr(out),
+                                   ctypes.byref(dims), _DTYPE_CODE[value.dtype], _DTYPE_CODE[loc.dtype],
+                                   _stream(value.device))
+    _lib.check(rc, "cape_msda_forward")
+    return out
+
+
+@ms_deform_attn.register_fake
+def _(value, spatial_shapes, level_start_index, sampling_locations, attention_weights):
+    n, _, m, d = value.shape
+    return value.new_empty((n, sampling_locations.shape[1], m * d))
+
+
+@torch.library.custom_op("cape::ms_deform_attn_backward", mutates_args=(), device_types="cuda")
+def ms_deform_attn_backward(grad_out: torch.Tensor, value: torch.Tensor, spatial_shapes: torch.Tensor,
+                            level_start_index: torch.Tensor, sampling_locations: torch.Tensor,
+                            attention_weights: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    lib = _lib.load()
+    _check_shapes(value, spatial_shapes, level_start_index, sampling_locations, attention_weights)
+    value = value.contiguous()
+    loc, attn = _aux(sampling_locations, attention_weights, value.dtype)
+    shapes = _meta(spatial_shapes, value.device)
+    starts = _meta(level_start_index, value.device)
+    dims = _dims(value, loc)
+    grad_out = grad_out.to(value.dtype).contiguous()
+    grad_value = torch.empty(value.shape, dtype=torch.float32, device=value.device)   # zeroed by the library
+    grad_loc = torch.empty_like(loc)
+    grad_attn = torch.empty_like(attn)
+    with torch.cuda.device(value.device):
+        rc = lib.cape_msda_backward(_ptr(grad_out), _ptr(value), _ptr(shapes), _ptr(starts), _ptr(loc), _ptr(attn),
+                                    _ptr(grad_value), _ptr(grad_loc), _ptr(grad_attn), ctypes.byref(dims),
+                                    _DTYPE_CODE[value.dtype], _DTYPE_CODE[loc.dtype], 1, _stream(value.device))
+    _lib.check(rc, "cape_msda_backward")
+    return (grad_value.to(value.dtype), grad_loc.to(sampling_locations.dtype), grad_attn.to(attention_weights.dtype))
+
+
+@ms_deform_attn_backward.register_fake
+def _(grad_out, value, spatial_shapes, level_start_index, sampling_locations, attention_weights):
+    return (torch.empty_like(value), torch.empty_like(sampling_locations), torch.empty_like(attention_weights))
+
+
+def _setup_context(ctx, inputs, output):
+    value, spatial_shapes, level_start_index, loc, attn = inputs
+    ctx.save_for_backward(value, spatial_shapes, level_start_index, loc, attn)
+
+
+def _backward(ctx, grad_out):
+    value, spatial_shapes, level_start_index, loc, attn = ctx.saved_tensors
+    gv, gl, ga = torch.ops.cape.ms_deform_attn_backward(grad_out, value, spatial_shapes, level_start_index, loc, attn)
+    return gv, None, None, gl, ga
+
+
+ms_deform_attn.register_autograd(_backward, setup_context=_setup_context)
+
+# The reference runs this path in fp32 under autocast (grid_sampler is on autocast's fp32 list):
+# same policy here, so AMP training sees identical dtypes at the seam.
+torch.library.register_autocast("cape::ms_deform_attn", "cuda", torch.float32)
+
+
+@torch.library.custom_op("cape::ms_deform_attn_decode", mutates_args=(), device_types="cuda")
+def ms_deform_attn_decode(value_cache: torch.Tensor, spatial_shapes: torch.Tensor, level_start_index: torch.Tensor,
+                          reference_points: torch.Tensor, sampling_offsets: torch.Tensor,
+                          attention_logits: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    if value_cache.dim() != 4 or sampling_offsets.dim() != 6 or sampling_offsets.shape[-1] != 2:
+        raise ValueError("value_cache must be (B,S,M,D) and sampling_offsets (B,k,M,L,P,2)")
+    b, k, m, l, p, _ = sampling_offsets.shape
+    if tuple(reference_points.shape) != (b, k, l, 2):
+        raise ValueError(f"reference_points must be {(b, k, l, 2)}, got {tuple(reference_points.shape)}")
+    if attention_logits.numel() != b * k * m * l * p:
+        raise ValueError("attention_logits must have B*k*M*L*P elements")
+    if value_cache.dtype not in _DTYPE_CODE:
+        raise TypeError(f"unsupported value dtype {value_cache.dtype}")
+    value_cache = value_cache.contiguous()
+    ref = reference_points.float().contiguous()
+    off = sampling_offsets.float().contiguous()
+    logits = attention_logits.float().contiguous()
+    shapes = _meta(spatial_shapes, value_cache.device)
+    starts = _meta(level_start_index, value_cache.device)
+    dims = _lib.Dims(b, value_cache.shape[1], m, value_cache.shape[3], k, l, p)
+    out = torch.empty((b, k, m * value_cache.shape[3]), dtype=value_cache.dtype, device=value_cache.device)
+    with torch.cuda.device(value_cache.device):
+        rc = lib.cape_msda_decode(_ptr(value_cache), _ptr(shapes), _ptr(starts), _ptr(ref), _ptr(off), _ptr(logits),
+                                  _ptr(out), ctypes.byref(dims), _DTYPE_CODE[value_cache.dtype],
+                                  _stream(value_cache.device))
+    _lib.check(rc, "cape_msda_decode")
+    return out
+
+
+@ms_deform_attn_decode.register_fake
+def _(value_cache, spatial_shapes, level_start_index, reference_points, sampling_offsets, attention_logits):
+    b, k = sampling_offsets.shape[:2]
+    return value_cache.new_empty((b, k, value_cache.shape[2] * value_cache.shape[3]))

@@ -1,0 +1,135 @@
+/*
+ * cape_msda.h — C ABI of libcape_msda.so: multi-scale deformable attention for NVIDIA B200 (sm_100a).
+ *
+ * The reference (nkkrnkl/category-agnostic-pose-estimation) has no native code and no FFI; its seam for
+ * this path is the Python call
+ *     output = ms_deform_attn_core_pytorch(value, input_spatial_shapes, sampling_locations, attention_weights)
+ * at models/deformable_transformer.py:112 (function body :115-141), reached from MSDeformAttn.forward
+ * (:76-114).  The entry points below are what a ctypes binding on that seam calls; argument order mirrors
+ * upstream Deformable-DETR's MSDeformAttnFunction
+ *     (value, spatial_shapes, level_start_index, sampling_locations, attention_weights).
+ * INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions
+ *   - Every pointer named *_dev / value / loc / attn / out / grad_* is DEVICE memory on the current CUDA device,
+ *     C-contiguous, 16-byte aligned.  The caller owns every buffer (inputs, outputs, workspaces); the library
+ *     never allocates, frees or retains a pointer beyond the call.
+ *   - All calls are asynchronous: work is enqueued on `stream` (a cudaStream_t / CUstream; NULL = legacy default
+ *     stream); nothing synchronises the device.  Re-entrant and thread-safe (autograd calls backward from its own
+ *     worker thread).
+ *   - Return value: 0 on success; > 0 a cudaError_t; < 0 a CAPE_ERR_* code.  cape_last_error() returns a
+ *     thread-local message for the last failing call on the calling thread.
+ *   - There is no CPU implementation: host pointers passed where device pointers are expected are rejected with
+ *     CAPE_ERR_NOT_DEVICE_PTR.
+ *
+ * Layouts (reference shapes, models/deformable_transformer.py:76-141)
+ *   value               (N, S, M, D)           S = sum_l H_l*W_l; level l is rows start_l .. start_l + H_l*W_l
+ *   spatial_shapes      (L, 2) int64           rows (H_l, W_l)
+ *   level_start_index   (L,)   int64
+ *   sampling_locations  (N, Lq, M, L, P, 2)    last dim (x, y), normalised to [0,1], unclamped
+ *   attention_weights   (N, Lq, M, L, P)
+ *   output              (N, Lq, M*D)
+ */
+#ifndef CAPE_MSDA_H_
+#define CAPE_MSDA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define CAPE_API __attribute__((visibility("default")))
+#else
+#define CAPE_API
+#endif
+
+#define CAPE_ABI_VERSION 1
+
+/* element types */
+#define CAPE_DTYPE_F32 0
+#define CAPE_DTYPE_BF16 1
+#define CAPE_DTYPE_F16 2
+
+/* library error codes (negative; positive values are cudaError_t) */
+#define CAPE_ERR_BAD_DIMS (-1)        /* a dimension is <0, L>8, P>8, D not a multiple of 4 or >256, N*S*M*D overflow */
+#define CAPE_ERR_BAD_DTYPE (-2)       /* unknown or unsupported dtype combination */
+#define CAPE_ERR_NULL_PTR (-3)        /* a required pointer is NULL */
+#define CAPE_ERR_MISALIGNED (-4)      /* a tensor base pointer is not 16-byte aligned */
+#define CAPE_ERR_NOT_DEVICE_PTR (-5)  /* a tensor pointer is not device-accessible memory */
+#define CAPE_ERR_WORKSPACE (-6)       /* workspace too small */
+
+/* Problem dimensions, shared by every entry point. */
+typedef struct cape_msda_dims {
+    int32_t N;   /* batch (episodes x queries per episode)        */
+    int32_t S;   /* value rows per batch element = sum_l H_l*W_l  */
+    int32_t M;   /* heads                                         */
+    int32_t D;   /* channels per head (32 in CAPE)                */
+    int32_t Lq;  /* queries                                       */
+    int32_t L;   /* levels  (<= 8)                                */
+    int32_t P;   /* points per level (<= 8)                       */
+} cape_msda_dims;
+
+CAPE_API int cape_abi_version(void);
+CAPE_API const char* cape_last_error(void);
+
+/*
+ * Forward.  Replaces ms_deform_attn_core_pytorch (models/deformable_transformer.py:115-141).
+ *   value_dtype : CAPE_DTYPE_* of value and out.
+ *   aux_dtype   : CAPE_DTYPE_* of sampling_locations and attention_weights (F32, or the same as value_dtype).
+ */
+CAPE_API int cape_msda_forward(const void* value, const int64_t* spatial_shapes_dev, const int64_t* level_start_index_dev,
+                      const void* sampling_locations, const void* attention_weights, void* out,
+                      const cape_msda_dims* dims, int value_dtype, int aux_dtype, void* stream);
+
+/*
+ * Backward (what autograd derives from :129-141 through grid_sampler_2d_backward).
+ *   grad_out          (N, Lq, M*D)   value_dtype
+ *   grad_value        (N, S, M, D)   ALWAYS fp32, accumulated with atomics: the caller zero-fills it first
+ *                                    (or passes zero_grad_value = 1 to have the library enqueue the memset).
+ *   grad_loc          (N, Lq, M, L, P, 2)   aux_dtype   fully overwritten
+ *   grad_attn         (N, Lq, M, L, P)      aux_dtype   fully overwritten
+ */
+CAPE_API int cape_msda_backward(const void* grad_out, const void* value, const int64_t* spatial_shapes_dev,
+                       const int64_t* level_start_index_dev, const void* sampling_locations,
+                       const void* attention_weights, float* grad_value, void* grad_loc, void* grad_attn,
+                       const cape_msda_dims* dims, int value_dtype, int aux_dtype, int zero_grad_value,
+                       void* stream);
+
+/*
+ * Incremental decode: the prologue of MSDeformAttn.forward fused with the core, on a cached projected value
+ * (the role of the reference's dead VCache, models/kv_cache.py:37-70; call site deformable_transformer_v2.py:360-363).
+ *   value_cache        (B, S, M, D)      value_dtype — value_proj(memory), written once per sequence
+ *   reference_points   (B, k, L, 2)      fp32        — deformable_transformer.py:102-105 (2-d branch)
+ *   sampling_offsets   (B, k, M, L, P, 2) fp32       — raw output of the sampling_offsets Linear (:99)
+ *   attention_logits   (B, k, M, L*P)    fp32        — raw output of the attention_weights Linear (:100), pre-softmax
+ *   out                (B, k, M*D)       value_dtype
+ * dims->N = B, dims->Lq = k (the newly appended tokens only).
+ */
+CAPE_API int cape_msda_decode(const void* value_cache, const int64_t* spatial_shapes_dev, const int64_t* level_start_index_dev,
+                     const float* reference_points, const float* sampling_offsets, const float* attention_logits,
+                     void* out, const cape_msda_dims* dims, int value_dtype, void* stream);
+
+/*
+ * Host-buffer round trip used for end-to-end measurement and for callers without device buffers:
+ * copies the inputs from (ideally pinned) HOST memory into the caller-provided device workspace, runs forward and,
+ * when grad_out_host != NULL, backward, and copies the results back to HOST memory — all enqueued on `stream`.
+ * fp32 only.  cape_msda_host_workspace_bytes() gives the device workspace size for `dims`.
+ */
+CAPE_API size_t cape_msda_host_workspace_bytes(const cape_msda_dims* dims, int with_backward);
+CAPE_API int cape_msda_forward_backward_host(const float* value_host, const int64_t* spatial_shapes_host,
+                                    const int64_t* level_start_index_host, const float* loc_host,
+                                    const float* attn_host, const float* grad_out_host, float* out_host,
+                                    float* grad_value_host, float* grad_loc_host, float* grad_attn_host,
+                                    const cape_msda_dims* dims, void* workspace_dev, size_t workspace_bytes,
+                                    void* stream);
+
+/* Counts kernels this library has launched since load (bench.py reports it as gpu_launches). */
+CAPE_API uint64_t cape_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAPE_MSDA_H_ */

@@ -1,0 +1,174 @@
+"""Generate tests/golden/*.npz by running the REAL reference.  Build-container only.
+
+    python -m oracle.make_golden            (needs /root/reference; the GPU box never runs this)
+
+The reference's own tests hold no vectors for MSDeformAttn, so the parity pin is
+the reference's own outputs on committed inputs: this script imports
+``/root/reference/models/deformable_transformer.py`` by file path (the ``models`` package itself
+needs pycocotools, which is absent) and records, for every case, the inputs, the forward output of
+``ms_deform_attn_core_pytorch`` (:115-141) and the autograd gradients, both from an fp32 run (what a
+user of the reference gets) and from an fp64 run (tight target for the closed-form oracles).
+One extra case records ``MSDeformAttn.forward`` (:76-114) with seeded random weights.
+"""
+from __future__ import annotations
+
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_ROOT = "/root/reference"
+OUT_DIR = os.path.join(REPO, "tests", "golden")
+
+
+def load_reference():
+    sys.path.insert(0, REF_ROOT)
+    spec = importlib.util.spec_from_file_location(
+        "ref_deformable_transformer", os.path.join(REF_ROOT, "models", "deformable_transformer.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def load_synthetic():
+    path = os.path.join(REPO, "category-agnostic-pose-estimation_b200", "synthetic.py")
+    spec = importlib.util.spec_from_file_location("cape_synthetic", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def run_reference(ref, value, shapes, loc, attn, gout, dtype):
+    v = value.to(dtype).clone().requires_grad_(True)
+    l = loc.to(dtype).clone().requires_grad_(True)
+    a = attn.to(dtype).clone().requires_grad_(True)
+    out = ref.ms_deform_attn_core_pytorch(v, shapes, l, a)
+    gv, gl, ga = torch.autograd.grad(out, (v, l, a), gout.to(dtype))
+    return out.detach(), gv, gl, ga
+
+
+def record_core_case(ref, name, inp):
+    shapes = inp["spatial_shapes"]
+    rec = {
+        "value": inp["value"].numpy(), "spatial_shapes": shapes.numpy(),
+        "level_start_index": inp["level_start_index"].numpy(),
+        "sampling_locations": inp["sampling_locations"].numpy(),
+        "attention_weights": inp["attention_weights"].numpy(),
+        "grad_output": inp["grad_output"].numpy(),
+    }
+    for tag, dt in (("32", torch.float32), ("64", torch.float64)):
+        out, gv, gl, ga = run_reference(ref, inp["value"], shapes, inp["sampling_locations"],
+                                        inp["attention_weights"], inp["grad_output"], dt)
+        rec["out" + tag] = out.numpy()
+        rec["grad_value" + tag] = gv.numpy()
+        rec["grad_loc" + tag] = gl.numpy()
+        rec["grad_attn" + tag] = ga.numpy()
+    path = os.path.join(OUT_DIR, name + ".npz")
+    np.savez_compressed(path, **rec)
+    print(f"{name}: {os.path.getsize(path) / 1024:.1f} KiB")
+
+
+def edge_case_inputs(syn):
+    """Hand-placed locations: pixel centres, cell borders, the exact -1 / W pixel-coordinate ends,
+    fully out of bounds, plus zero-weighted samples."""
+    shapes = ((6, 8), (3, 4), (2, 2), (1, 2))
+    base = syn.make_inputs(1, 24, shapes, dist="uniform", seed=11)
+    loc = base["sampling_locations"]
+    L = len(shapes)
+    specials = []
+    for h, w in shapes:
+        specials.append([
+            (0.5 / w, 0.5 / h),            # centre of pixel (0,0): x = 0 exactly
+            ((w - 0.5) / w, (h - 0.5) / h),  # centre of the last pixel
+            (1.0 / w, 1.0 / h),            # cell border: x = 0.5
+            (0.0, 0.0),                    # image corner: x = -0.5
+            (1.0, 1.0),                    # x = W - 0.5
+            (-0.5 / w, -0.5 / h),          # x = -1 exactly (weight 0, gradient not 0)
+            (1.0 + 0.5 / w, 1.0 + 0.5 / h),  # x = W exactly
+            (-1.0, 0.3), (0.4, 2.0), (-3.0, -3.0), (5.0, 5.0),   # far outside
+            (0.5, -0.25 / h), (-0.25 / w, 0.5), (0.5, 1.0 + 0.25 / h), (1.0 + 0.25 / w, 0.5),
+            (0.5, 0.5),
+        ])
+    for q in range(16):
+        for l in range(L):
+            x, y = specials[l][q]
+            loc[0, q, :, l, :, 0] = x
+            loc[0, q, :, l, :, 1] = y
+    # queries 16..19: first two levels weighted zero, 20..23: only point 0 carries weight
+    attn = base["attention_weights"]
+    attn[0, 16:20, :, :2] = 0.0
+    attn[0, 20:24, :, :, 1:] = 0.0
+    base["sampling_locations"] = loc.contiguous()
+    base["attention_weights"] = attn.contiguous()
+    return base
+
+
+def record_module_case(ref, syn):
+    torch.manual_seed(1234)
+    d_model, n_levels, n_heads, n_points = 64, 4, 2, 4
+    shapes = ((6, 8), (3, 4), (2, 2), (1, 2))
+    s = sum(h * w for h, w in shapes)
+    mod = ref.MSDeformAttn(d_model, n_levels, n_heads, n_points)
+    with torch.no_grad():                     # the zero-initialised projections would hide bugs
+        for p in mod.parameters():
+            p.add_(torch.randn_like(p) * 0.1)
+    n, lq = 2, 9
+    query = torch.randn(n, lq, d_model)
+    src = torch.randn(n, s, d_model)
+    refpts = torch.rand(n, lq, n_levels, 2)
+    mask = torch.zeros(n, s, dtype=torch.bool)
+    mask[1, -5:] = True
+    shapes_t = torch.tensor(shapes, dtype=torch.int64)
+    starts_t = torch.tensor(syn.level_start_index(shapes), dtype=torch.int64)
+    rec = {"query": query.numpy(), "input_flatten": src.numpy(), "reference_points": refpts.numpy(),
+           "padding_mask": mask.numpy(), "spatial_shapes": shapes_t.numpy(),
+           "level_start_index": starts_t.numpy(),
+           "d_model": d_model, "n_levels": n_levels, "n_heads": n_heads, "n_points": n_points}
+    for k, v in mod.state_dict().items():
+        rec["param." + k] = v.numpy()
+    q = query.clone().requires_grad_(True)
+    x = src.clone().requires_grad_(True)
+    out = mod(q, refpts, x, shapes_t, starts_t, mask)
+    gout = torch.randn_like(out)
+    params = list(mod.parameters())
+    grads = torch.autograd.grad(out, [q, x] + params, gout)
+    rec["out"] = out.detach().numpy()
+    rec["grad_output"] = gout.numpy()
+    rec["grad_query"] = grads[0].numpy()
+    rec["grad_input_flatten"] = grads[1].numpy()
+    for (k, _), gval in zip(mod.named_parameters(), grads[2:]):
+        rec["grad_param." + k] = gval.numpy()
+    # 4-d reference points branch (:106-108)
+    ref4 = torch.cat([refpts, torch.rand(n, lq, n_levels, 2) * 0.3 + 0.05], -1)
+    rec["reference_points4"] = ref4.numpy()
+    rec["out_ref4"] = mod(query, ref4, src, shapes_t, starts_t, None).detach().numpy()
+    path = os.path.join(OUT_DIR, "module_forward.npz")
+    np.savez_compressed(path, **rec)
+    print(f"module_forward: {os.path.getsize(path) / 1024:.1f} KiB")
+
+
+def main():
+    os.makedirs(OUT_DIR, exist_ok=True)
+    ref = load_reference()
+    syn = load_synthetic()
+    torch.set_num_threads(1)      # fixed summation order inside ATen
+    record_core_case(ref, "core_uniform", syn.make_inputs(
+        2, 37, ((8, 8), (4, 4), (2, 2), (1, 1)), dist="uniform", seed=1))
+    enc_shapes = ((6, 8), (3, 4), (2, 2), (1, 2))
+    record_core_case(ref, "core_encoder_nonsquare", syn.make_inputs(
+        1, sum(h * w for h, w in enc_shapes), enc_shapes, dist="encoder", seed=2))
+    record_core_case(ref, "core_edges", edge_case_inputs(syn))
+    record_core_case(ref, "core_generic_dims", syn.make_inputs(
+        2, 11, ((5, 7), (3, 2)), n_heads=3, head_dim=16, n_points=3, dist="uniform", seed=3))
+    record_core_case(ref, "core_lq1", syn.make_inputs(
+        3, 1, ((8, 8), (4, 4), (2, 2), (1, 1)), dist="uniform", seed=4))
+    record_core_case(ref, "core_d64_p8", syn.make_inputs(
+        1, 5, ((4, 4), (2, 2), (1, 1)), n_heads=2, head_dim=64, n_points=8, dist="uniform", seed=5))
+    record_module_case(ref, syn)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,123 @@
+"""Host-side mirror of the reference interface: module layout, error behaviour, shape inference, sharding maths."""
+import math
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import cape_b200
+from cape_b200 import synthetic
+from tests.conftest import GOLDEN
+
+
+def test_state_dict_layout_matches_reference_module():
+    g = np.load(os.path.join(GOLDEN, "module_forward.npz"))
+    ref = {k[len("param."):]: g[k].shape for k in g.files if k.startswith("param.")}
+    mod = cape_b200.MSDeformAttn(int(g["d_model"]), int(g["n_levels"]), int(g["n_heads"]), int(g["n_points"]))
+    mine = {k: tuple(v.shape) for k, v in mod.state_dict().items()}
+    assert mine == {k: tuple(v) for k, v in ref.items()}
+    assert [n for n, _ in mod.named_buffers()] == []          # no persistent buffers under new names
+    # CAPE configuration: 230,272 parameters per module
+    assert sum(p.numel() for p in cape_b200.MSDeformAttn(256, 4, 8, 4).parameters()) == 230272
+
+
+def test_initialisation_follows_reference_reset_parameters():
+    torch.manual_seed(0)
+    m = cape_b200.MSDeformAttn(256, 4, 8, 4)
+    assert float(m.sampling_offsets.weight.detach().abs().max()) == 0.0
+    assert float(m.attention_weights.weight.abs().max()) == 0.0 and float(m.attention_weights.bias.abs().max()) == 0.0
+    want = synthetic.head_direction_offsets(8, 4, 4).reshape(-1)
+    assert torch.allclose(m.sampling_offsets.bias, want)
+    assert float(m.value_proj.bias.abs().max()) == 0.0 and float(m.output_proj.bias.abs().max()) == 0.0
+    bound = math.sqrt(6.0 / (256 + 256))
+    assert float(m.value_proj.weight.abs().max()) <= bound + 1e-6
+
+
+def test_constructor_and_forward_errors():
+    with pytest.raises(ValueError, match="divisible"):
+        cape_b200.MSDeformAttn(100, 4, 8, 4)
+    m = cape_b200.MSDeformAttn(32, 2, 2, 2)
+    q = torch.zeros(1, 3, 32)
+    src = torch.zeros(1, 8, 32)
+    shapes = torch.tensor([[2, 2], [2, 2]])
+    starts = torch.tensor([0, 4])
+    with pytest.raises(ValueError, match="2 or 4"):
+        m(q, torch.zeros(1, 3, 2, 3), src, shapes, starts)
+    with pytest.raises(AssertionError):
+        m(q, torch.zeros(1, 3, 2, 2), torch.zeros(1, 9, 32), shapes, starts)
+
+
+def test_cpu_tensors_are_rejected_not_computed():
+    inp = synthetic.make_inputs(1, 2, ((2, 2),), n_heads=1, head_dim=4, n_points=1)
+    with pytest.raises(NotImplementedError):
+        cape_b200.ms_deform_attn_core_pytorch(inp["value"], inp["spatial_shapes"], inp["sampling_locations"],
+                                              inp["attention_weights"])
+
+
+def test_fake_tensor_shape_inference():
+    v = torch.empty(3, 85, 8, 32, device="meta")
+    loc = torch.empty(3, 7, 8, 4, 4, 2, device="meta")
+    attn = torch.empty(3, 7, 8, 4, 4, device="meta")
+    shapes = torch.empty(4, 2, dtype=torch.int64, device="meta")
+    starts = torch.empty(4, dtype=torch.int64, device="meta")
+    out = torch.ops.cape.ms_deform_attn(v, shapes, starts, loc, attn)
+    assert out.shape == (3, 7, 256) and out.dtype == v.dtype
+    gv, gl, ga = torch.ops.cape.ms_deform_attn_backward(out, v, shapes, starts, loc, attn)
+    assert gv.shape == v.shape and gl.shape == loc.shape and ga.shape == attn.shape
+    dec = torch.ops.cape.ms_deform_attn_decode(v, shapes, starts, torch.empty(3, 1, 4, 2, device="meta"),
+                                               torch.empty(3, 1, 8, 4, 4, 2, device="meta"),
+                                               torch.empty(3, 1, 8, 16, device="meta"))
+    assert dec.shape == (3, 1, 256)
+
+
+def test_level_start_index_helpers():
+    shapes = torch.tensor(synthetic.CAPE_PYRAMID)
+    assert cape_b200.level_start_index_from_shapes(shapes).tolist() == [0, 4096, 5120, 5376]
+    assert synthetic.level_start_index(synthetic.CAPE_PYRAMID) == [0, 4096, 5120, 5376]
+    assert synthetic.level_start_index(synthetic.CAPE_PYRAMID_512) == [0, 1024, 1280, 1344]
+
+
+def test_algorithmic_bytes_match_baseline_table():
+    # BASELINE.md §3 worked values (fp32)
+    for (n, lq), (fwd_mb, bwd_mb) in {(2, 5440): (39.0, 66.8), (4, 5440): (78.0, 133.7), (20, 5440): (389.9, 668.5),
+                                      (2, 1000): (16.3, 30.5), (20, 200): (121.7, 239.2)}.items():
+        a_fwd, a_bwd = synthetic.algorithmic_bytes(n, lq, 5440)
+        assert abs(a_fwd / 1e6 - fwd_mb) < 0.06 and abs(a_bwd / 1e6 - bwd_mb) < 0.06
+
+
+def test_synthetic_inputs_are_deterministic_and_well_formed():
+    a = synthetic.make_inputs(2, 50, seed=3)
+    b = synthetic.make_inputs(2, 50, seed=3)
+    for k in a:
+        assert torch.equal(a[k], b[k])
+    assert a["value"].shape == (2, 5440, 8, 32) and a["sampling_locations"].shape == (2, 50, 8, 4, 4, 2)
+    assert torch.allclose(a["attention_weights"].flatten(3).sum(-1), torch.ones(2, 50, 8), atol=1e-5)
+    loc = a["sampling_locations"]
+    assert -1.5 < float(loc.min()) < 0.0 and 1.0 < float(loc.max()) < 2.5      # some corners out of bounds
+
+
+def test_patch_reference_rebinds_the_seam_and_restores_it():
+    fake = types.ModuleType("fake_models.deformable_transformer")
+    original = lambda *a: "reference"
+    fake.ms_deform_attn_core_pytorch = original
+    fake.MSDeformAttn = object
+    cape_b200.patch_reference(fake, swap_module_class=True)
+    assert fake.ms_deform_attn_core_pytorch is cape_b200.ms_deform_attn_core_pytorch
+    assert fake.MSDeformAttn is cape_b200.MSDeformAttn
+    cape_b200.unpatch_reference(fake)
+    assert fake.ms_deform_attn_core_pytorch is original and fake.MSDeformAttn is object
+
+
+def test_value_cache_protocol_without_buffers():
+    m = cape_b200.MSDeformAttn(32, 1, 1, 1)
+    m.cache = cape_b200.ValueCache()
+    assert "cache" not in "".join(m.state_dict().keys())
+    v = torch.zeros(2, 4, 1, 32)
+    assert m._cache_load(2, 4) is None           # nothing stored by this module yet
+    m._cache_store(v)
+    assert m._cache_load(2, 4) is v
+    assert m._cache_load(3, 4) is None           # batch changed: do not trust the cache
+    m.cache = cape_b200.ValueCache()             # _setup_caches attaches a fresh holder every forward_inference
+    assert m._cache_load(2, 4) is None
