@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py — MSDeformAttn fwd+bwd achieved HBM GB/s on B200 (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload (config.workload): the named training shape of BASELINE.md — one encoder MSDeformAttn call for a
+micro-batch of 10 episodes x 2 queries: N=20, Lq=S=5440 (pyramid 64/32/16/8), 8 heads x 32 channels, 4 levels,
+4 points, fp32, "encoder-like" sampling locations.  A step = forward + backward (grad_value memset
+included).  Every rank runs the same per-GPU workload on its own episodes (weak scaling, no collective on the op path).
+
+value   = sum over ranks of algorithmic bytes (A_fwd + A_bwd, each tensor once) x K / max-over-ranks device time,
+          inputs resident in HBM, CUDA events on the launching stream.
+e2e     = same metric through the C-ABI host entry point (cape_msda_forward_backward_host): pinned HOST buffers in,
+          results back on the host, copies inside the timed region.
+roofline= the dominant kernel (backward) against the measured HBM copy peak in MEASURED_PEAKS.json.
+cpu_baseline = the oracle port of the reference path (oracle/msda_torch.py: the same per-level grid_sample
+          formulation on ATen's CPU kernels) timed on this box's host cores on a bounded sample.
+--impl reference times that CPU port alone, same metric/unit/config, rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+METRIC = "msda_fwd_bwd_achieved_hbm_gbps"
+UNIT = "GB/s"
+WORKLOAD = dict(N=20, Lq=5440, S=5440, M=8, D=32, L=4, P=4)
+FALLBACK_HBM_GBS = 6650.0   # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def config_dict(world):
+    return {
+        "workload": "MSDeformAttn encoder call, CAPE training micro-batch (10 episodes x 2 queries): N=20, Lq=5440, "
+                    "S=5440 (64/32/16/8 pyramid), M=8, D=32, L=4, P=4, fp32, encoder-like locations; step = fwd + bwd",
+        "per_gpu_batch": WORKLOAD["N"], "global_batch": WORKLOAD["N"] * world,
+        "parallelism": f"dp{world} (episodes sharded, no collective on the op path)",
+        "l2": "per-step tensors total 1.06 GB (inputs 390 MB) > 126 MB L2: no flush needed between iterations",
+    }
+
+
+def measured_peak():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def recorded_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture, if any."""
+    try:
+        with open(os.path.join(REPO, "profiles", "traffic.json")) as f:
+            return json.load(f).get("bwd_dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+# ---- clocks sampling during the timed region ---------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        self.index = index
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nvml = None
+
+    def _poll_nvml(self):
+        n = self._nvml
+        while not self._stop.is_set():
+            try:
+                self.samples.append(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM))
+                try:
+                    mask = n.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:
+                    mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def _poll_smi(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                parts = [p.strip() for p in out.split(",")]
+                self.samples.append(int(parts[0]))
+                self.max_mhz = int(parts[1])
+                for name, val in zip(names, parts[2:]):
+                    if val.lower().startswith("active"):
+                        self.reasons.add(name)
+            except Exception:
+                pass
+
+    def start(self):
+        self._thread = threading.Thread(target=self._poll_nvml if self._nvml else self._poll_smi, daemon=True)
+        self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread:
+            self._thread.join(timeout=10)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ---- CPU arm (oracle port of the reference path) -----------------------------------------------------------------
+def cpu_step_fn(n, lq):
+    import torch
+    from oracle import msda_torch
+    import cape_b200
+    inp = cape_b200.synthetic.make_inputs(n, lq, dist="encoder", seed=0)
+    shapes = inp["spatial_shapes"].tolist()
+
+    def step():
+        msda_torch.msda_core_fwd_bwd(inp["value"], shapes, inp["sampling_locations"], inp["attention_weights"],
+                                     inp["grad_output"])
+    a_fwd, a_bwd = cape_b200.synthetic.algorithmic_bytes(n, lq, WORKLOAD["S"])
+    return step, a_fwd + a_bwd
+
+
+def cpu_baseline(budget_s=20.0):
+    """Bounded sample: N=4 (2 episodes x 2 queries), Lq=5440 — same pyramid, same location distribution."""
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    n, lq = 4, WORKLOAD["Lq"]
+    step, nbytes = cpu_step_fn(n, lq)
+    step()                                        # warm-up
+    times = []
+    t_start = time.perf_counter()
+    while len(times) < 5 and (time.perf_counter() - t_start < budget_s or len(times) < 2):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    best = min(times)
+    return {"value": round(nbytes / best / 1e9, 4), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"oracle/msda_torch.py (reference's grid_sample formulation on ATen CPU kernels), fp32, N={n}, "
+                      f"Lq={lq}, fwd+autograd bwd, best of {len(times)} after 1 warm-up ({best * 1e3:.0f} ms/step)"}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    # size the per-step sample so that (warmup + steps) steps end within ~150 s
+    n, lq = 2, WORKLOAD["Lq"]
+    step, nbytes = cpu_step_fn(n, lq)
+    step()
+    t0 = time.perf_counter()
+    step()
+    t1 = time.perf_counter() - t0
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    if t1 > budget:                               # shrink the query count, keep the pyramid
+        lq = max(64, int(lq * budget / t1))
+        step, nbytes = cpu_step_fn(n, lq)
+    elif t1 * 2 < budget:
+        n = 4
+        step, nbytes = cpu_step_fn(n, lq)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = nbytes * args.steps / dt / 1e9
+    sample = (f"oracle/msda_torch.py on {torch.get_num_threads()} host threads, fp32, N={n}, Lq={lq} per step "
+              f"(bounded sample of the N=20 workload)")
+    line = {"impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(world),
+            "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---- B200 arm ----------------------------------------------------------------------------------------------------
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import cape_b200
+    from cape_b200 import _lib, dist as cdist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    lib = _lib.load()
+    w = WORKLOAD
+    inp = cape_b200.synthetic.make_inputs(w["N"], w["Lq"], dist="encoder", seed=rank, device=dev)
+    value, loc, attn, gout = inp["value"], inp["sampling_locations"], inp["attention_weights"], inp["grad_output"]
+    shapes, starts = inp["spatial_shapes"], inp["level_start_index"]
+    out = torch.empty(w["N"], w["Lq"], w["M"] * w["D"], device=dev)
+    gvalue = torch.empty_like(value)
+    gloc = torch.empty_like(loc)
+    gattn = torch.empty_like(attn)
+    dims = _lib.Dims(w["N"], w["S"], w["M"], w["D"], w["Lq"], w["L"], w["P"])
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    stream = torch.cuda.current_stream(dev)
+    sp = ctypes.c_void_p(stream.cuda_stream)
+    a_fwd, a_bwd = cape_b200.synthetic.algorithmic_bytes(w["N"], w["Lq"], w["S"])
+
+    def fwd():
+        _lib.check(lib.cape_msda_forward(p(value), p(shapes), p(starts), p(loc), p(attn), p(out), ctypes.byref(dims),
+                                         0, 0, sp), "forward")
+
+    def zero():
+        gvalue.zero_()
+
+    def bwd():
+        _lib.check(lib.cape_msda_backward(p(gout), p(value), p(shapes), p(starts), p(loc), p(attn), p(gvalue), p(gloc),
+                                          p(gattn), ctypes.byref(dims), 0, 0, 0, sp), "backward")
+
+    for _ in range(max(args.warmup, 3)):
+        fwd(); zero(); bwd()
+    torch.cuda.synchronize(dev)
+
+    K = args.steps
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
+    sampler = ClockSampler(local_rank)
+    cdist.barrier(dev)
+    torch.cuda.synchronize(dev)
+    launches0 = lib.cape_launch_count()
+    sampler.start()
+    t_begin = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_begin.record(stream)
+    for i in range(K):
+        ev[i][0].record(stream)
+        fwd()
+        ev[i][1].record(stream)
+        zero()
+        ev[i][2].record(stream)
+        bwd()
+        ev[i][3].record(stream)
+    t_end.record(stream)
+    torch.cuda.synchronize(dev)
+    clocks = sampler.stop()
+    launches = lib.cape_launch_count() - launches0
+    cdist.barrier(dev)
+    total_ms = t_begin.elapsed_time(t_end)
+    fwd_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / K
+    zero_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / K
+    bwd_ms = sum(e[2].elapsed_time(e[3]) for e in ev) / K
+    slow_ms = cdist.max_over_ranks(total_ms, dev)
+
+    # ---- end to end through the host-buffer ABI: pinned host tensors in, results back on the host ----
+    e2e_steps = max(2, min(K, 5))
+    host = {k: t.cpu().pin_memory() for k, t in (("value", value), ("loc", loc), ("attn", attn), ("gout", gout))}
+    shapes_h, starts_h = shapes.cpu(), starts.cpu()
+    res = {"out": torch.empty(out.shape).pin_memory(), "gvalue": torch.empty(value.shape).pin_memory(),
+           "gloc": torch.empty(loc.shape).pin_memory(), "gattn": torch.empty(attn.shape).pin_memory()}
+    del out, gvalue, gloc, gattn
+    ws_bytes = lib.cape_msda_host_workspace_bytes(ctypes.byref(dims), 1)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+
+    def e2e_step():
+        _lib.check(lib.cape_msda_forward_backward_host(
+            p(host["value"]), p(shapes_h), p(starts_h), p(host["loc"]), p(host["attn"]), p(host["gout"]),
+            p(res["out"]), p(res["gvalue"]), p(res["gloc"]), p(res["gattn"]), ctypes.byref(dims), p(ws), ws_bytes, sp),
+            "forward_backward_host")
+    e2e_step()
+    torch.cuda.synchronize(dev)
+    cdist.barrier(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    e2e_ms = cdist.max_over_ranks(e0.elapsed_time(e1), dev)
+    h2d = sum(t.numel() * t.element_size() for t in host.values()) + shapes_h.numel() * 8 + starts_h.numel() * 8
+    d2h = sum(t.numel() * t.element_size() for t in res.values())
+    checksum = float(res["out"].double().sum())           # the result really is on the host
+
+    if rank != 0:
+        return
+    peak, peak_src = measured_peak()
+    alg = (a_fwd + a_bwd) * world
+    value_gbs = alg * K / (slow_ms * 1e-3) / 1e9
+    bwd_gbs = a_bwd / (bwd_ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": round(value_gbs, 2), "unit": UNIT, "n_gpus": world, "steps": K,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(slow_ms / K, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(world),
+        "roofline": {"bound": "hbm", "kernel": "msda_bwd_fast_kernel<float,float,4>", "achieved": round(bwd_gbs, 2),
+                     "peak": peak, "unit": "GB/s", "frac": round(bwd_gbs / peak, 4), "traffic": recorded_traffic(),
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": a_bwd,
+                     "avg_launch_ms": round(bwd_ms, 4)},
+        "kernels": {"fwd_ms": round(fwd_ms, 4), "fwd_gbs": round(a_fwd / (fwd_ms * 1e-3) / 1e9, 2),
+                    "grad_value_memset_ms": round(zero_ms, 4), "bwd_ms": round(bwd_ms, 4),
+                    "bwd_gbs": round(bwd_gbs, 2),
+                    "fwd_bwd_frac_of_peak": round((a_fwd + a_bwd) / ((fwd_ms + zero_ms + bwd_ms) * 1e-3) / 1e9 / peak, 4)},
+        "e2e": {"value": round(alg * e2e_steps / (e2e_ms * 1e-3) / 1e9, 2), "unit": UNIT,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "ms_per_step": round(e2e_ms / e2e_steps, 3), "api": "cape_msda_forward_backward_host (C ABI, pinned host buffers)",
+                "out_checksum": checksum},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline()
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29511"),
+               os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    from cape_b200 import dist as cdist
+    cdist.init_from_env()
+    try:
+        run_b200(args, rank, world, local_rank)
+    finally:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

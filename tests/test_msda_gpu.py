@@ -1,0 +1,388 @@
+"""Parity of the CUDA path (through the C ABI / torch.library ops) against the oracle and the golden fixtures.
+
+Tolerances are BASELINE.json's: forward 1e-5 relative (max|a-b| / max|b|) in fp32, 2e-2 in bf16, gradients 1e-4
+relative in fp32.  All tests need a GPU (`-m gpu`); /root/reference is never read here.
+"""
+import ctypes
+import glob
+import os
+import threading
+
+import numpy as np
+import pytest
+import torch
+
+import cape_b200
+from cape_b200 import _lib, synthetic
+from oracle import msda_c, msda_numpy
+from tests.conftest import GOLDEN, rel_err
+
+pytestmark = pytest.mark.gpu
+
+FWD_TOL_F32 = 1e-5
+GRAD_TOL_F32 = 1e-4
+FWD_TOL_BF16 = 2e-2
+
+CORE_CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "core_*.npz")))
+
+
+def _cuda(x, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    return t.to(dtype) if dtype is not None else t
+
+
+def _run_fwd_bwd(inp, dtype=torch.float32, aux_dtype=None):
+    """inp: dict of CPU torch tensors / numpy arrays.  Returns numpy (out, gv, gl, ga)."""
+    get = (lambda k: inp[k] if isinstance(inp[k], torch.Tensor) else torch.from_numpy(inp[k]))
+    aux_dtype = aux_dtype or dtype
+    v = get("value").cuda().to(dtype).requires_grad_(True)
+    loc = get("sampling_locations").cuda().to(aux_dtype).requires_grad_(True)
+    attn = get("attention_weights").cuda().to(aux_dtype).requires_grad_(True)
+    shapes = get("spatial_shapes").cuda()
+    starts = get("level_start_index").cuda()
+    out = cape_b200.ms_deform_attn(v, shapes, starts, loc, attn)
+    gv, gl, ga = torch.autograd.grad(out, (v, loc, attn), get("grad_output").cuda().to(dtype))
+    torch.cuda.synchronize()
+    return tuple(t.detach().float().cpu().numpy() for t in (out, gv, gl, ga))
+
+
+def test_library_is_loaded_and_counts_launches():
+    assert cape_b200.library_available()
+    before = cape_b200.launch_count()
+    inp = synthetic.make_inputs(1, 4, ((4, 4), (2, 2), (1, 1), (1, 1)), device="cuda")
+    cape_b200.ms_deform_attn(inp["value"], inp["spatial_shapes"], inp["level_start_index"],
+                             inp["sampling_locations"], inp["attention_weights"])
+    torch.cuda.synchronize()
+    assert cape_b200.launch_count() == before + 1
+    maps = open("/proc/self/maps").read()
+    assert "libcape_msda.so" in maps
+
+
+@pytest.mark.parametrize("case", CORE_CASES)
+def test_golden_fixtures_fp32(case):
+    """CUDA fp32 vs the reference's own fp32 outputs (fixtures made by oracle/make_golden.py)."""
+    g = np.load(os.path.join(GOLDEN, case + ".npz"))
+    out, gv, gl, ga = _run_fwd_bwd(g)
+    assert rel_err(out, g["out32"]) < FWD_TOL_F32
+    assert rel_err(gv, g["grad_value32"]) < GRAD_TOL_F32
+    assert rel_err(gl, g["grad_loc32"]) < GRAD_TOL_F32
+    assert rel_err(ga, g["grad_attn32"]) < GRAD_TOL_F32
+
+
+@pytest.mark.parametrize("dist", ["encoder", "uniform"])
+@pytest.mark.parametrize("n,lq", [(2, 5440), (1, 1000), (3, 200), (5, 1)])
+def test_cape_pyramid_fp32_vs_c_oracle(dist, n, lq):
+    inp = synthetic.make_inputs(n, lq, dist=dist, seed=n * 100 + lq)
+    a = tuple(inp[k].numpy() for k in ("value", "spatial_shapes", "level_start_index", "sampling_locations",
+                                       "attention_weights"))
+    want_out = msda_c.msda_forward(*a, dtype=np.float32)
+    want_g = msda_c.msda_backward(inp["grad_output"].numpy(), *a, dtype=np.float32)
+    out, gv, gl, ga = _run_fwd_bwd(inp)
+    assert rel_err(out, want_out) < FWD_TOL_F32
+    assert rel_err(gv, want_g[0]) < GRAD_TOL_F32
+    assert rel_err(gl, want_g[1]) < GRAD_TOL_F32
+    assert rel_err(ga, want_g[2]) < GRAD_TOL_F32
+
+
+@pytest.mark.parametrize("shapes", [synthetic.CAPE_PYRAMID_512, ((16, 12), (8, 6), (4, 3)), ((20, 20),),
+                                    ((9, 5), (4, 4))])
+def test_other_pyramids_fp32(shapes):
+    """1360-token pyramid, non-square levels, 3 / 1 / 2 levels (L < 4 fast path)."""
+    inp = synthetic.make_inputs(2, 77, shapes, dist="uniform", seed=len(shapes))
+    a = tuple(inp[k].numpy() for k in ("value", "spatial_shapes", "level_start_index", "sampling_locations",
+                                       "attention_weights"))
+    want_out = msda_c.msda_forward(*a, dtype=np.float32)
+    want_g = msda_c.msda_backward(inp["grad_output"].numpy(), *a, dtype=np.float32)
+    out, gv, gl, ga = _run_fwd_bwd(inp)
+    assert rel_err(out, want_out) < FWD_TOL_F32
+    for got, want in zip((gv, gl, ga), want_g):
+        assert rel_err(got, want) < GRAD_TOL_F32
+
+
+@pytest.mark.parametrize("m,d,l,p", [(3, 16, 2, 3), (2, 64, 3, 8), (1, 4, 1, 1), (4, 32, 5, 4), (8, 32, 4, 2),
+                                     (2, 256, 1, 2)])
+def test_generic_dims_fp32(m, d, l, p):
+    shapes = ((7, 5), (4, 3), (3, 3), (2, 2), (2, 1))[:l]
+    inp = synthetic.make_inputs(2, 19, shapes, n_heads=m, head_dim=d, n_points=p, dist="uniform", seed=m + d)
+    a = tuple(inp[k].numpy() for k in ("value", "spatial_shapes", "level_start_index", "sampling_locations",
+                                       "attention_weights"))
+    want_out = msda_c.msda_forward(*a, dtype=np.float32)
+    want_g = msda_c.msda_backward(inp["grad_output"].numpy(), *a, dtype=np.float32)
+    out, gv, gl, ga = _run_fwd_bwd(inp)
+    assert rel_err(out, want_out) < FWD_TOL_F32
+    for got, want in zip((gv, gl, ga), want_g):
+        assert rel_err(got, want) < GRAD_TOL_F32
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("aux_fp32", [True, False])
+def test_half_precision_vs_oracle_on_rounded_inputs(dtype, aux_fp32):
+    """bf16 / fp16 value: the kernel against the fp32 oracle evaluated on the SAME rounded inputs (what autocast
+    feeds the reference), tolerance 2e-2."""
+    inp = synthetic.make_inputs(2, 600, dist="encoder", seed=21)
+    aux = torch.float32 if aux_fp32 else dtype
+    rounded = dict(inp)
+    rounded["value"] = inp["value"].to(dtype).float()
+    rounded["grad_output"] = inp["grad_output"].to(dtype).float()
+    rounded["sampling_locations"] = inp["sampling_locations"].to(aux).float()
+    rounded["attention_weights"] = inp["attention_weights"].to(aux).float()
+    a = tuple(rounded[k].numpy() for k in ("value", "spatial_shapes", "level_start_index", "sampling_locations",
+                                           "attention_weights"))
+    want_out = msda_c.msda_forward(*a, dtype=np.float32)
+    want_g = msda_c.msda_backward(rounded["grad_output"].numpy(), *a, dtype=np.float32)
+    out, gv, gl, ga = _run_fwd_bwd(inp, dtype=dtype, aux_dtype=aux)
+    assert rel_err(out, want_out) < FWD_TOL_BF16
+    for got, want in zip((gv, gl, ga), want_g):
+        assert rel_err(got, want) < FWD_TOL_BF16
+
+
+def test_core_pytorch_drop_in_signature_and_list_shapes():
+    inp = synthetic.make_inputs(2, 33, ((8, 8), (4, 4), (2, 2), (1, 1)), seed=5)
+    want = msda_c.msda_forward(*(inp[k].numpy() for k in ("value", "spatial_shapes", "level_start_index",
+                                                           "sampling_locations", "attention_weights")))
+    v, loc, attn = (inp[k].cuda() for k in ("value", "sampling_locations", "attention_weights"))
+    out_t = cape_b200.ms_deform_attn_core_pytorch(v, inp["spatial_shapes"].cuda(), loc, attn)
+    out_l = cape_b200.ms_deform_attn_core_pytorch(v, [(8, 8), (4, 4), (2, 2), (1, 1)], loc, attn)
+    out_f = cape_b200.MSDeformAttnFunction.apply(v, inp["spatial_shapes"].cuda(), inp["level_start_index"].cuda(),
+                                                 loc, attn, 64)
+    assert out_t.shape == (2, 33, 256) and out_t.is_contiguous()
+    for o in (out_t, out_l, out_f):
+        assert rel_err(o.cpu().numpy(), want) < FWD_TOL_F32
+
+
+def test_non_contiguous_and_cpu_resident_metadata():
+    inp = synthetic.make_inputs(2, 21, ((8, 8), (4, 4), (2, 2), (1, 1)), seed=6)
+    want = msda_c.msda_forward(*(inp[k].numpy() for k in ("value", "spatial_shapes", "level_start_index",
+                                                           "sampling_locations", "attention_weights")))
+    v = inp["value"].cuda().permute(0, 2, 1, 3).contiguous().permute(0, 2, 1, 3)     # same values, strided view
+    assert not v.is_contiguous()
+    out = cape_b200.ms_deform_attn(v, inp["spatial_shapes"], inp["level_start_index"],   # metadata left on the CPU
+                                   inp["sampling_locations"].cuda(), inp["attention_weights"].cuda())
+    assert rel_err(out.cpu().numpy(), want) < FWD_TOL_F32
+
+
+def test_empty_and_degenerate_inputs():
+    shapes = torch.tensor([[4, 4], [2, 2], [1, 1], [1, 1]], device="cuda")
+    starts = torch.tensor([0, 16, 20, 21], device="cuda")
+    v = torch.randn(2, 22, 8, 32, device="cuda")
+    out = cape_b200.ms_deform_attn(v, shapes, starts, torch.zeros(2, 0, 8, 4, 4, 2, device="cuda"),
+                                   torch.zeros(2, 0, 8, 4, 4, device="cuda"))
+    assert out.shape == (2, 0, 256)
+    out = cape_b200.ms_deform_attn(v[:0], shapes, starts, torch.zeros(0, 3, 8, 4, 4, 2, device="cuda"),
+                                   torch.zeros(0, 3, 8, 4, 4, device="cuda"))
+    assert out.shape == (0, 3, 256)
+    # every sample far outside the map, NaN / inf locations: zeros, not a fault
+    loc = torch.full((2, 3, 8, 4, 4, 2), 7.5, device="cuda")
+    loc[0, 0] = float("inf")
+    loc[0, 1] = float("nan")
+    loc[1, 2] = -1e30
+    attn = torch.full((2, 3, 8, 4, 4), 1 / 16, device="cuda")
+    out = cape_b200.ms_deform_attn(v, shapes, starts, loc, attn)
+    torch.cuda.synchronize()
+    assert float(out.abs().max()) == 0.0
+
+
+def test_error_behaviour():
+    v = torch.randn(1, 4, 1, 4, device="cuda")
+    shapes = torch.tensor([[2, 2]], device="cuda")
+    starts = torch.tensor([0], device="cuda")
+    with pytest.raises((ValueError, RuntimeError)):
+        cape_b200.ms_deform_attn(v, shapes, starts, torch.zeros(1, 2, 1, 1, 1, 3, device="cuda"),
+                                 torch.zeros(1, 2, 1, 1, 1, device="cuda"))
+    with pytest.raises((ValueError, RuntimeError)):
+        cape_b200.ms_deform_attn(v, shapes, starts, torch.zeros(1, 2, 1, 1, 1, 2, device="cuda"),
+                                 torch.zeros(1, 2, 1, 1, 2, device="cuda"))
+    # raw ABI: host pointer where a device pointer is expected -> CAPE_ERR_NOT_DEVICE_PTR, with a message
+    lib = _lib.load()
+    host = np.zeros(64, dtype=np.float32)
+    dims = _lib.Dims(1, 4, 1, 4, 1, 1, 1)
+    hp = ctypes.c_void_p(host.ctypes.data)
+    rc = lib.cape_msda_forward(hp, ctypes.c_void_p(shapes.data_ptr()), ctypes.c_void_p(starts.data_ptr()), hp, hp, hp,
+                               ctypes.byref(dims), 0, 0, None)
+    assert rc == -5 and b"host memory" in lib.cape_last_error() or rc == -5
+    # misaligned device pointer
+    base = torch.zeros(64, device="cuda")
+    rc = lib.cape_msda_forward(ctypes.c_void_p(base.data_ptr() + 4), ctypes.c_void_p(shapes.data_ptr()),
+                               ctypes.c_void_p(starts.data_ptr()), ctypes.c_void_p(base.data_ptr()),
+                               ctypes.c_void_p(base.data_ptr()), ctypes.c_void_p(base.data_ptr()),
+                               ctypes.byref(dims), 0, 0, None)
+    assert rc == -4
+
+
+def test_decode_variant_matches_prologue_plus_core():
+    """cape::ms_deform_attn_decode == softmax + (ref + off/(W,H)) + core on the cached value
+    (deformable_transformer.py:99-105,112), for Lq = 1 (one new token) and Lq = 3."""
+    for b, k, seed in ((4, 1, 0), (2, 3, 1), (64, 1, 2)):
+        g = torch.Generator().manual_seed(seed)
+        shapes = synthetic.CAPE_PYRAMID
+        s = sum(h * w for h, w in shapes)
+        value = torch.randn(b, s, 8, 32, generator=g)
+        ref = torch.rand(b, k, 4, 2, generator=g)
+        off = torch.randn(b, k, 8, 4, 4, 2, generator=g) * 3
+        logits = torch.randn(b, k, 8, 16, generator=g)
+        want = msda_numpy.msda_decode(value.numpy(), np.array(shapes), synthetic.level_start_index(shapes),
+                                      ref.numpy(), off.numpy(), logits.numpy(), dtype=np.float64)
+        got = cape_b200.ms_deform_attn_decode(value.cuda(), torch.tensor(shapes).cuda(), None, ref.cuda(), off.cuda(),
+                                              logits.cuda())
+        assert got.shape == (b, k, 256)
+        assert rel_err(got.cpu().numpy(), want) < FWD_TOL_F32
+        got16 = cape_b200.ms_deform_attn_decode(value.cuda().bfloat16(), torch.tensor(shapes).cuda(), None, ref.cuda(),
+                                                off.cuda(), logits.cuda())
+        want16 = msda_numpy.msda_decode(value.bfloat16().float().numpy(), np.array(shapes),
+                                        synthetic.level_start_index(shapes), ref.numpy(), off.numpy(), logits.numpy())
+        assert rel_err(got16.float().cpu().numpy(), want16) < FWD_TOL_BF16
+
+
+def test_decode_generic_dims():
+    g = torch.Generator().manual_seed(3)
+    shapes = ((5, 7), (3, 2))
+    value = torch.randn(2, 41, 3, 16, generator=g)
+    ref = torch.rand(2, 2, 2, 2, generator=g)
+    off = torch.randn(2, 2, 3, 2, 3, 2, generator=g)
+    logits = torch.randn(2, 2, 3, 6, generator=g)
+    want = msda_numpy.msda_decode(value.numpy(), np.array(shapes), [0, 35], ref.numpy(), off.numpy(), logits.numpy())
+    got = cape_b200.ms_deform_attn_decode(value.cuda(), shapes, None, ref.cuda(), off.cuda(), logits.cuda())
+    assert rel_err(got.cpu().numpy(), want) < FWD_TOL_F32
+
+
+def test_module_mirror_matches_reference_module_fixture():
+    """MSDeformAttn mirror with the reference's weights: forward + every gradient vs the reference module's own
+    outputs (deformable_transformer.py:76-114), 2-d and 4-d reference points, padding mask."""
+    g = np.load(os.path.join(GOLDEN, "module_forward.npz"))
+    mod = cape_b200.MSDeformAttn(int(g["d_model"]), int(g["n_levels"]), int(g["n_heads"]), int(g["n_points"])).cuda()
+    mod.load_state_dict({k[len("param."):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("param.")})
+    q = _cuda(g["query"]).requires_grad_(True)
+    x = _cuda(g["input_flatten"]).requires_grad_(True)
+    shapes, starts = _cuda(g["spatial_shapes"]), _cuda(g["level_start_index"])
+    out = mod(q, _cuda(g["reference_points"]), x, shapes, starts, _cuda(g["padding_mask"]))
+    assert rel_err(out.detach().cpu().numpy(), g["out"]) < FWD_TOL_F32
+    params = dict(mod.named_parameters())
+    grads = torch.autograd.grad(out, [q, x] + list(params.values()), _cuda(g["grad_output"]))
+    assert rel_err(grads[0].cpu().numpy(), g["grad_query"]) < GRAD_TOL_F32
+    assert rel_err(grads[1].cpu().numpy(), g["grad_input_flatten"]) < GRAD_TOL_F32
+    for (name, _), gr in zip(params.items(), grads[2:]):
+        assert rel_err(gr.cpu().numpy(), g["grad_param." + name]) < GRAD_TOL_F32, name
+    out4 = mod(q, _cuda(g["reference_points4"]), x, shapes, starts, None)
+    assert rel_err(out4.detach().cpu().numpy(), g["out_ref4"]) < FWD_TOL_F32
+    # inference path: fused decode prologue, and use_cache served from an attached holder — same numbers
+    mod.eval()
+    mod.cache = cape_b200.ValueCache()
+    with torch.no_grad():
+        first = mod(q, _cuda(g["reference_points"]), x, shapes, starts, _cuda(g["padding_mask"]), use_cache=False)
+        launches = cape_b200.launch_count()
+        again = mod(q, _cuda(g["reference_points"]), torch.zeros_like(x), shapes, starts, _cuda(g["padding_mask"]),
+                    use_cache=True)      # memory argument ignored: the cached projection is used
+    assert cape_b200.launch_count() == launches + 1
+    assert rel_err(first.cpu().numpy(), g["out"]) < FWD_TOL_F32
+    assert torch.equal(first, again)
+
+
+def test_autocast_runs_the_core_in_fp32_like_the_reference():
+    inp = synthetic.make_inputs(1, 16, ((8, 8), (4, 4), (2, 2), (1, 1)), device="cuda", seed=9)
+    with torch.autocast("cuda", dtype=torch.float16):
+        out = cape_b200.ms_deform_attn(inp["value"].half(), inp["spatial_shapes"], inp["level_start_index"],
+                                       inp["sampling_locations"], inp["attention_weights"])
+    assert out.dtype == torch.float32
+
+
+def test_backward_from_autograd_thread_and_side_stream():
+    inp = synthetic.make_inputs(2, 64, ((8, 8), (4, 4), (2, 2), (1, 1)), seed=10)
+    a = tuple(inp[k].numpy() for k in ("value", "spatial_shapes", "level_start_index", "sampling_locations",
+                                       "attention_weights"))
+    want = msda_c.msda_backward(inp["grad_output"].numpy(), *a, dtype=np.float32)
+    results = {}
+
+    def work():
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            v = inp["value"].cuda().requires_grad_(True)
+            loc = inp["sampling_locations"].cuda().requires_grad_(True)
+            attn = inp["attention_weights"].cuda().requires_grad_(True)
+            out = cape_b200.ms_deform_attn(v, inp["spatial_shapes"].cuda(), inp["level_start_index"].cuda(), loc, attn)
+            (out * inp["grad_output"].cuda()).sum().backward()
+            s.synchronize()
+            results["g"] = (v.grad.cpu().numpy(), loc.grad.cpu().numpy(), attn.grad.cpu().numpy())
+
+    t = threading.Thread(target=work)
+    t.start()
+    t.join()
+    for got, w in zip(results["g"], want):
+        assert rel_err(got, w) < GRAD_TOL_F32
+
+
+def test_full_size_properties_training_shape():
+    """N=20, Lq=5440 (BASELINE.json's named shape): size-independent identities instead of an oracle run.
+    out is linear in value and in attention_weights, so
+        <out(v), g> == <v, grad_value(g)>          (adjoint)
+        <out(v), g> == <attn, grad_attn(g)>        (Euler, degree 1 in attn)
+        out(a*v1 + b*v2) == a*out(v1) + b*out(v2)  (linearity)
+    and a slice is checked against the C oracle."""
+    n, lq = 20, 5440
+    inp = synthetic.make_inputs(n, lq, dist="encoder", seed=1234, device="cuda")
+    v = inp["value"].requires_grad_(True)
+    loc = inp["sampling_locations"].requires_grad_(True)
+    attn = inp["attention_weights"].requires_grad_(True)
+    g = inp["grad_output"]
+    out = cape_b200.ms_deform_attn(v, inp["spatial_shapes"], inp["level_start_index"], loc, attn)
+    gv, gl, ga = torch.autograd.grad(out, (v, loc, attn), g)
+    lhs = (out.double() * g.double()).sum().item()
+    assert abs(lhs - (v.detach().double() * gv.double()).sum().item()) < 1e-6 * abs(lhs) + 1e-3
+    assert abs(lhs - (attn.detach().double() * ga.double()).sum().item()) < 1e-6 * abs(lhs) + 1e-3
+    v2 = torch.randn_like(v)
+    with torch.no_grad():
+        o2 = cape_b200.ms_deform_attn(v2, inp["spatial_shapes"], inp["level_start_index"], loc, attn)
+        o12 = cape_b200.ms_deform_attn(0.5 * v + 2.0 * v2, inp["spatial_shapes"], inp["level_start_index"], loc, attn)
+    assert rel_err((0.5 * out.detach() + 2.0 * o2).cpu().numpy(), o12.cpu().numpy()) < 1e-5
+    # last batch element against the oracle
+    sl = slice(n - 1, n)
+    a = (v.detach()[sl].cpu().numpy(), inp["spatial_shapes"].cpu().numpy(), inp["level_start_index"].cpu().numpy(),
+         loc.detach()[sl].cpu().numpy(), attn.detach()[sl].cpu().numpy())
+    want_out = msda_c.msda_forward(*a, dtype=np.float32)
+    want_g = msda_c.msda_backward(g[sl].cpu().numpy(), *a, dtype=np.float32)
+    assert rel_err(out.detach()[sl].cpu().numpy(), want_out) < FWD_TOL_F32
+    assert rel_err(gv[sl].cpu().numpy(), want_g[0]) < GRAD_TOL_F32
+    assert rel_err(gl[sl].cpu().numpy(), want_g[1]) < GRAD_TOL_F32
+    assert rel_err(ga[sl].cpu().numpy(), want_g[2]) < GRAD_TOL_F32
+
+
+def test_host_buffer_round_trip_abi():
+    """cape_msda_forward_backward_host: pinned host buffers in, results back on the host."""
+    lib = _lib.load()
+    inp = synthetic.make_inputs(2, 300, dist="encoder", seed=77)
+    names = ("value", "sampling_locations", "attention_weights", "grad_output")
+    pinned = {k: inp[k].contiguous().pin_memory() for k in names}
+    dims = _lib.Dims(2, 5440, 8, 32, 300, 4, 4)
+    ws_bytes = lib.cape_msda_host_workspace_bytes(ctypes.byref(dims), 1)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    out = torch.empty(2, 300, 256).pin_memory()
+    gv = torch.empty(2, 5440, 8, 32).pin_memory()
+    gl = torch.empty(2, 300, 8, 4, 4, 2).pin_memory()
+    ga = torch.empty(2, 300, 8, 4, 4).pin_memory()
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    stream = torch.cuda.current_stream()
+    rc = lib.cape_msda_forward_backward_host(p(pinned["value"]), p(inp["spatial_shapes"]), p(inp["level_start_index"]),
+                                             p(pinned["sampling_locations"]), p(pinned["attention_weights"]),
+                                             p(pinned["grad_output"]), p(out), p(gv), p(gl), p(ga), ctypes.byref(dims),
+                                             p(ws), ws_bytes, ctypes.c_void_p(stream.cuda_stream))
+    _lib.check(rc, "cape_msda_forward_backward_host")
+    stream.synchronize()
+    a = tuple(inp[k].numpy() for k in ("value", "spatial_shapes", "level_start_index", "sampling_locations",
+                                       "attention_weights"))
+    assert rel_err(out.numpy(), msda_c.msda_forward(*a, dtype=np.float32)) < FWD_TOL_F32
+    want_g = msda_c.msda_backward(inp["grad_output"].numpy(), *a, dtype=np.float32)
+    for got, want in zip((gv, gl, ga), want_g):
+        assert rel_err(got.numpy(), want) < GRAD_TOL_F32
+    # too-small workspace is refused
+    rc = lib.cape_msda_forward_backward_host(p(pinned["value"]), p(inp["spatial_shapes"]), p(inp["level_start_index"]),
+                                             p(pinned["sampling_locations"]), p(pinned["attention_weights"]),
+                                             p(pinned["grad_output"]), p(out), p(gv), p(gl), p(ga), ctypes.byref(dims),
+                                             p(ws), 1024, ctypes.c_void_p(stream.cuda_stream))
+    assert rc == -6
+
+
+def test_opcheck_registration():
+    inp = synthetic.make_inputs(1, 5, ((4, 4), (2, 2), (1, 1), (1, 1)), device="cuda", seed=3)
+    args = (inp["value"].requires_grad_(True), inp["spatial_shapes"], inp["level_start_index"],
+            inp["sampling_locations"].requires_grad_(True), inp["attention_weights"].requires_grad_(True))
+    torch.library.opcheck(torch.ops.cape.ms_deform_attn.default, args,
+                          test_utils=("test_schema", "test_faketensor", "test_autograd_registration"))
