@@ -13,6 +13,8 @@
 // holds the sums, lane k == l keeps level l's result, and after the level loop lanes k < L write the grad_loc /
 // grad_attn entries of the (q, m).  grad_value is scattered with 16-byte vector reductions (REDG.E.ADD.F32x4): 8 lanes
 // cover one 128 B corner row.
+#include <cstdlib>
+
 #include "msda_common.cuh"
 #include "msda_launch.h"
 
@@ -20,68 +22,93 @@ namespace cape {
 
 namespace {
 
-constexpr int kBwdWarps = 8;
+int env_int(const char* name, int fallback) {
+    const char* v = std::getenv(name);
+    if (!v || !*v) return fallback;
+    const int x = std::atoi(v);
+    return x > 0 ? x : fallback;
+}
 
+constexpr int kBwdMaxThreads = 512;
+
+template <typename VT, int L>
+struct BwdLevels {
+    int H[L], W[L];
+    int off[L];   // element offset of the level's first row inside this batch element's (S, M, D) block (< 2^31)
+    __device__ __forceinline__ void load(const int64_t* __restrict__ shapes, const int64_t* __restrict__ starts,
+                                         int rowStride) {
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+            H[l] = static_cast<int>(__ldg(shapes + 2 * l));
+            W[l] = static_cast<int>(__ldg(shapes + 2 * l + 1));
+            off[l] = static_cast<int>(__ldg(starts + l)) * rowStride;
+        }
+    }
+    __device__ __forceinline__ float lane_dim(int lane) const {
+        int dim = 1;
+#pragma unroll
+        for (int l = 0; l < L; ++l)
+            if ((lane >> 3) == l) dim = (lane & 1) ? H[l] : W[l];
+        return static_cast<float>(dim);
+    }
+};
+
+// One level, 4 points (one per 8-lane group).  (px, py) are pixel coordinates from pixel_coord().  Branch-free:
+// out-of-bounds corners load zeros and their REDG is predicated off.
 template <typename VT>
 __device__ __forceinline__ void scatter_level(const VT* __restrict__ vbase, float* __restrict__ gbase, int rowStride,
-                                              int H, int W, int start, float locx, float locy, float a,
+                                              int levelOff, int H, int W, float px, float py, float a,
                                               const float4& g, float& ga, float& gx, float& gy) {
-    ga = 0.f;
-    gx = 0.f;
-    gy = 0.f;
-    int x0, y0;
-    float lx, ly;
-    if (!sample_coords(locx, locy, H, W, x0, y0, lx, ly)) return;
+    const float xf = floorf(px), yf = floorf(py);
+    const float lx = px - xf, ly = py - yf;
+    const int x0 = static_cast<int>(xf), y0 = static_cast<int>(yf);
+    const bool x0ok = static_cast<unsigned>(x0) < static_cast<unsigned>(W);
+    const bool x1ok = static_cast<unsigned>(x0 + 1) < static_cast<unsigned>(W);
+    const bool y0ok = static_cast<unsigned>(y0) < static_cast<unsigned>(H);
+    const bool y1ok = static_cast<unsigned>(y0 + 1) < static_cast<unsigned>(H);
+    const int o00 = (y0 * W + x0) * rowStride + levelOff;   // 32-bit element offsets: S*M*D < 2^31 (checked by the ABI)
+    const int o10 = o00 + W * rowStride;
+    const float4 v00 = ld4_or_zero(vbase + o00, y0ok & x0ok);
+    const float4 v01 = ld4_or_zero(vbase + o00 + rowStride, y0ok & x1ok);
+    const float4 v10 = ld4_or_zero(vbase + o10, y1ok & x0ok);
+    const float4 v11 = ld4_or_zero(vbase + o10 + rowStride, y1ok & x1ok);
     const float hx = 1.f - lx, hy = 1.f - ly;
-    const bool x0ok = x0 >= 0, x1ok = x0 + 1 < W, y0ok = y0 >= 0, y1ok = y0 + 1 < H;
-    const int64_t off00 = static_cast<int64_t>(start + y0 * W + x0) * rowStride;
-    const int64_t offRow = static_cast<int64_t>(W) * rowStride;
-    float4 v00 = make_float4(0.f, 0.f, 0.f, 0.f), v01 = v00, v10 = v00, v11 = v00;
-    if (y0ok && x0ok) v00 = ld4(vbase + off00);
-    if (y0ok && x1ok) v01 = ld4(vbase + off00 + rowStride);
-    if (y1ok && x0ok) v10 = ld4(vbase + off00 + offRow);
-    if (y1ok && x1ok) v11 = ld4(vbase + off00 + offRow + rowStride);
-    if (y0ok && x0ok) {
-        const float c = a * hy * hx;
-        red_add4(gbase + off00, c * g.x, c * g.y, c * g.z, c * g.w);
-    }
-    if (y0ok && x1ok) {
-        const float c = a * hy * lx;
-        red_add4(gbase + off00 + rowStride, c * g.x, c * g.y, c * g.z, c * g.w);
-    }
-    if (y1ok && x0ok) {
-        const float c = a * ly * hx;
-        red_add4(gbase + off00 + offRow, c * g.x, c * g.y, c * g.z, c * g.w);
-    }
-    if (y1ok && x1ok) {
-        const float c = a * ly * lx;
-        red_add4(gbase + off00 + offRow + rowStride, c * g.x, c * g.y, c * g.z, c * g.w);
-    }
+    const float ahy = a * hy, aly = a * ly;
+    float c = ahy * hx;
+    red_add4_if(gbase + o00, y0ok & x0ok, c * g.x, c * g.y, c * g.z, c * g.w);
+    c = ahy * lx;
+    red_add4_if(gbase + o00 + rowStride, y0ok & x1ok, c * g.x, c * g.y, c * g.z, c * g.w);
+    c = aly * hx;
+    red_add4_if(gbase + o10, y1ok & x0ok, c * g.x, c * g.y, c * g.z, c * g.w);
+    c = aly * lx;
+    red_add4_if(gbase + o10 + rowStride, y1ok & x1ok, c * g.x, c * g.y, c * g.z, c * g.w);
     const float d00 = dot4(g, v00), d01 = dot4(g, v01), d10 = dot4(g, v10), d11 = dot4(g, v11);   // 0 for OOB corners
     ga = hy * (hx * d00 + lx * d01) + ly * (hx * d10 + lx * d11);
     gx = hy * (d01 - d00) + ly * (d11 - d10);
     gy = hx * (d10 - d00) + lx * (d11 - d01);
 }
 
-template <typename VT, typename AT, int L>
-__global__ void __launch_bounds__(kBwdWarps * 32)
+template <typename VT, typename AT, int L, int MC>
+__global__ void __launch_bounds__(kBwdMaxThreads)
 msda_bwd_fast_kernel(const VT* __restrict__ gout, const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                      const int64_t* __restrict__ starts, const AT* __restrict__ locp, const AT* __restrict__ attnp,
-                     float* __restrict__ gvalue, AT* __restrict__ gloc, AT* __restrict__ gattn, int N, int S, int M,
+                     float* __restrict__ gvalue, AT* __restrict__ gloc, AT* __restrict__ gattn, int N, int S, int M_rt,
                      int Lq, int q_per_cta, int q_tiles) {
     constexpr int D = 32;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int M = MC ? MC : M_rt;
+    const int lane = threadIdx.x & 31, warp = uniform_warp_id(), nwarps = blockDim.x >> 5;
     const int p = lane >> 3, k = lane & 7;
     int bid = blockIdx.x;
     const int qt = bid % q_tiles;
     bid /= q_tiles;
     const int m = bid % M, n = bid / M;
-    Levels<L> lv;
-    lv.load(shapes, starts);
     const int rowStride = M * D;
+    BwdLevels<VT, L> lv;
+    lv.load(shapes, starts, rowStride);
     const int64_t headOff = (static_cast<int64_t>(n) * S * M + m) * D + k * 4;
     const VT* vbase = value + headOff;
     float* gbase = gvalue + headOff;
+    const float dimf = lv.lane_dim(lane);
     const int q_end = min(Lq, (qt + 1) * q_per_cta);
     for (int q = qt * q_per_cta + warp; q < q_end; q += nwarps) {
         const int64_t qm = (static_cast<int64_t>(n) * Lq + q) * M + m;
@@ -89,14 +116,15 @@ msda_bwd_fast_kernel(const VT* __restrict__ gout, const VT* __restrict__ value, 
         if (lane < L * 8) locv = to_f32(locp[qm * (L * 8) + lane]);
         if (lane < L * 4) attnv = to_f32(attnp[qm * (L * 4) + lane]);
         const float4 g = ld4(gout + qm * D + k * 4);
+        locv = pixel_coord(locv, dimf);
         float r_ga = 0.f, r_gx = 0.f, r_gy = 0.f;
 #pragma unroll
         for (int l = 0; l < L; ++l) {
-            const float locx = __shfl_sync(kFullMask, locv, l * 8 + p * 2);
-            const float locy = __shfl_sync(kFullMask, locv, l * 8 + p * 2 + 1);
+            const float px = __shfl_sync(kFullMask, locv, l * 8 + p * 2);
+            const float py = __shfl_sync(kFullMask, locv, l * 8 + p * 2 + 1);
             const float a = __shfl_sync(kFullMask, attnv, l * 4 + p);
             float ga, gx, gy;
-            scatter_level(vbase, gbase, rowStride, lv.H[l], lv.W[l], lv.start[l], locx, locy, a, g, ga, gx, gy);
+            scatter_level(vbase, gbase, rowStride, lv.off[l], lv.H[l], lv.W[l], px, py, a, g, ga, gx, gy);
 #pragma unroll
             for (int s = 1; s <= 4; s <<= 1) {
                 ga += __shfl_xor_sync(kFullMask, ga, s);
@@ -195,21 +223,29 @@ cudaError_t launch_typed(const BwdArgs& a, cudaStream_t stream) {
     AT* gloc = static_cast<AT*>(a.grad_loc);
     AT* gattn = static_cast<AT*>(a.grad_attn);
     if (d.D == 32 && d.P == 4 && d.L >= 1 && d.L <= 4) {
-        int q_per_cta = 64;
-        while (q_per_cta > 8 &&
-               static_cast<int64_t>(d.N) * d.M * ((d.Lq + q_per_cta - 1) / q_per_cta) < 148 * 8)
-            q_per_cta >>= 1;
+        int threads = env_int("CAPE_BWD_THREADS", 256);
+        threads = (threads / 32) * 32;
+        if (threads < 32) threads = 32;
+        if (threads > kBwdMaxThreads) threads = kBwdMaxThreads;
+        int q_per_cta = env_int("CAPE_BWD_QPC", 128);
+        while (q_per_cta > 1 && static_cast<int64_t>(d.N) * d.M * ((d.Lq + q_per_cta - 1) / q_per_cta) < 148 * 4) q_per_cta >>= 1;
         if (q_per_cta > d.Lq) q_per_cta = d.Lq;
+        if (q_per_cta < 1) q_per_cta = 1;
+        if (threads > q_per_cta * 32) threads = q_per_cta * 32;
         const int q_tiles = (d.Lq + q_per_cta - 1) / q_per_cta;
-        const int warps = q_per_cta < kBwdWarps ? q_per_cta : kBwdWarps;
         const int64_t grid = static_cast<int64_t>(d.N) * d.M * q_tiles;
         if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-        const dim3 gdim(static_cast<unsigned>(grid)), b(warps * 32);
+        const dim3 gdim(static_cast<unsigned>(grid)), b(threads);
 #define CAPE_BWD_CASE(LL)                                                                                          \
     case LL:                                                                                                       \
-        msda_bwd_fast_kernel<VT, AT, LL><<<gdim, b, 0, stream>>>(gout, value, a.shapes, a.starts, loc, attn,        \
-                                                                 a.grad_value, gloc, gattn, d.N, d.S, d.M, d.Lq,   \
-                                                                 q_per_cta, q_tiles);                              \
+        if (d.M == 8)                                                                                              \
+            msda_bwd_fast_kernel<VT, AT, LL, 8><<<gdim, b, 0, stream>>>(gout, value, a.shapes, a.starts, loc, attn, \
+                                                                        a.grad_value, gloc, gattn, d.N, d.S, d.M,  \
+                                                                        d.Lq, q_per_cta, q_tiles);                 \
+        else                                                                                                       \
+            msda_bwd_fast_kernel<VT, AT, LL, 0><<<gdim, b, 0, stream>>>(gout, value, a.shapes, a.starts, loc, attn, \
+                                                                        a.grad_value, gloc, gattn, d.N, d.S, d.M,  \
+                                                                        d.Lq, q_per_cta, q_tiles);                 \
         break;
         switch (d.L) {
             CAPE_BWD_CASE(1)

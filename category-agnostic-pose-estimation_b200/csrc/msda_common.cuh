@@ -36,6 +36,44 @@ __device__ __forceinline__ float4 ld4(const __half* p) {
     const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
     return make_float4(a.x, a.y, b.x, b.y);
 }
+// 4-channel load that yields zeros when `pred` is false (zeros padding: an out-of-bounds corner contributes nothing).
+// The destination is zero-initialised in C++ and conditionally overwritten by a predicated load inside one asm
+// statement ("+" constraints), which keeps ptxas from loading into temporaries and selecting afterwards.
+__device__ __forceinline__ float4 ld4_or_zero(const float* p, bool pred) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t@p ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+        : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
+        : "l"(p), "r"(static_cast<int>(pred)));
+    return v;
+}
+__device__ __forceinline__ uint2 ld2u_or_zero(const void* p, bool pred) {
+    uint2 r = make_uint2(0u, 0u);
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p ld.global.nc.v2.b32 {%0, %1}, [%2];\n\t}"
+        : "+r"(r.x), "+r"(r.y)
+        : "l"(p), "r"(static_cast<int>(pred)));
+    return r;
+}
+__device__ __forceinline__ float4 ld4_or_zero(const __nv_bfloat16* p, bool pred) {
+    const uint2 r = ld2u_or_zero(p, pred);
+    float4 f;
+    f.x = __uint_as_float(r.x << 16);
+    f.y = __uint_as_float(r.x & 0xffff0000u);
+    f.z = __uint_as_float(r.y << 16);
+    f.w = __uint_as_float(r.y & 0xffff0000u);
+    return f;
+}
+__device__ __forceinline__ float4 ld4_or_zero(const __half* p, bool pred) {
+    const uint2 r = ld2u_or_zero(p, pred);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void fma4(float w, const float4& v, float4& acc) {
+    acc.x = fmaf(w, v.x, acc.x);
+    acc.y = fmaf(w, v.y, acc.y);
+    acc.z = fmaf(w, v.z, acc.z);
+    acc.w = fmaf(w, v.w, acc.w);
+}
 __device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ void st4(__nv_bfloat16* p, const float4& v) {
     const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
@@ -63,6 +101,12 @@ template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return
 // fp32 vector reduction into global memory (REDG.E.ADD.F32x4 on sm_90+); p must be 16-byte aligned.
 __device__ __forceinline__ void red_add4(float* p, float x, float y, float z, float w) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+
+// Same, executed only when `pred` (the predicate rides on the REDG itself: no branch).
+__device__ __forceinline__ void red_add4_if(float* p, bool pred, float x, float y, float z, float w) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t@p red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n\t}"
+                 ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(w), "r"(static_cast<int>(pred)) : "memory");
 }
 
 // ---- per-level metadata held in registers --------------------------------------------------------------------
@@ -94,6 +138,19 @@ __device__ __forceinline__ bool sample_coords(float locx, float locy, int H, int
     y0 = static_cast<int>(yf);
     return true;
 }
+
+// Pixel coordinate of one normalised location component on a map dimension `dim` (= W for x, H for y), or the
+// sentinel -4 when no corner can be in bounds along this axis (also for NaN / inf): with the sentinel, floor() gives
+// -4 and both unsigned corner tests ((unsigned)i < dim, (unsigned)(i + 1) < dim) fail, so no separate "ok" flag is
+// carried around.  Arithmetic order as in sample_coords().
+__device__ __forceinline__ float pixel_coord(float loc, float dimf) {
+    const float g = fmaf(2.f, loc, -1.f);
+    const float x = __fsub_rn(__fmul_rn(__fadd_rn(g, 1.f), 0.5f * dimf), 0.5f);
+    return (x >= -1.f && x < dimf) ? x : -4.f;
+}
+
+// Warp index that the compiler can prove uniform (so shuffles in warp-uniform loops need no reconvergence code).
+__device__ __forceinline__ int uniform_warp_id() { return __shfl_sync(kFullMask, static_cast<int>(threadIdx.x >> 5), 0); }
 
 __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
     return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));

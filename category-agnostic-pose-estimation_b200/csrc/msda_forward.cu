@@ -10,8 +10,14 @@
 //           lane fetches the same corner of the 4 points of one level (4 x 128 B rows per warp instruction);
 //   the 32 location floats and 16 weights of a (q, m) are one coalesced 128 B + 64 B load, distributed by shuffles,
 //   and prefetched one query ahead;
+//   the level loop is branch-free (out-of-bounds corners are predicated loads of zero), so the shuffles need no
+//   reconvergence and the 16 corner loads of a query are all in flight together;
 //   the 4 point-partials are folded with two xor-shuffles and lanes 0-7 store the 128 B output row.
+// Measured on B200 (profiles/r01_ubench_gather_scatter.txt) an SM sustains one 128 B row per ~1.7 clk from L1, so the
+// 64 corner rows of a (q, m) bound this kernel well below the HBM roofline; see DESIGN.md.
 // Everything else (other D / P / L) takes the generic kernel: one warp per (n, q, m), lanes strided over channels.
+#include <cstdlib>
+
 #include "msda_common.cuh"
 #include "msda_launch.h"
 
@@ -19,37 +25,63 @@ namespace cape {
 
 namespace {
 
-constexpr int kFwdWarps = 8;
+constexpr int kFwdMaxThreads = 1024;
 
+// Per-level constants kept in registers for the whole CTA.
+template <typename VT, int L>
+struct FwdLevels {
+    int H[L], W[L];
+    const VT* base[L];   // first row of the level for this (n, m, channel quad)
+    __device__ __forceinline__ void load(const int64_t* __restrict__ shapes, const int64_t* __restrict__ starts,
+                                         const VT* vbase, int rowStride) {
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+            H[l] = static_cast<int>(__ldg(shapes + 2 * l));
+            W[l] = static_cast<int>(__ldg(shapes + 2 * l + 1));
+            base[l] = vbase + static_cast<int64_t>(__ldg(starts + l)) * rowStride;
+        }
+    }
+    // map dimension that loc float `lane` (= [l][p][xy]) is scaled by: W_l for x, H_l for y
+    __device__ __forceinline__ float lane_dim(int lane) const {
+        int dim = 1;
+#pragma unroll
+        for (int l = 0; l < L; ++l)
+            if ((lane >> 3) == l) dim = (lane & 1) ? H[l] : W[l];
+        return static_cast<float>(dim);
+    }
+};
+
+// One level, 4 points (one per 8-lane group), 4 corners each.  (px, py) are pixel coordinates from pixel_coord().
 template <typename VT>
-__device__ __forceinline__ void gather_level(const VT* __restrict__ vbase, int rowStride, int H, int W, int start,
-                                             float locx, float locy, float a, float4& acc) {
-    int x0, y0;
-    float lx, ly;
-    if (!sample_coords(locx, locy, H, W, x0, y0, lx, ly)) return;
-    const float hx = 1.f - lx, hy = 1.f - ly;
-    const bool x0ok = x0 >= 0, x1ok = x0 + 1 < W, y0ok = y0 >= 0, y1ok = y0 + 1 < H;
-    const VT* p00 = vbase + static_cast<int64_t>(start + y0 * W + x0) * rowStride;
+__device__ __forceinline__ void gather_level(const VT* __restrict__ base, int rowStride, int H, int W, float px,
+                                             float py, float a, float4& acc) {
+    const float xf = floorf(px), yf = floorf(py);
+    const float lx = px - xf, ly = py - yf;
+    const int x0 = static_cast<int>(xf), y0 = static_cast<int>(yf);
+    const bool x0ok = static_cast<unsigned>(x0) < static_cast<unsigned>(W);
+    const bool x1ok = static_cast<unsigned>(x0 + 1) < static_cast<unsigned>(W);
+    const bool y0ok = static_cast<unsigned>(y0) < static_cast<unsigned>(H);
+    const bool y1ok = static_cast<unsigned>(y0 + 1) < static_cast<unsigned>(H);
+    const VT* p00 = base + static_cast<int64_t>(y0 * W + x0) * rowStride;
     const VT* p10 = p00 + static_cast<int64_t>(W) * rowStride;
-    float4 v00 = make_float4(0.f, 0.f, 0.f, 0.f), v01 = v00, v10 = v00, v11 = v00;
-    if (y0ok && x0ok) v00 = ld4(p00);
-    if (y0ok && x1ok) v01 = ld4(p00 + rowStride);
-    if (y1ok && x0ok) v10 = ld4(p10);
-    if (y1ok && x1ok) v11 = ld4(p10 + rowStride);
-    const float w00 = a * hy * hx, w01 = a * hy * lx, w10 = a * ly * hx, w11 = a * ly * lx;
-    acc.x = fmaf(w00, v00.x, fmaf(w01, v01.x, fmaf(w10, v10.x, fmaf(w11, v11.x, acc.x))));
-    acc.y = fmaf(w00, v00.y, fmaf(w01, v01.y, fmaf(w10, v10.y, fmaf(w11, v11.y, acc.y))));
-    acc.z = fmaf(w00, v00.z, fmaf(w01, v01.z, fmaf(w10, v10.z, fmaf(w11, v11.z, acc.z))));
-    acc.w = fmaf(w00, v00.w, fmaf(w01, v01.w, fmaf(w10, v10.w, fmaf(w11, v11.w, acc.w))));
+    const float ahy = a * (1.f - ly), aly = a * ly, hx = 1.f - lx;
+    const float4 v00 = ld4_or_zero(p00, y0ok & x0ok);
+    const float4 v01 = ld4_or_zero(p00 + rowStride, y0ok & x1ok);
+    const float4 v10 = ld4_or_zero(p10, y1ok & x0ok);
+    const float4 v11 = ld4_or_zero(p10 + rowStride, y1ok & x1ok);
+    fma4(ahy * hx, v00, acc);
+    fma4(ahy * lx, v01, acc);
+    fma4(aly * hx, v10, acc);
+    fma4(aly * lx, v11, acc);
 }
 
 // Per-(q, m) sample table held one float per lane: lane i < 8L holds loc[i] (= [l][p][xy]), lane i < 4L holds attn[i].
+// finish() turns the raw prefetch into pixel coordinates (and, FUSED, first applies the softmax over the 4L logits and
+// loc = ref + off / (W_l, H_l), deformable_transformer.py:100-105) — once per (q, m), one coordinate per lane.
 template <typename AT, int L, bool FUSED>
 struct SampleTable {
     float loc, attn;
-    // raw (not yet transformed) prefetch of the next query
-    __device__ __forceinline__ void fetch(const void* locp, const void* attnp, const float* refp, int64_t qm, int64_t nq,
-                                          int lane) {
+    __device__ __forceinline__ void fetch(const void* locp, const void* attnp, int64_t qm, int lane) {
         loc = 0.f;
         attn = FUSED ? -INFINITY : 0.f;
         if (FUSED) {
@@ -57,8 +89,6 @@ struct SampleTable {
             const float* g = static_cast<const float*>(attnp) + qm * (L * 4);
             if (lane < L * 8) loc = __ldg(o + lane);
             if (lane < L * 4) attn = __ldg(g + lane);
-            (void)refp;
-            (void)nq;
         } else {
             const AT* o = static_cast<const AT*>(locp) + qm * (L * 8);
             const AT* g = static_cast<const AT*>(attnp) + qm * (L * 4);
@@ -66,63 +96,58 @@ struct SampleTable {
             if (lane < L * 4) attn = to_f32(g[lane]);
         }
     }
-    // FUSED: softmax over the 4L logits and loc = ref + off / (W_l, H_l)   (deformable_transformer.py:100-105)
-    __device__ __forceinline__ void finish(const float* refp, int64_t nq, int lane, const Levels<L>& lv) {
-        if (!FUSED) return;
-        float mx = attn;
+    __device__ __forceinline__ void finish(const float* refp, int64_t nq, int lane, float dimf) {
+        if (FUSED) {
+            float mx = attn;
 #pragma unroll
-        for (int s = 8; s >= 1; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFullMask, mx, s));
-        float e = (lane < L * 4) ? expf(attn - mx) : 0.f;
-        float sum = e;
+            for (int s = 8; s >= 1; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFullMask, mx, s));
+            const float e = (lane < L * 4) ? expf(attn - mx) : 0.f;
+            float sum = e;
 #pragma unroll
-        for (int s = 8; s >= 1; s >>= 1) sum += __shfl_xor_sync(kFullMask, sum, s);
-        attn = e / sum;
-        if (lane < L * 8) {
-            const int l = lane >> 3, c = lane & 1;
-            int dim = 1;
-#pragma unroll
-            for (int i = 0; i < L; ++i)
-                if (i == l) dim = c ? lv.H[i] : lv.W[i];
-            const float r = __ldg(refp + nq * (L * 2) + l * 2 + c);
-            loc = r + loc / static_cast<float>(dim);
+            for (int s = 8; s >= 1; s >>= 1) sum += __shfl_xor_sync(kFullMask, sum, s);
+            attn = e / sum;
+            if (lane < L * 8) loc = __ldg(refp + nq * (L * 2) + (lane >> 3) * 2 + (lane & 1)) + loc / dimf;
         }
+        loc = pixel_coord(loc, dimf);
     }
 };
 
-template <typename VT, typename AT, int L, bool FUSED>
-__global__ void __launch_bounds__(kFwdWarps * 32)
+// MC: compile-time head count (row stride = MC * 32 elements) or 0 for a run-time stride.
+template <typename VT, typename AT, int L, bool FUSED, int MC>
+__global__ void __launch_bounds__(kFwdMaxThreads)
 msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                      const int64_t* __restrict__ starts, const void* __restrict__ locp,
                      const void* __restrict__ attnp, const float* __restrict__ refp, VT* __restrict__ out, int N, int S,
-                     int M, int Lq, int q_per_cta, int q_tiles) {
+                     int M_rt, int Lq, int q_per_cta, int q_tiles) {
     constexpr int D = 32;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int M = MC ? MC : M_rt;
+    const int lane = threadIdx.x & 31, warp = uniform_warp_id(), nwarps = blockDim.x >> 5;
     const int p = lane >> 3, k = lane & 7;
     int bid = blockIdx.x;
     const int qt = bid % q_tiles;
     bid /= q_tiles;
     const int m = bid % M, n = bid / M;
-    Levels<L> lv;
-    lv.load(shapes, starts);
     const int rowStride = M * D;
-    const VT* vbase = value + (static_cast<int64_t>(n) * S * M + m) * D + k * 4;
+    FwdLevels<VT, L> lv;
+    lv.load(shapes, starts, value + (static_cast<int64_t>(n) * S * M + m) * D + k * 4, rowStride);
+    const float dimf = lv.lane_dim(lane);
     const int q_end = min(Lq, (qt + 1) * q_per_cta);
     int q = qt * q_per_cta + warp;
     if (q >= q_end) return;
     SampleTable<AT, L, FUSED> cur, nxt;
-    nxt.fetch(locp, attnp, refp, (static_cast<int64_t>(n) * Lq + q) * M + m, static_cast<int64_t>(n) * Lq + q, lane);
+    nxt.fetch(locp, attnp, (static_cast<int64_t>(n) * Lq + q) * M + m, lane);
     for (; q < q_end; q += nwarps) {
         const int64_t nq = static_cast<int64_t>(n) * Lq + q;
         cur = nxt;
-        if (q + nwarps < q_end) nxt.fetch(locp, attnp, refp, (nq + nwarps) * M + m, nq + nwarps, lane);
-        cur.finish(refp, nq, lane, lv);
+        if (q + nwarps < q_end) nxt.fetch(locp, attnp, (nq + nwarps) * M + m, lane);
+        cur.finish(refp, nq, lane, dimf);
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int l = 0; l < L; ++l) {
-            const float locx = __shfl_sync(kFullMask, cur.loc, l * 8 + p * 2);
-            const float locy = __shfl_sync(kFullMask, cur.loc, l * 8 + p * 2 + 1);
+            const float px = __shfl_sync(kFullMask, cur.loc, l * 8 + p * 2);
+            const float py = __shfl_sync(kFullMask, cur.loc, l * 8 + p * 2 + 1);
             const float a = __shfl_sync(kFullMask, cur.attn, l * 4 + p);
-            gather_level(vbase, rowStride, lv.H[l], lv.W[l], lv.start[l], locx, locy, a, acc);
+            gather_level(lv.base[l], rowStride, lv.H[l], lv.W[l], px, py, a, acc);
         }
 #pragma unroll
         for (int s = 8; s <= 16; s <<= 1) {
@@ -135,7 +160,7 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
     }
 }
 
-// Generic path: any D (multiple of 4 not required here), L <= 8, P <= 8.  One warp per (n, q, m); lanes stride over d.
+// Generic path: any D <= 256, L <= 8, P <= 8.  One warp per (n, q, m); lanes stride over d.
 template <typename VT, typename AT, bool FUSED>
 __global__ void __launch_bounds__(128)
 msda_fwd_generic_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
@@ -201,42 +226,76 @@ msda_fwd_generic_kernel(const VT* __restrict__ value, const int64_t* __restrict_
     }
 }
 
+// Launch geometry of the fast path.  Default: 512-thread CTAs (16 warps) over 512 consecutive queries — two CTAs per
+// SM at 64 registers, each sweeping a compact window of the (n, m) value rows.  CAPE_FWD_THREADS / CAPE_FWD_QPC
+// override it for tuning runs.
+struct FastGeometry {
+    int threads, q_per_cta, q_tiles;
+    int64_t grid;
+};
+
+int env_int(const char* name, int fallback) {
+    const char* v = std::getenv(name);
+    if (!v || !*v) return fallback;
+    const int x = std::atoi(v);
+    return x > 0 ? x : fallback;
+}
+
+FastGeometry fast_geometry(const cape_msda_dims& d, const char* env_threads, const char* env_qpc, int def_threads,
+                           int def_qpc) {
+    int threads = env_int(env_threads, def_threads);
+    threads = (threads / 32) * 32;
+    if (threads < 32) threads = 32;
+    if (threads > kFwdMaxThreads) threads = kFwdMaxThreads;
+    int q_per_cta = env_int(env_qpc, def_qpc);
+    // small problems (decode: Lq = 1..k): shrink the tile until the grid covers the chip a few times over
+    while (q_per_cta > 1 && static_cast<int64_t>(d.N) * d.M * ((d.Lq + q_per_cta - 1) / q_per_cta) < 148 * 4) q_per_cta >>= 1;
+    if (q_per_cta > d.Lq) q_per_cta = d.Lq;
+    if (q_per_cta < 1) q_per_cta = 1;
+    if (threads > q_per_cta * 32) threads = q_per_cta * 32;
+    FastGeometry g;
+    g.threads = threads;
+    g.q_per_cta = q_per_cta;
+    g.q_tiles = (d.Lq + q_per_cta - 1) / q_per_cta;
+    g.grid = static_cast<int64_t>(d.N) * d.M * g.q_tiles;
+    return g;
+}
+
+template <typename VT, typename AT, bool FUSED, int L>
+void launch_fast(const FwdArgs& a, const FastGeometry& g, cudaStream_t stream) {
+    const cape_msda_dims& d = a.d;
+    const VT* value = static_cast<const VT*>(a.value);
+    VT* out = static_cast<VT*>(a.out);
+    const dim3 grid(static_cast<unsigned>(g.grid)), block(g.threads);
+    if (d.M == 8)
+        msda_fwd_fast_kernel<VT, AT, L, FUSED, 8><<<grid, block, 0, stream>>>(
+            value, a.shapes, a.starts, a.loc, a.attn, a.ref_points, out, d.N, d.S, d.M, d.Lq, g.q_per_cta, g.q_tiles);
+    else
+        msda_fwd_fast_kernel<VT, AT, L, FUSED, 0><<<grid, block, 0, stream>>>(
+            value, a.shapes, a.starts, a.loc, a.attn, a.ref_points, out, d.N, d.S, d.M, d.Lq, g.q_per_cta, g.q_tiles);
+}
+
 template <typename VT, typename AT, bool FUSED>
 cudaError_t launch_typed(const FwdArgs& a, cudaStream_t stream) {
     const cape_msda_dims& d = a.d;
     const int64_t total_qm = static_cast<int64_t>(d.N) * d.Lq * d.M;
     if (total_qm == 0) return cudaSuccess;
-    const VT* value = static_cast<const VT*>(a.value);
-    VT* out = static_cast<VT*>(a.out);
     if (d.D == 32 && d.P == 4 && d.L >= 1 && d.L <= 4) {
-        // queries per CTA: enough CTAs to fill 148 SMs several times over, enough queries per warp to amortise setup
-        int q_per_cta = 64;
-        while (q_per_cta > 8 && static_cast<int64_t>(d.N) * d.M * ((d.Lq + q_per_cta - 1) / q_per_cta) < 148 * 8) q_per_cta >>= 1;
-        if (q_per_cta > d.Lq) q_per_cta = d.Lq;
-        const int q_tiles = (d.Lq + q_per_cta - 1) / q_per_cta;
-        const int warps = q_per_cta < kFwdWarps ? q_per_cta : kFwdWarps;
-        const int64_t grid = static_cast<int64_t>(d.N) * d.M * q_tiles;
-        if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-        const dim3 g(static_cast<unsigned>(grid)), b(warps * 32);
-#define CAPE_FWD_CASE(LL)                                                                                           \
-    case LL:                                                                                                        \
-        msda_fwd_fast_kernel<VT, AT, LL, FUSED><<<g, b, 0, stream>>>(value, a.shapes, a.starts, a.loc, a.attn,       \
-                                                                     a.ref_points, out, d.N, d.S, d.M, d.Lq,        \
-                                                                     q_per_cta, q_tiles);                           \
-        break;
+        const FastGeometry g = fast_geometry(d, "CAPE_FWD_THREADS", "CAPE_FWD_QPC", 512, 512);
+        if (g.grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
         switch (d.L) {
-            CAPE_FWD_CASE(1)
-            CAPE_FWD_CASE(2)
-            CAPE_FWD_CASE(3)
-            CAPE_FWD_CASE(4)
+            case 1: launch_fast<VT, AT, FUSED, 1>(a, g, stream); break;
+            case 2: launch_fast<VT, AT, FUSED, 2>(a, g, stream); break;
+            case 3: launch_fast<VT, AT, FUSED, 3>(a, g, stream); break;
+            default: launch_fast<VT, AT, FUSED, 4>(a, g, stream); break;
         }
-#undef CAPE_FWD_CASE
     } else {
         const int warps = 4;
         const int64_t grid = (total_qm + warps - 1) / warps;
         if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
         msda_fwd_generic_kernel<VT, AT, FUSED><<<static_cast<unsigned>(grid), warps * 32, 0, stream>>>(
-            value, a.shapes, a.starts, a.loc, a.attn, a.ref_points, out, total_qm, d.S, d.M, d.D, d.Lq, d.L, d.P);
+            static_cast<const VT*>(a.value), a.shapes, a.starts, a.loc, a.attn, a.ref_points, static_cast<VT*>(a.out),
+            total_qm, d.S, d.M, d.D, d.Lq, d.L, d.P);
     }
     count_launch();
     return cudaGetLastError();
