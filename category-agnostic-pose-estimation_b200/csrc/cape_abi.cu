@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 
 #include "msda_launch.h"
 
@@ -222,6 +223,28 @@ HostPlan plan_host(const cape_msda_dims& d, bool bwd) {
 }
 }  // namespace
 
+namespace {
+// Two non-blocking copy streams per device, created on first use and kept for the life of the process.
+struct HelperStreams {
+    cudaStream_t in, out;
+};
+bool get_helper_streams(HelperStreams* hs) {
+    static std::mutex mu;
+    static HelperStreams per_device[64] = {};
+    static bool made[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!made[dev]) {
+        if (cudaStreamCreateWithFlags(&per_device[dev].in, cudaStreamNonBlocking) != cudaSuccess) return false;
+        if (cudaStreamCreateWithFlags(&per_device[dev].out, cudaStreamNonBlocking) != cudaSuccess) return false;
+        made[dev] = true;
+    }
+    *hs = per_device[dev];
+    return true;
+}
+}  // namespace
+
 size_t cape_msda_host_workspace_bytes(const cape_msda_dims* dims, int with_backward) {
     if (check_dims(dims)) return 0;
     return plan_host(*dims, with_backward != 0).total;
@@ -245,39 +268,101 @@ int cape_msda_forward_backward_host(const float* value_host, const int64_t* spat
     if (workspace_bytes < p.total)
         return fail(CAPE_ERR_WORKSPACE, "workspace %zu B < required %zu B", workspace_bytes, p.total);
     const cape_msda_dims& d = *dims;
-    const size_t nv = static_cast<size_t>(d.N) * d.S * d.M * d.D * 4;
-    const size_t no = static_cast<size_t>(d.N) * d.Lq * d.M * d.D * 4;
-    const size_t na = static_cast<size_t>(d.N) * d.Lq * d.M * d.L * d.P * 4;
+    // per batch element sizes (all tensors are N-major, so a chunk of the batch is a contiguous slice of each)
+    const size_t ev = static_cast<size_t>(d.S) * d.M * d.D * 4;
+    const size_t eo = static_cast<size_t>(d.Lq) * d.M * d.D * 4;
+    const size_t ea = static_cast<size_t>(d.Lq) * d.M * d.L * d.P * 4;
     char* ws = static_cast<char*>(workspace_dev);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     cudaError_t e;
-#define CAPE_COPY(dst, src, bytes, kind)                                                    \
-    if ((bytes) && (e = cudaMemcpyAsync((dst), (src), (bytes), (kind), s)) != cudaSuccess)  \
-        return fail_cuda(e, "cape_msda_forward_backward_host copy");
-    CAPE_COPY(ws + p.shapes, spatial_shapes_host, static_cast<size_t>(d.L) * 16, cudaMemcpyHostToDevice)
-    CAPE_COPY(ws + p.starts, level_start_index_host, static_cast<size_t>(d.L) * 8, cudaMemcpyHostToDevice)
-    CAPE_COPY(ws + p.value, value_host, nv, cudaMemcpyHostToDevice)
-    CAPE_COPY(ws + p.loc, loc_host, na * 2, cudaMemcpyHostToDevice)
-    CAPE_COPY(ws + p.attn, attn_host, na, cudaMemcpyHostToDevice)
-    if (bwd) CAPE_COPY(ws + p.gout, grad_out_host, no, cudaMemcpyHostToDevice)
-    rc = cape_msda_forward(ws + p.value, reinterpret_cast<const int64_t*>(ws + p.shapes),
-                           reinterpret_cast<const int64_t*>(ws + p.starts), ws + p.loc, ws + p.attn, ws + p.out, dims,
-                           CAPE_DTYPE_F32, CAPE_DTYPE_F32, stream);
-    if (rc) return rc;
-    if (bwd) {
-        rc = cape_msda_backward(ws + p.gout, ws + p.value, reinterpret_cast<const int64_t*>(ws + p.shapes),
-                                reinterpret_cast<const int64_t*>(ws + p.starts), ws + p.loc, ws + p.attn,
-                                reinterpret_cast<float*>(ws + p.gvalue), ws + p.gloc, ws + p.gattn, dims, CAPE_DTYPE_F32,
-                                CAPE_DTYPE_F32, /*zero_grad_value=*/1, stream);
+#define CAPE_TRY(call, what) \
+    if ((e = (call)) != cudaSuccess) return fail_cuda(e, what);
+    CAPE_TRY(cudaMemcpyAsync(ws + p.shapes, spatial_shapes_host, static_cast<size_t>(d.L) * 16, cudaMemcpyHostToDevice, s),
+             "copy spatial_shapes")
+    CAPE_TRY(cudaMemcpyAsync(ws + p.starts, level_start_index_host, static_cast<size_t>(d.L) * 8, cudaMemcpyHostToDevice, s),
+             "copy level_start_index")
+    if (d.N == 0) return 0;
+
+    // Software pipeline over chunks of the batch: H2D of chunk c+1 and D2H of chunk c-1 overlap the kernels of chunk c
+    // (PCIe is full duplex).  Copies ride on two library-owned helper streams forked from / joined to `stream` with
+    // events; kernels stay on the caller's stream.
+    const size_t bytes_in = static_cast<size_t>(d.N) * (ev + 3 * ea + (bwd ? eo : 0));
+    constexpr int kMaxChunks = 8;
+    int chunks = bytes_in > (static_cast<size_t>(32) << 20) ? (d.N < kMaxChunks ? d.N : kMaxChunks) : 1;
+    HelperStreams hs;
+    if (chunks > 1 && !get_helper_streams(&hs)) chunks = 1;
+    cudaEvent_t fork = nullptr, in_done[kMaxChunks] = {}, k_done[kMaxChunks] = {}, out_done = nullptr;
+    if (chunks > 1) {
+        CAPE_TRY(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming), "event")
+        CAPE_TRY(cudaEventCreateWithFlags(&out_done, cudaEventDisableTiming), "event")
+        for (int c = 0; c < chunks; ++c) {
+            CAPE_TRY(cudaEventCreateWithFlags(&in_done[c], cudaEventDisableTiming), "event")
+            CAPE_TRY(cudaEventCreateWithFlags(&k_done[c], cudaEventDisableTiming), "event")
+        }
+        CAPE_TRY(cudaEventRecord(fork, s), "fork")
+        CAPE_TRY(cudaStreamWaitEvent(hs.in, fork, 0), "fork")
+        CAPE_TRY(cudaStreamWaitEvent(hs.out, fork, 0), "fork")
+    }
+    cudaStream_t s_in = chunks > 1 ? hs.in : s, s_out = chunks > 1 ? hs.out : s;
+    const int per = (d.N + chunks - 1) / chunks;
+    for (int c = 0; c < chunks; ++c) {
+        const int n0 = c * per, nc = (n0 + per <= d.N ? per : d.N - n0);
+        if (nc <= 0) break;
+        const size_t o = static_cast<size_t>(n0);
+        CAPE_TRY(cudaMemcpyAsync(ws + p.value + o * ev, reinterpret_cast<const char*>(value_host) + o * ev, nc * ev,
+                                 cudaMemcpyHostToDevice, s_in), "H2D value")
+        CAPE_TRY(cudaMemcpyAsync(ws + p.loc + o * 2 * ea, reinterpret_cast<const char*>(loc_host) + o * 2 * ea,
+                                 nc * 2 * ea, cudaMemcpyHostToDevice, s_in), "H2D sampling_locations")
+        CAPE_TRY(cudaMemcpyAsync(ws + p.attn + o * ea, reinterpret_cast<const char*>(attn_host) + o * ea, nc * ea,
+                                 cudaMemcpyHostToDevice, s_in), "H2D attention_weights")
+        if (bwd)
+            CAPE_TRY(cudaMemcpyAsync(ws + p.gout + o * eo, reinterpret_cast<const char*>(grad_out_host) + o * eo, nc * eo,
+                                     cudaMemcpyHostToDevice, s_in), "H2D grad_out")
+        if (chunks > 1) {
+            CAPE_TRY(cudaEventRecord(in_done[c], s_in), "record")
+            CAPE_TRY(cudaStreamWaitEvent(s, in_done[c], 0), "wait")
+        }
+        cape_msda_dims dc = d;
+        dc.N = nc;
+        rc = cape_msda_forward(ws + p.value + o * ev, reinterpret_cast<const int64_t*>(ws + p.shapes),
+                               reinterpret_cast<const int64_t*>(ws + p.starts), ws + p.loc + o * 2 * ea,
+                               ws + p.attn + o * ea, ws + p.out + o * eo, &dc, CAPE_DTYPE_F32, CAPE_DTYPE_F32, stream);
         if (rc) return rc;
+        if (bwd) {
+            rc = cape_msda_backward(ws + p.gout + o * eo, ws + p.value + o * ev,
+                                    reinterpret_cast<const int64_t*>(ws + p.shapes),
+                                    reinterpret_cast<const int64_t*>(ws + p.starts), ws + p.loc + o * 2 * ea,
+                                    ws + p.attn + o * ea, reinterpret_cast<float*>(ws + p.gvalue + o * ev),
+                                    ws + p.gloc + o * 2 * ea, ws + p.gattn + o * ea, &dc, CAPE_DTYPE_F32, CAPE_DTYPE_F32,
+                                    /*zero_grad_value=*/1, stream);
+            if (rc) return rc;
+        }
+        if (chunks > 1) {
+            CAPE_TRY(cudaEventRecord(k_done[c], s), "record")
+            CAPE_TRY(cudaStreamWaitEvent(s_out, k_done[c], 0), "wait")
+        }
+        CAPE_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(out_host) + o * eo, ws + p.out + o * eo, nc * eo,
+                                 cudaMemcpyDeviceToHost, s_out), "D2H out")
+        if (bwd) {
+            CAPE_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(grad_value_host) + o * ev, ws + p.gvalue + o * ev, nc * ev,
+                                     cudaMemcpyDeviceToHost, s_out), "D2H grad_value")
+            CAPE_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(grad_loc_host) + o * 2 * ea, ws + p.gloc + o * 2 * ea,
+                                     nc * 2 * ea, cudaMemcpyDeviceToHost, s_out), "D2H grad_loc")
+            CAPE_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(grad_attn_host) + o * ea, ws + p.gattn + o * ea, nc * ea,
+                                     cudaMemcpyDeviceToHost, s_out), "D2H grad_attn")
+        }
     }
-    CAPE_COPY(out_host, ws + p.out, no, cudaMemcpyDeviceToHost)
-    if (bwd) {
-        CAPE_COPY(grad_value_host, ws + p.gvalue, nv, cudaMemcpyDeviceToHost)
-        CAPE_COPY(grad_loc_host, ws + p.gloc, na * 2, cudaMemcpyDeviceToHost)
-        CAPE_COPY(grad_attn_host, ws + p.gattn, na, cudaMemcpyDeviceToHost)
+    if (chunks > 1) {   // join: the caller's stream completes only after the last D2H and the last H2D
+        CAPE_TRY(cudaEventRecord(out_done, s_out), "join")
+        CAPE_TRY(cudaStreamWaitEvent(s, out_done, 0), "join")
+        cudaEventDestroy(fork);
+        cudaEventDestroy(out_done);
+        for (int c = 0; c < chunks; ++c) {
+            cudaEventDestroy(in_done[c]);
+            cudaEventDestroy(k_done[c]);
+        }
     }
-#undef CAPE_COPY
+#undef CAPE_TRY
     return 0;
 }
 

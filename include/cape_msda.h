@@ -117,6 +117,10 @@ CAPE_API int cape_msda_decode(const void* value_cache, const int64_t* spatial_sh
  * copies the inputs from (ideally pinned) HOST memory into the caller-provided device workspace, runs forward and,
  * when grad_out_host != NULL, backward, and copies the results back to HOST memory — all enqueued on `stream`.
  * fp32 only.  cape_msda_host_workspace_bytes() gives the device workspace size for `dims`.
+ * Large batches are split into up to 8 chunks along N and software-pipelined: the H2D copy of chunk c+1 and the D2H copy
+ * of chunk c-1 run on two library-owned helper streams (created once per device) while chunk c's kernels run on
+ * `stream`; `stream` is joined to both before the call's work counts as complete, so the caller still only
+ * synchronises `stream`.  This is the one place the library owns CUDA resources (two streams per device).
  */
 CAPE_API size_t cape_msda_host_workspace_bytes(const cape_msda_dims* dims, int with_backward);
 CAPE_API int cape_msda_forward_backward_host(const float* value_host, const int64_t* spatial_shapes_host,

@@ -380,6 +380,36 @@ def test_host_buffer_round_trip_abi():
     assert rc == -6
 
 
+def test_host_buffer_round_trip_pipelined_chunks():
+    """N=6 at the CAPE shape exceeds the 32 MB threshold: the call splits the batch into ragged chunks (2,2,2) on helper
+    streams; results must equal the device-resident op's."""
+    lib = _lib.load()
+    n, lq = 6, 5440
+    inp = synthetic.make_inputs(n, lq, dist="encoder", seed=78)
+    pinned = {k: inp[k].contiguous().pin_memory() for k in ("value", "sampling_locations", "attention_weights",
+                                                             "grad_output")}
+    dims = _lib.Dims(n, 5440, 8, 32, lq, 4, 4)
+    ws_bytes = lib.cape_msda_host_workspace_bytes(ctypes.byref(dims), 1)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    res = [torch.empty(s).pin_memory() for s in ((n, lq, 256), (n, 5440, 8, 32), (n, lq, 8, 4, 4, 2), (n, lq, 8, 4, 4))]
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    stream = torch.cuda.Stream()
+    for _ in range(2):            # second call reuses the helper streams
+        for r in res:
+            r.fill_(float("nan"))
+        rc = lib.cape_msda_forward_backward_host(
+            p(pinned["value"]), p(inp["spatial_shapes"]), p(inp["level_start_index"]), p(pinned["sampling_locations"]),
+            p(pinned["attention_weights"]), p(pinned["grad_output"]), p(res[0]), p(res[1]), p(res[2]), p(res[3]),
+            ctypes.byref(dims), p(ws), ws_bytes, ctypes.c_void_p(stream.cuda_stream))
+        _lib.check(rc, "cape_msda_forward_backward_host")
+        stream.synchronize()      # only the caller's stream is synchronised
+        want = _run_fwd_bwd(inp)
+        assert rel_err(res[0].numpy(), want[0]) == 0.0
+        assert rel_err(res[1].numpy(), want[1]) < 1e-5      # atomics: summation order differs run to run
+        assert rel_err(res[2].numpy(), want[2]) == 0.0
+        assert rel_err(res[3].numpy(), want[3]) == 0.0
+
+
 def test_opcheck_registration():
     inp = synthetic.make_inputs(1, 5, ((4, 4), (2, 2), (1, 1), (1, 1)), device="cuda", seed=3)
     args = (inp["value"].requires_grad_(True), inp["spatial_shapes"], inp["level_start_index"],
