@@ -1,0 +1,210 @@
+"""Host-side mirrors of the callers either side of the op: the deformable encoder
+layer / encoder, the CAPE decoder layer (v1) and its KV cache.  Plain PyTorch host code around ``cape::ms_deform_attn``;
+parameter names, shapes and forward signatures follow the reference so ``state_dict()`` is interchangeable.
+
+    DeformableTransformerEncoderLayer   /root/reference/models/deformable_transformer.py:155-231
+    DeformableTransformerEncoder        /root/reference/models/deformable_transformer.py:232-291
+    TransformerDecoderLayer (v1)        /root/reference/models/deformable_transformer_v2.py:262-370
+    KVCache                             /root/reference/models/kv_cache.py:3-36
+
+Differences from the reference are host-side only: reference points of the encoder are built from a host copy of the
+pyramid (one ``tolist()`` per distinct shapes tensor instead of a device sync per level per call), and the decoder
+layer accepts ``input_pos`` as a Python int so that a decode step needs no device->host read (the reference evaluates
+``input_pos[0] != 0`` on a CUDA tensor for every layer and step, deformable_transformer_v2.py:363).
+"""
+from __future__ import annotations
+
+import copy
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .modules import MSDeformAttn, ValueCache
+
+
+def _activation(name: str):
+    if name == "relu":
+        return F.relu
+    if name == "gelu":
+        return F.gelu
+    if name == "glu":
+        return F.glu
+    raise RuntimeError(f"activation should be relu/gelu, not {name}.")
+
+
+def _clones(module: nn.Module, n: int) -> nn.ModuleList:
+    return nn.ModuleList([copy.deepcopy(module) for _ in range(n)])
+
+
+class KVCache(nn.Module):
+    """Self-attention K/V store for incremental decoding (kv_cache.py:3-36): ``update`` writes the new token at
+    ``input_pos`` and returns the prefix ``[:, :pos+1]``.  Buffers are non-persistent so they never enter checkpoints
+    (the reference's leak into ``state_dict()``)."""
+
+    def __init__(self, max_batch_size, max_seq_length, model_dim, dtype=torch.float32):
+        super().__init__()
+        shape = (max_batch_size, max_seq_length, model_dim)
+        self.register_buffer("k_cache", torch.zeros(shape, dtype=dtype), persistent=False)
+        self.register_buffer("v_cache", torch.zeros(shape, dtype=dtype), persistent=False)
+
+    def update(self, input_pos, k_val, v_val):
+        pos = int(input_pos[0]) if not isinstance(input_pos, int) else input_pos
+        self.k_cache[:, pos:pos + k_val.shape[1]] = k_val
+        self.v_cache[:, pos:pos + v_val.shape[1]] = v_val
+        end = pos + k_val.shape[1]
+        return self.k_cache[:, :end], self.v_cache[:, :end]
+
+
+class DeformableTransformerEncoderLayer(nn.Module):
+    """MSDeformAttn self-attention (query = src + pos, value = src) -> add & norm -> FFN -> add & norm
+    (deformable_transformer.py:212-231)."""
+
+    def __init__(self, d_model=256, d_ffn=1024, dropout=0.1, activation="relu", n_levels=4, n_heads=8, n_points=4):
+        super().__init__()
+        self.self_attn = MSDeformAttn(d_model, n_levels, n_heads, n_points)
+        self.dropout1 = nn.Dropout(dropout)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.linear1 = nn.Linear(d_model, d_ffn)
+        self.activation = _activation(activation)
+        self.dropout2 = nn.Dropout(dropout)
+        self.linear2 = nn.Linear(d_ffn, d_model)
+        self.dropout3 = nn.Dropout(dropout)
+        self.norm2 = nn.LayerNorm(d_model)
+
+    @staticmethod
+    def with_pos_embed(tensor, pos):
+        return tensor if pos is None else tensor + pos
+
+    def forward_ffn(self, src):
+        hidden = self.dropout2(self.activation(self.linear1(src)))
+        return self.norm2(src + self.dropout3(self.linear2(hidden)))
+
+    def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None):
+        attn = self.self_attn(self.with_pos_embed(src, pos), reference_points, src, spatial_shapes, level_start_index,
+                              padding_mask)
+        src = self.norm1(src + self.dropout1(attn))
+        return self.forward_ffn(src)
+
+
+_SHAPES_CACHE: dict = {}
+
+
+def _shapes_as_list(spatial_shapes):
+    """Host copy of the pyramid.  Tensors are read once per (object, version): in CAPE the same shapes tensor is passed
+    to every layer of a forward, so this is one device->host read per model forward instead of one per level per layer."""
+    if not isinstance(spatial_shapes, torch.Tensor):
+        return [(int(h), int(w)) for h, w in spatial_shapes]
+    key = id(spatial_shapes)
+    hit = _SHAPES_CACHE.get(key)
+    if hit is not None and hit[0]() is spatial_shapes and hit[1] == spatial_shapes._version:
+        return hit[2]
+    import weakref
+    as_list = [(int(h), int(w)) for h, w in spatial_shapes.tolist()]
+    if len(_SHAPES_CACHE) > 64:
+        _SHAPES_CACHE.clear()
+    _SHAPES_CACHE[key] = (weakref.ref(spatial_shapes), spatial_shapes._version, as_list)
+    return as_list
+
+
+class DeformableTransformerEncoder(nn.Module):
+    def __init__(self, encoder_layer, num_layers):
+        super().__init__()
+        self.layers = _clones(encoder_layer, num_layers)
+        self.num_layers = num_layers
+
+    @staticmethod
+    def get_reference_points(spatial_shapes, valid_ratios, device):
+        """Pixel centres of every level, normalised by the valid extent, then scaled to every level's valid ratio
+        (deformable_transformer.py:248-271).  Returns (N, S, L, 2)."""
+        per_level = []
+        for lvl, (h, w) in enumerate(_shapes_as_list(spatial_shapes)):
+            ys = torch.linspace(0.5, h - 0.5, h, dtype=torch.float32, device=device)
+            xs = torch.linspace(0.5, w - 0.5, w, dtype=torch.float32, device=device)
+            gy, gx = torch.meshgrid(ys, xs, indexing="ij")
+            gy = gy.reshape(-1)[None] / (valid_ratios[:, None, lvl, 1] * h)
+            gx = gx.reshape(-1)[None] / (valid_ratios[:, None, lvl, 0] * w)
+            per_level.append(torch.stack((gx, gy), -1))
+        points = torch.cat(per_level, 1)
+        return points[:, :, None] * valid_ratios[:, None]
+
+    def forward(self, src, spatial_shapes, level_start_index, valid_ratios, pos=None, padding_mask=None):
+        reference_points = self.get_reference_points(spatial_shapes, valid_ratios, device=src.device)
+        out = src
+        for layer in self.layers:
+            out = layer(out, pos, reference_points, spatial_shapes, level_start_index, padding_mask)
+        return out
+
+
+class TransformerDecoderLayer(nn.Module):
+    """The only decoder layer CAPE can run (v1; deformable_transformer_v2.py:262-370): q/k/v projections, causal
+    self-attention (with KVCache when decoding), support cross-attention over the <=100 support keypoints,
+    MSDeformAttn cross-attention onto the encoder memory, FFN.  Returns ``(tgt, None)`` like the reference."""
+
+    def __init__(self, d_model=256, d_ffn=1024, dropout=0.1, activation="relu", n_levels=4, n_heads=8, n_points=4,
+                 use_qkv_proj=True):
+        super().__init__()
+        self.d_model = d_model
+        if use_qkv_proj:
+            self.attn_q = nn.Linear(d_model, d_model, bias=False)
+            self.attn_k = nn.Linear(d_model, d_model, bias=False)
+            self.attn_v = nn.Linear(d_model, d_model, bias=False)
+        else:
+            self.attn_q = self.attn_k = self.attn_v = nn.Identity()
+        self.self_attn = nn.MultiheadAttention(d_model, n_heads, dropout=dropout)
+        self.dropout2 = nn.Dropout(dropout)
+        self.norm2 = nn.LayerNorm(d_model)
+        self.support_attn = nn.MultiheadAttention(d_model, n_heads, dropout=dropout, batch_first=True)
+        self.dropout_support = nn.Dropout(dropout)
+        self.norm_support = nn.LayerNorm(d_model)
+        self.cross_attn = MSDeformAttn(d_model, n_levels, n_heads, n_points)
+        self.dropout1 = nn.Dropout(dropout)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.linear1 = nn.Linear(d_model, d_ffn)
+        self.activation = _activation(activation)
+        self.dropout3 = nn.Dropout(dropout)
+        self.linear2 = nn.Linear(d_ffn, d_model)
+        self.dropout4 = nn.Dropout(dropout)
+        self.norm3 = nn.LayerNorm(d_model)
+        self.kv_cache = None
+
+    def setup_caches(self, max_batch_size, max_seq_length, dtype=torch.float32, device=None):
+        """What ``DeformableTransformer._setup_caches`` does per layer (deformable_transformer_v2.py:256-259), with a
+        buffer-free value holder instead of ``VCache``."""
+        self.kv_cache = KVCache(max_batch_size, max_seq_length, self.d_model, dtype).to(device)
+        self.cross_attn.cache = ValueCache()
+
+    @staticmethod
+    def with_pos_embed(tensor, pos):
+        return tensor if pos is None else tensor + pos[:, :tensor.size(1)]
+
+    def forward_ffn(self, tgt):
+        hidden = self.dropout3(self.activation(self.linear1(tgt)))
+        return self.norm3(tgt + self.dropout4(self.linear2(hidden)))
+
+    def forward(self, tgt, query_pos, reference_points, src, src_spatial_shapes, level_start_index,
+                src_padding_mask=None, tgt_masks=None, attn_concat_src=False, input_pos=None, support_features=None,
+                support_mask=None):
+        q = self.with_pos_embed(self.attn_q(tgt), query_pos)
+        k = self.attn_k(tgt)
+        v = self.attn_v(tgt)
+        first_pos = None
+        if input_pos is not None:
+            first_pos = input_pos if isinstance(input_pos, int) else int(input_pos[0])
+            if self.kv_cache is not None:
+                k, v = self.kv_cache.update(first_pos, k, v)                                  # :325-328
+        if attn_concat_src:                                                                   # :333-337
+            k = torch.cat([src, k], dim=1)
+            v = torch.cat([src, v], dim=1)
+            tgt_masks = torch.cat([torch.zeros(q.size(1), src.size(1), device=q.device), tgt_masks],
+                                  dim=1).to(dtype=torch.float32)
+        attn = self.self_attn(q.transpose(0, 1), k.transpose(0, 1), v.transpose(0, 1), attn_mask=tgt_masks)[0]
+        tgt = self.norm2(tgt + self.dropout2(attn.transpose(0, 1)))                           # :339-341
+        if support_features is not None:                                                      # :350-357
+            sup = self.support_attn(tgt, support_features, support_features, key_padding_mask=support_mask)[0]
+            tgt = self.norm_support(tgt + self.dropout_support(sup))
+        cross = self.cross_attn(self.with_pos_embed(tgt, query_pos), reference_points, src, src_spatial_shapes,
+                                level_start_index, src_padding_mask,
+                                use_cache=(first_pos is not None and first_pos != 0))         # :360-363
+        tgt = self.norm1(tgt + self.dropout1(cross))
+        return self.forward_ffn(tgt), None

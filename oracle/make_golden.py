@@ -41,6 +41,126 @@ def load_synthetic():
     return mod
 
 
+def load_reference_v2():
+    """models.deformable_transformer_v2 needs the ``models`` package, whose __init__ pulls in pycocotools and timm
+    (absent here): stub them."""
+    import types
+    sys.path.insert(0, REF_ROOT)
+    for name in ("pycocotools", "pycocotools.coco", "pycocotools.mask"):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.COCO = object
+            sys.modules[name] = m
+    if "timm" not in sys.modules:
+        timm = types.ModuleType("timm")
+        layers = types.ModuleType("timm.layers")
+
+        class _Identity(torch.nn.Module):
+            def __init__(self, *a, **k):
+                super().__init__()
+
+            def forward(self, x):
+                return x
+        layers.DropPath = _Identity
+        layers.Mlp = _Identity
+        timm.layers = layers
+        sys.modules["timm"] = timm
+        sys.modules["timm.layers"] = layers
+    for name in ("albumentations", "matplotlib", "matplotlib.pyplot"):
+        if name not in sys.modules:
+            try:
+                __import__(name)
+            except Exception:
+                sys.modules[name] = types.ModuleType(name)
+    import importlib
+    return (importlib.import_module("models.deformable_transformer"),
+            importlib.import_module("models.deformable_transformer_v2"),
+            importlib.import_module("models.kv_cache"))
+
+
+def record_layer_cases(syn):
+    """Encoder stack (deformable_transformer.py:155-291) and decoder layer v1 (deformable_transformer_v2.py:262-370),
+    teacher-forced and token-by-token with the reference's KVCache, dropout 0, seeded weights."""
+    dt, v2, kvc = load_reference_v2()
+    torch.manual_seed(4321)
+    d_model, d_ffn, n_levels, n_heads, n_points = 64, 96, 4, 2, 4
+    shapes = ((6, 8), (3, 4), (2, 2), (1, 2))
+    s = sum(h * w for h, w in shapes)
+    shapes_t = torch.tensor(shapes, dtype=torch.int64)
+    starts_t = torch.tensor(syn.level_start_index(shapes), dtype=torch.int64)
+    n = 2
+
+    def randomise(module):
+        with torch.no_grad():
+            for p in module.parameters():
+                p.add_(torch.randn_like(p) * 0.05)
+
+    # ---- encoder, 2 layers
+    enc = dt.DeformableTransformerEncoder(
+        dt.DeformableTransformerEncoderLayer(d_model, d_ffn, 0.0, "relu", n_levels, n_heads, n_points), 2)
+    randomise(enc)
+    src = torch.randn(n, s, d_model)
+    pos = torch.randn(n, s, d_model) * 0.5
+    valid = torch.ones(n, n_levels, 2)
+    valid[1] = torch.rand(n_levels, 2) * 0.3 + 0.7
+    x = src.clone().requires_grad_(True)
+    out = enc(x, shapes_t, starts_t, valid, pos, None)
+    gout = torch.randn_like(out)
+    gsrc, = torch.autograd.grad(out, x, gout)
+    rec = {"src": src.numpy(), "pos": pos.numpy(), "valid_ratios": valid.numpy(), "spatial_shapes": shapes_t.numpy(),
+           "level_start_index": starts_t.numpy(), "out": out.detach().numpy(), "grad_output": gout.numpy(),
+           "grad_src": gsrc.numpy(), "d_model": d_model, "d_ffn": d_ffn, "n_levels": n_levels, "n_heads": n_heads,
+           "n_points": n_points, "reference_points": enc.get_reference_points(shapes_t, valid, "cpu").numpy()}
+    for k, v in enc.state_dict().items():
+        rec["param." + k] = v.numpy()
+    path = os.path.join(OUT_DIR, "encoder_stack.npz")
+    np.savez_compressed(path, **rec)
+    print(f"encoder_stack: {os.path.getsize(path) / 1024:.1f} KiB")
+
+    # ---- decoder layer v1
+    layer = v2.TransformerDecoderLayer(d_model, d_ffn, 0.0, "relu", n_levels, n_heads, n_points)
+    randomise(layer)
+    layer.eval()
+    t_len, n_sup = 7, 5
+    tgt = torch.randn(n, t_len, d_model)
+    qpos = torch.randn(n, t_len, d_model) * 0.5
+    refp = torch.rand(n, t_len, n_levels, 2)
+    memory = torch.randn(n, s, d_model)
+    sup = torch.randn(n, n_sup, d_model)
+    sup_mask = torch.zeros(n, n_sup, dtype=torch.bool)
+    sup_mask[1, -2:] = True
+    causal = torch.triu(torch.full((t_len, t_len), float("-inf")), diagonal=1)
+    t = tgt.clone().requires_grad_(True)
+    mem = memory.clone().requires_grad_(True)
+    out, _ = layer(t, qpos, refp, mem, shapes_t, starts_t, None, causal, support_features=sup, support_mask=sup_mask)
+    gout = torch.randn_like(out)
+    g_t, g_mem = torch.autograd.grad(out, (t, mem), gout)
+    rec = {"tgt": tgt.numpy(), "query_pos": qpos.numpy(), "reference_points": refp.numpy(), "memory": memory.numpy(),
+           "support_features": sup.numpy(), "support_mask": sup_mask.numpy(), "causal_mask": causal.numpy(),
+           "spatial_shapes": shapes_t.numpy(), "level_start_index": starts_t.numpy(),
+           "out_teacher_forced": out.detach().numpy(), "grad_output": gout.numpy(), "grad_tgt": g_t.numpy(),
+           "grad_memory": g_mem.numpy(), "d_model": d_model, "d_ffn": d_ffn, "n_levels": n_levels, "n_heads": n_heads,
+           "n_points": n_points}
+    # token by token with the reference's own caches (what forward_inference drives, roomformer_v2.py:481-598)
+    layer.kv_cache = kvc.KVCache(n, t_len, d_model, torch.float32)
+    layer.cross_attn.cache = kvc.VCache(n, s, n_heads, d_model // n_heads, torch.float32)
+    steps = []
+    with torch.no_grad():
+        for i in range(t_len):
+            o, _ = layer(tgt[:, i:i + 1], qpos[:, i:i + 1], refp[:, i:i + 1], memory, shapes_t, starts_t, None,
+                         torch.zeros(1, i + 1), input_pos=torch.tensor([i]), support_features=sup, support_mask=sup_mask)
+            steps.append(o)
+    rec["out_incremental"] = torch.cat(steps, 1).numpy()
+    layer.kv_cache = None
+    del layer.cross_attn.cache
+    for k, v in layer.state_dict().items():
+        rec["param." + k] = v.numpy()
+    path = os.path.join(OUT_DIR, "decoder_layer.npz")
+    np.savez_compressed(path, **rec)
+    print(f"decoder_layer: {os.path.getsize(path) / 1024:.1f} KiB; teacher-forced vs incremental max diff "
+          f"{float((out.detach() - torch.cat(steps, 1)).abs().max()):.2e}")
+
+
 def run_reference(ref, value, shapes, loc, attn, gout, dtype):
     v = value.to(dtype).clone().requires_grad_(True)
     l = loc.to(dtype).clone().requires_grad_(True)
@@ -168,6 +288,7 @@ def main():
     record_core_case(ref, "core_d64_p8", syn.make_inputs(
         1, 5, ((4, 4), (2, 2), (1, 1)), n_heads=2, head_dim=64, n_points=8, dist="uniform", seed=5))
     record_module_case(ref, syn)
+    record_layer_cases(syn)
 
 
 if __name__ == "__main__":

@@ -121,3 +121,34 @@ def test_value_cache_protocol_without_buffers():
     assert m._cache_load(3, 4) is None           # batch changed: do not trust the cache
     m.cache = cape_b200.ValueCache()             # _setup_caches attaches a fresh holder every forward_inference
     assert m._cache_load(2, 4) is None
+
+
+def _params(g):
+    return {k[len("param."):]: g[k] for k in g.files if k.startswith("param.")}
+
+
+def test_layer_mirrors_have_the_reference_state_dict_layout():
+    g = np.load(os.path.join(GOLDEN, "encoder_stack.npz"))
+    kw = dict(d_model=int(g["d_model"]), d_ffn=int(g["d_ffn"]), dropout=0.0, n_levels=int(g["n_levels"]),
+              n_heads=int(g["n_heads"]), n_points=int(g["n_points"]))
+    enc = cape_b200.DeformableTransformerEncoder(cape_b200.DeformableTransformerEncoderLayer(**kw), 2)
+    assert {k: tuple(v.shape) for k, v in enc.state_dict().items()} == {k: v.shape for k, v in _params(g).items()}
+    enc.load_state_dict({k: torch.from_numpy(v) for k, v in _params(g).items()})
+    # reference points are host logic: compare on the CPU
+    ref = enc.get_reference_points(torch.from_numpy(g["spatial_shapes"]), torch.from_numpy(g["valid_ratios"]), "cpu")
+    assert torch.allclose(ref, torch.from_numpy(g["reference_points"]), atol=1e-7)
+
+    g = np.load(os.path.join(GOLDEN, "decoder_layer.npz"))
+    layer = cape_b200.TransformerDecoderLayer(**kw)
+    assert {k: tuple(v.shape) for k, v in layer.state_dict().items()} == {k: v.shape for k, v in _params(g).items()}
+    layer.setup_caches(2, 7)
+    assert set(layer.state_dict()) == set(_params(g))          # caches never enter the checkpoint
+
+
+def test_kv_cache_update_returns_prefix():
+    kv = cape_b200.KVCache(2, 5, 4)
+    for i in range(3):
+        k, v = kv.update(torch.tensor([i]), torch.full((2, 1, 4), float(i)), torch.full((2, 1, 4), float(-i)))
+        assert k.shape == (2, i + 1, 4) and float(k[0, i, 0]) == i and float(v[1, i, 3]) == -i
+    k, _ = kv.update(1, torch.full((2, 1, 4), 9.0), torch.zeros(2, 1, 4))      # python-int position
+    assert k.shape == (2, 2, 4) and float(k[0, 1, 0]) == 9.0

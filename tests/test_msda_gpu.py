@@ -410,6 +410,84 @@ def test_host_buffer_round_trip_pipelined_chunks():
         assert rel_err(res[3].numpy(), want[3]) == 0.0
 
 
+def _layer_kwargs(g):
+    return dict(d_model=int(g["d_model"]), d_ffn=int(g["d_ffn"]), dropout=0.0, n_levels=int(g["n_levels"]),
+                n_heads=int(g["n_heads"]), n_points=int(g["n_points"]))
+
+
+def _load_params(module, g):
+    module.load_state_dict({k[len("param."):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("param.")})
+    return module.cuda()
+
+
+def test_encoder_stack_mirror_matches_reference():
+    """2-layer DeformableTransformerEncoder (deformable_transformer.py:155-291) with the reference's weights."""
+    g = np.load(os.path.join(GOLDEN, "encoder_stack.npz"))
+    enc = _load_params(cape_b200.DeformableTransformerEncoder(
+        cape_b200.DeformableTransformerEncoderLayer(**_layer_kwargs(g)), 2), g)
+    x = _cuda(g["src"]).requires_grad_(True)
+    out = enc(x, _cuda(g["spatial_shapes"]), _cuda(g["level_start_index"]), _cuda(g["valid_ratios"]), _cuda(g["pos"]))
+    assert rel_err(out.detach().cpu().numpy(), g["out"]) < FWD_TOL_F32
+    gx, = torch.autograd.grad(out, x, _cuda(g["grad_output"]))
+    assert rel_err(gx.cpu().numpy(), g["grad_src"]) < GRAD_TOL_F32
+
+
+def test_decoder_layer_mirror_teacher_forced_and_incremental():
+    """TransformerDecoderLayer v1 (deformable_transformer_v2.py:262-370): teacher-forced forward/backward, then the same
+    sequence token by token with KV cache + projected-value cache, then one decode step replayed from a CUDA graph."""
+    g = np.load(os.path.join(GOLDEN, "decoder_layer.npz"))
+    layer = _load_params(cape_b200.TransformerDecoderLayer(**_layer_kwargs(g)), g).eval()
+    shapes, starts = _cuda(g["spatial_shapes"]), _cuda(g["level_start_index"])
+    sup, sup_mask = _cuda(g["support_features"]), _cuda(g["support_mask"])
+    qpos, refp = _cuda(g["query_pos"]), _cuda(g["reference_points"])
+    tgt = _cuda(g["tgt"]).requires_grad_(True)
+    mem = _cuda(g["memory"]).requires_grad_(True)
+    out, _ = layer(tgt, qpos, refp, mem, shapes, starts, None, _cuda(g["causal_mask"]), support_features=sup,
+                   support_mask=sup_mask)
+    assert rel_err(out.detach().cpu().numpy(), g["out_teacher_forced"]) < FWD_TOL_F32
+    g_t, g_m = torch.autograd.grad(out, (tgt, mem), _cuda(g["grad_output"]))
+    assert rel_err(g_t.cpu().numpy(), g["grad_tgt"]) < GRAD_TOL_F32
+    assert rel_err(g_m.cpu().numpy(), g["grad_memory"]) < GRAD_TOL_F32
+
+    n, t_len = g["tgt"].shape[:2]
+    layer.setup_caches(n, t_len, device="cuda")
+    tgt, mem = tgt.detach(), mem.detach()
+    steps = []
+    with torch.no_grad():
+        for i in range(t_len):
+            launches = cape_b200.launch_count()
+            o, _ = layer(tgt[:, i:i + 1], qpos[:, i:i + 1], refp[:, i:i + 1], mem, shapes, starts, None,
+                         torch.zeros(1, i + 1, device="cuda"), input_pos=i, support_features=sup, support_mask=sup_mask)
+            assert cape_b200.launch_count() == launches + 1          # one fused sampling kernel per step
+            steps.append(o)
+    inc = torch.cat(steps, 1)
+    assert rel_err(inc.cpu().numpy(), g["out_incremental"]) < FWD_TOL_F32
+    assert layer.cross_attn.cache.get().shape == (n, g["memory"].shape[1], int(g["n_heads"]), 32)
+
+    # CUDA graph: capture the last decode step (static shapes, cached value) and replay it on new token features
+    i = t_len - 1
+    static_tgt = tgt[:, i:i + 1].clone()
+    mask = torch.zeros(1, i + 1, device="cuda")
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side), torch.no_grad():
+        for _ in range(2):          # warm-up outside capture
+            layer(static_tgt, qpos[:, i:i + 1], refp[:, i:i + 1], mem, shapes, starts, None, mask, input_pos=i,
+                  support_features=sup, support_mask=sup_mask)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph), torch.no_grad():
+        static_out, _ = layer(static_tgt, qpos[:, i:i + 1], refp[:, i:i + 1], mem, shapes, starts, None, mask,
+                              input_pos=i, support_features=sup, support_mask=sup_mask)
+    static_tgt.copy_(tgt[:, i:i + 1] * 0.5)
+    graph.replay()
+    with torch.no_grad():
+        eager, _ = layer(tgt[:, i:i + 1] * 0.5, qpos[:, i:i + 1], refp[:, i:i + 1], mem, shapes, starts, None, mask,
+                         input_pos=i, support_features=sup, support_mask=sup_mask)
+    torch.cuda.synchronize()
+    assert torch.allclose(static_out, eager, atol=1e-6, rtol=1e-5)
+
+
 def test_opcheck_registration():
     inp = synthetic.make_inputs(1, 5, ((4, 4), (2, 2), (1, 1), (1, 1)), device="cuda", seed=3)
     args = (inp["value"].requires_grad_(True), inp["spatial_shapes"], inp["level_start_index"],
