@@ -11,7 +11,8 @@ import os
 import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcape_msda.so")
+# CAPE_MSDA_LIB points the loader at another build of the same ABI (used by tools/ for profiling variants).
+LIB_PATH = os.environ.get("CAPE_MSDA_LIB") or os.path.join(HERE, "libcape_msda.so")
 ABI_VERSION = 1
 
 DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2

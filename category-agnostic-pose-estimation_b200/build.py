@@ -41,17 +41,28 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, variant: str = "") -> str:
+    """variant: "" = the product library.  "nored" / "noload" = profiling-only variants of the backward kernel
+    (results invalid; written to tools/, loaded only by tools/tune.py through CAPE_MSDA_LIB)."""
+    global LIB
+    extra = []
+    if variant:
+        extra = {"nored": ["-DCAPE_EXP_NO_RED"], "noload": ["-DCAPE_EXP_NO_LOAD"]}[variant]
+        lib = os.path.join(os.path.dirname(HERE), "tools", f"libcape_msda_{variant}.so")
+        return _compile(lib, extra, verbose, os.path.join(HERE, "build", variant))
     if not force and not _stale():
         return LIB
+    return _compile(LIB, extra, verbose, os.path.join(HERE, "build"))
+
+
+def _compile(LIB: str, extra, verbose: bool, build_dir: str) -> str:
     nvcc = _nvcc()
     objs = []
-    build_dir = os.path.join(HERE, "build")
     os.makedirs(build_dir, exist_ok=True)
     procs = []
     for src in SOURCES:
         obj = os.path.join(build_dir, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)
@@ -71,4 +82,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    variant = ""
+    for a in sys.argv[1:]:
+        if a.startswith("--variant="):
+            variant = a.split("=", 1)[1]
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, variant=variant))

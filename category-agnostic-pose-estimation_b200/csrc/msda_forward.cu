@@ -6,17 +6,22 @@
 // Mapping (fast path, D = 32, P = 4, L <= 4 — the CAPE configuration, train_cape_episodic.py:168-188):
 //   CTA   = one (n, head m) and a run of consecutive queries, so that every warp of the CTA gathers from the same
 //           (n, m) value rows and neighbouring queries share their L1-resident corner rows;
-//   warp  = one query at a time; its 32 lanes are (point p = lane>>3, channel quad k = lane&7): one 16-byte load per
-//           lane fetches the same corner of the 4 points of one level (4 x 128 B rows per warp instruction);
-//   the 32 location floats and 16 weights of a (q, m) are one coalesced 128 B + 64 B load, distributed by shuffles,
-//   and prefetched one query ahead;
-//   the level loop is branch-free (out-of-bounds corners are predicated loads of zero), so the shuffles need no
-//   reconvergence and the 16 corner loads of a query are all in flight together;
-//   the 4 point-partials are folded with two xor-shuffles and lanes 0-7 store the 128 B output row.
+//   warp  = FOUR consecutive queries at a time, one per 8-lane group: lane = (query slot g = lane>>3, channel quad
+//           k = lane&7).  Each group walks its own query's 16 samples; one LDG.128 per lane fetches the same corner of
+//           the 4 queries' current sample (4 x 128 B rows per warp instruction).  A group owns its whole output row, so
+//           there is no cross-lane reduction at the end — the LSU wavefront pipe, which shuffles share with the row
+//           gathers, is what bounds this kernel;
+//   the 32 location floats and 16 weights of a (q, m) are loaded by the query's group (float4 + float2 per lane,
+//           128 B + 64 B coalesced), prefetched one query quad ahead; lane k turns its 4 floats into pixel coordinates
+//           once (sentinel -4 when an axis is fully out of bounds, so validity is two unsigned compares) and the
+//           sample loop distributes them inside the group with 3 shuffles per sample;
+//   out-of-bounds corners are predicated loads into zero-initialised registers (one asm statement per corner so
+//           ptxas does not load-then-select); the loop is branch-free.
 // Measured on B200 (profiles/r01_ubench_gather_scatter.txt) an SM sustains one 128 B row per ~1.7 clk from L1, so the
 // 64 corner rows of a (q, m) bound this kernel well below the HBM roofline; see DESIGN.md.
 // Everything else (other D / P / L) takes the generic kernel: one warp per (n, q, m), lanes strided over channels.
 #include <cstdlib>
+#include <type_traits>
 
 #include "msda_common.cuh"
 #include "msda_launch.h"
@@ -51,7 +56,7 @@ struct FwdLevels {
     }
 };
 
-// One level, 4 points (one per 8-lane group), 4 corners each.  (px, py) are pixel coordinates from pixel_coord().
+// One sample per 8-lane group (4 per warp instruction), 4 corners each.  (px, py) are pixel coordinates from pixel_coord().
 template <typename VT>
 __device__ __forceinline__ void gather_level(const VT* __restrict__ base, int rowStride, int H, int W, float px,
                                              float py, float a, float4& acc) {
@@ -75,42 +80,34 @@ __device__ __forceinline__ void gather_level(const VT* __restrict__ base, int ro
     fma4(aly * lx, v11, acc);
 }
 
-// Per-(q, m) sample table held one float per lane: lane i < 8L holds loc[i] (= [l][p][xy]), lane i < 4L holds attn[i].
-// finish() turns the raw prefetch into pixel coordinates (and, FUSED, first applies the softmax over the 4L logits and
-// loc = ref + off / (W_l, H_l), deformable_transformer.py:100-105) — once per (q, m), one coordinate per lane.
-template <typename AT, int L, bool FUSED>
-struct SampleTable {
-    float loc, attn;
-    __device__ __forceinline__ void fetch(const void* locp, const void* attnp, int64_t qm, int lane) {
-        loc = 0.f;
-        attn = FUSED ? -INFINITY : 0.f;
-        if (FUSED) {
-            const float* o = static_cast<const float*>(locp) + qm * (L * 8);
-            const float* g = static_cast<const float*>(attnp) + qm * (L * 4);
-            if (lane < L * 8) loc = __ldg(o + lane);
-            if (lane < L * 4) attn = __ldg(g + lane);
-        } else {
-            const AT* o = static_cast<const AT*>(locp) + qm * (L * 8);
-            const AT* g = static_cast<const AT*>(attnp) + qm * (L * 4);
-            if (lane < L * 8) loc = to_f32(o[lane]);
-            if (lane < L * 4) attn = to_f32(g[lane]);
-        }
-    }
-    __device__ __forceinline__ void finish(const float* refp, int64_t nq, int lane, float dimf) {
-        if (FUSED) {
-            float mx = attn;
-#pragma unroll
-            for (int s = 8; s >= 1; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFullMask, mx, s));
-            const float e = (lane < L * 4) ? expf(attn - mx) : 0.f;
-            float sum = e;
-#pragma unroll
-            for (int s = 8; s >= 1; s >>= 1) sum += __shfl_xor_sync(kFullMask, sum, s);
-            attn = e / sum;
-            if (lane < L * 8) loc = __ldg(refp + nq * (L * 2) + (lane >> 3) * 2 + (lane & 1)) + loc / dimf;
-        }
-        loc = pixel_coord(loc, dimf);
-    }
+// The sample table of one (q, m), spread over the 8 lanes of the query's group: lane k holds location floats
+// 4k .. 4k+3 (= samples 2k and 2k+1, both of level k >> 1) and weights 2k, 2k+1.
+template <typename AT>
+struct RawSamples {
+    float4 loc;
+    float2 attn;
 };
+
+__device__ __forceinline__ void load_raw(const float* locp, const float* attnp, int64_t qm, int k, int L, bool on,
+                                         RawSamples<float>& r, float pad) {
+    r.loc = make_float4(0.f, 0.f, 0.f, 0.f);
+    r.attn = make_float2(pad, pad);
+    if (on && k < 2 * L) {
+        r.loc = __ldg(reinterpret_cast<const float4*>(locp + qm * (L * 8)) + k);
+        r.attn = __ldg(reinterpret_cast<const float2*>(attnp + qm * (L * 4)) + k);
+    }
+}
+template <typename HT>   // bf16 / fp16 location + weight tensors
+__device__ __forceinline__ void load_raw(const HT* locp, const HT* attnp, int64_t qm, int k, int L, bool on,
+                                         RawSamples<float>& r, float pad) {
+    r.loc = make_float4(0.f, 0.f, 0.f, 0.f);
+    r.attn = make_float2(pad, pad);
+    if (on && k < 2 * L) {
+        r.loc = ld4(locp + qm * (L * 8) + k * 4);
+        const HT* a = attnp + qm * (L * 4) + k * 2;
+        r.attn = make_float2(to_f32(a[0]), to_f32(a[1]));
+    }
+}
 
 // MC: compile-time head count (row stride = MC * 32 elements) or 0 for a run-time stride.
 template <typename VT, typename AT, int L, bool FUSED, int MC>
@@ -120,9 +117,10 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
                      const void* __restrict__ attnp, const float* __restrict__ refp, VT* __restrict__ out, int N, int S,
                      int M_rt, int Lq, int q_per_cta, int q_tiles) {
     constexpr int D = 32;
+    using LT = typename std::conditional<FUSED, float, AT>::type;   // dtype of the location / weight tensors
     const int M = MC ? MC : M_rt;
     const int lane = threadIdx.x & 31, warp = uniform_warp_id(), nwarps = blockDim.x >> 5;
-    const int p = lane >> 3, k = lane & 7;
+    const int g = lane >> 3, k = lane & 7;
     int bid = blockIdx.x;
     const int qt = bid % q_tiles;
     bid /= q_tiles;
@@ -130,33 +128,63 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
     const int rowStride = M * D;
     FwdLevels<VT, L> lv;
     lv.load(shapes, starts, value + (static_cast<int64_t>(n) * S * M + m) * D + k * 4, rowStride);
-    const float dimf = lv.lane_dim(lane);
+    // dimensions of the level whose samples this lane converts (level k >> 1)
+    float ownW = 1.f, ownH = 1.f;
+#pragma unroll
+    for (int l = 0; l < L; ++l)
+        if ((k >> 1) == l) {
+            ownW = static_cast<float>(lv.W[l]);
+            ownH = static_cast<float>(lv.H[l]);
+        }
+    const LT* loc_t = static_cast<const LT*>(locp);
+    const LT* attn_t = static_cast<const LT*>(attnp);
     const int q_end = min(Lq, (qt + 1) * q_per_cta);
-    int q = qt * q_per_cta + warp;
-    if (q >= q_end) return;
-    SampleTable<AT, L, FUSED> cur, nxt;
-    nxt.fetch(locp, attnp, (static_cast<int64_t>(n) * Lq + q) * M + m, lane);
-    for (; q < q_end; q += nwarps) {
+    int qw = qt * q_per_cta + warp * 4;                  // first query of this warp's quad (warp-uniform)
+    if (qw >= q_end) return;
+    const float pad = FUSED ? -INFINITY : 0.f;
+    const int grp = lane & 24;
+    RawSamples<float> cur, nxt;
+    load_raw(loc_t, attn_t, (static_cast<int64_t>(n) * Lq + qw + g) * M + m, k, L, qw + g < q_end, nxt, pad);
+    for (; qw < q_end; qw += nwarps * 4) {
+        const int q = qw + g;                            // this group's query
+        const bool on = q < q_end;
         const int64_t nq = static_cast<int64_t>(n) * Lq + q;
         cur = nxt;
-        if (q + nwarps < q_end) nxt.fetch(locp, attnp, (nq + nwarps) * M + m, lane);
-        cur.finish(refp, nq, lane, dimf);
+        load_raw(loc_t, attn_t, (nq + nwarps * 4) * M + m, k, L, q + nwarps * 4 < q_end, nxt, pad);
+        if (FUSED) {   // softmax over the group's 4L logits; loc = ref + off / (W_l, H_l)  (deformable_transformer.py:100-105)
+            float mx = fmaxf(cur.attn.x, cur.attn.y);
+#pragma unroll
+            for (int s = 4; s >= 1; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFullMask, mx, s));
+            const bool has = on && k < 2 * L;
+            const float e0 = has ? expf(cur.attn.x - mx) : 0.f, e1 = has ? expf(cur.attn.y - mx) : 0.f;
+            float sum = e0 + e1;
+#pragma unroll
+            for (int s = 4; s >= 1; s >>= 1) sum += __shfl_xor_sync(kFullMask, sum, s);
+            cur.attn = make_float2(e0 / sum, e1 / sum);
+            if (has) {
+                const float2 r = __ldg(reinterpret_cast<const float2*>(refp + nq * (L * 2)) + (k >> 1));
+                cur.loc.x = r.x + cur.loc.x / ownW;
+                cur.loc.y = r.y + cur.loc.y / ownH;
+                cur.loc.z = r.x + cur.loc.z / ownW;
+                cur.loc.w = r.y + cur.loc.w / ownH;
+            }
+        }
+        // pixel coordinates of this lane's two samples; a group without a query samples nothing
+        const float px0 = on ? pixel_coord(cur.loc.x, ownW) : -4.f, py0 = on ? pixel_coord(cur.loc.y, ownH) : -4.f;
+        const float px1 = on ? pixel_coord(cur.loc.z, ownW) : -4.f, py1 = on ? pixel_coord(cur.loc.w, ownH) : -4.f;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int l = 0; l < L; ++l) {
-            const float px = __shfl_sync(kFullMask, cur.loc, l * 8 + p * 2);
-            const float py = __shfl_sync(kFullMask, cur.loc, l * 8 + p * 2 + 1);
-            const float a = __shfl_sync(kFullMask, cur.attn, l * 4 + p);
-            gather_level(lv.base[l], rowStride, lv.H[l], lv.W[l], px, py, a, acc);
-        }
 #pragma unroll
-        for (int s = 8; s <= 16; s <<= 1) {
-            acc.x += __shfl_xor_sync(kFullMask, acc.x, s);
-            acc.y += __shfl_xor_sync(kFullMask, acc.y, s);
-            acc.z += __shfl_xor_sync(kFullMask, acc.z, s);
-            acc.w += __shfl_xor_sync(kFullMask, acc.w, s);
+            for (int p = 0; p < 4; ++p) {
+                const int s = l * 4 + p, src = grp | (s >> 1);
+                const float px = __shfl_sync(kFullMask, (s & 1) ? px1 : px0, src);
+                const float py = __shfl_sync(kFullMask, (s & 1) ? py1 : py0, src);
+                const float a = __shfl_sync(kFullMask, (s & 1) ? cur.attn.y : cur.attn.x, src);
+                gather_level(lv.base[l], rowStride, lv.H[l], lv.W[l], px, py, a, acc);
+            }
         }
-        if (p == 0) st4(out + (nq * M + m) * D + k * 4, acc);
+        if (on) st4(out + (nq * M + m) * D + k * 4, acc);
     }
 }
 
@@ -252,7 +280,7 @@ FastGeometry fast_geometry(const cape_msda_dims& d, const char* env_threads, con
     while (q_per_cta > 1 && static_cast<int64_t>(d.N) * d.M * ((d.Lq + q_per_cta - 1) / q_per_cta) < 148 * 4) q_per_cta >>= 1;
     if (q_per_cta > d.Lq) q_per_cta = d.Lq;
     if (q_per_cta < 1) q_per_cta = 1;
-    if (threads > q_per_cta * 32) threads = q_per_cta * 32;
+    if (threads > ((q_per_cta + 3) / 4) * 32) threads = ((q_per_cta + 3) / 4) * 32;   // a warp takes 4 queries at a time
     FastGeometry g;
     g.threads = threads;
     g.q_per_cta = q_per_cta;
