@@ -208,6 +208,106 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+# ---- side measurements (N=1 only; informational keys next to the contract's) -------------------------------------
+def _time_us(fn, reps):
+    import torch
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e3
+
+
+def op_sweep(lib, dev):
+    """BASELINE.json configs[1]: a few points of the op sweep (1k-20k queries, fp32 and bf16 value), raw ABI calls."""
+    import torch
+    import cape_b200
+    from cape_b200 import _lib
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    sp = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    rows = []
+    for n, lq in ((2, 1000), (2, 5440), (2, 20000), (4, 5440), (20, 200)):
+        inp = cape_b200.synthetic.make_inputs(n, lq, dist="encoder", seed=1, device=dev)
+        loc, attn = inp["sampling_locations"], inp["attention_weights"]
+        shapes, starts = inp["spatial_shapes"], inp["level_start_index"]
+        gvalue = torch.empty(inp["value"].shape, device=dev)
+        gloc, gattn = torch.empty_like(loc), torch.empty_like(attn)
+        dims = _lib.Dims(n, 5440, 8, 32, lq, 4, 4)
+        for name, dt, code, ev in (("f32", torch.float32, 0, 4), ("bf16", torch.bfloat16, 1, 2)):
+            value, gout = inp["value"].to(dt), inp["grad_output"].to(dt)
+            out = torch.empty(n, lq, 256, device=dev, dtype=dt)
+            fwd = lambda: _lib.check(lib.cape_msda_forward(p(value), p(shapes), p(starts), p(loc), p(attn), p(out),
+                                                           ctypes.byref(dims), code, 0, sp), "fwd")
+            bwd = lambda: _lib.check(lib.cape_msda_backward(p(gout), p(value), p(shapes), p(starts), p(loc), p(attn),
+                                                            p(gvalue), p(gloc), p(gattn), ctypes.byref(dims), code, 0, 1,
+                                                            sp), "bwd")
+            t_f, t_b = _time_us(fwd, 20), _time_us(bwd, 20)
+            a_f, a_b = cape_b200.synthetic.algorithmic_bytes(n, lq, 5440, e_value=ev)
+            rows.append({"N": n, "Lq": lq, "dtype": name, "fwd_us": round(t_f, 1), "bwd_us": round(t_b, 1),
+                         "gbs": round((a_f + a_b) / (t_f + t_b) / 1e3, 1)})
+    return rows
+
+
+def decode_step(dev):
+    """BASELINE.json configs[3]: one decoder-layer MSDeformAttn call while decoding, 64 episodes x 2 queries (N=128),
+    Lq=1: the mirror module with the projected-value cache + fused prologue vs the same module recomputing the
+    projection every token (what the reference does: its use_cache flag is ignored, deformable_transformer.py:76)."""
+    import torch
+    import cape_b200
+    n = 128
+    torch.manual_seed(0)
+    mod = cape_b200.MSDeformAttn(256, 4, 8, 4).to(dev).eval()
+    with torch.no_grad():
+        for prm in mod.parameters():
+            prm.add_(torch.randn_like(prm) * 0.02)
+    shapes = torch.tensor(cape_b200.synthetic.CAPE_PYRAMID, device=dev)
+    starts = cape_b200.level_start_index_from_shapes(shapes)
+    memory = torch.randn(n, 5440, 256, device=dev)
+    query = torch.randn(n, 1, 256, device=dev)
+    ref = torch.rand(n, 1, 4, 2, device=dev)
+    mod.cache = cape_b200.ValueCache()
+    with torch.no_grad():
+        mod(query, ref, memory, shapes, starts, None, use_cache=False)          # step 0 fills the cache
+        cached = _time_us(lambda: mod(query, ref, memory, shapes, starts, None, use_cache=True), 50)
+        uncached = _time_us(lambda: mod(query, ref, memory, shapes, starts, None, use_cache=False), 10)
+        graph = torch.cuda.CUDAGraph()
+        static_q = query.clone()
+        with torch.cuda.graph(graph):
+            static_out = mod(static_q, ref, memory, shapes, starts, None, use_cache=True)
+        graphed = _time_us(graph.replay, 200)
+    return {"N": n, "Lq": 1, "module_call_us": {"cached_fused": round(cached, 1), "cached_fused_cuda_graph": round(graphed, 1),
+                                                "recompute_value_proj_each_token": round(uncached, 1)},
+            "note": "one MSDeformAttn module call of a decode step; the reference recomputes value_proj over all 5440 "
+                    "memory tokens for every token and layer"}
+
+
+def gpu_eager_baseline(dev, alg_bytes):
+    """The reference's formulation (oracle/msda_torch.py: per-level grid_sample, stack, multiply, sum) run eagerly on this
+    GPU through ATen's CUDA kernels — what a user of the reference sees on the same box.  Baseline only."""
+    import torch
+    import cape_b200
+    from oracle import msda_torch
+    w = WORKLOAD
+    inp = cape_b200.synthetic.make_inputs(w["N"], w["Lq"], dist="encoder", seed=0, device=dev)
+    shapes = inp["spatial_shapes"].tolist()
+    torch.cuda.reset_peak_memory_stats(dev)
+    base = torch.cuda.memory_allocated(dev)
+
+    def step():
+        msda_torch.msda_core_fwd_bwd(inp["value"], shapes, inp["sampling_locations"], inp["attention_weights"],
+                                     inp["grad_output"])
+    t = _time_us(step, 5)
+    peak = torch.cuda.max_memory_allocated(dev) - base
+    return {"value": round(alg_bytes / t / 1e3, 2), "unit": UNIT, "ms_per_step": round(t / 1e3, 3),
+            "peak_extra_memory_mb": round(peak / 2 ** 20), "kind": "port",
+            "sample": "oracle/msda_torch.py on the same B200 (ATen grid_sampler_2d CUDA kernels), full N=20 workload, fp32"}
+
+
 # ---- B200 arm ----------------------------------------------------------------------------------------------------
 def run_b200(args, rank, world, local_rank):
     import torch
@@ -331,6 +431,10 @@ def run_b200(args, rank, world, local_rank):
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
+    if world == 1 and not args.no_extras:
+        line["sweep"] = op_sweep(lib, dev)
+        line["decode"] = decode_step(dev)
+        line["gpu_eager_baseline"] = gpu_eager_baseline(dev, a_fwd + a_bwd)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()
     print(json.dumps(line), flush=True)
@@ -343,6 +447,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the op sweep / decode / eager-GPU side measurements")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
