@@ -19,11 +19,11 @@ from .functional import (MSDeformAttnFunction, level_start_index_from_shapes, ms
                          ms_deform_attn_core_pytorch, ms_deform_attn_decode)
 from .modules import MSDeformAttn, ValueCache
 from .patch import patch_reference, unpatch_reference
-from .layers import (DeformableTransformerEncoder, DeformableTransformerEncoderLayer, KVCache,
+from .layers import (DeformableTransformerEncoder, DeformableTransformerEncoderLayer, IncrementalDecoder, KVCache,
                      TransformerDecoderLayer)
 from . import synthetic
 
 __all__ = ["MSDeformAttn", "ValueCache", "MSDeformAttnFunction", "ms_deform_attn", "ms_deform_attn_core_pytorch",
            "ms_deform_attn_decode", "level_start_index_from_shapes", "patch_reference", "unpatch_reference",
            "library_available", "launch_count", "CapeLibraryError", "synthetic", "DeformableTransformerEncoder",
-           "DeformableTransformerEncoderLayer", "TransformerDecoderLayer", "KVCache"]
+           "DeformableTransformerEncoderLayer", "TransformerDecoderLayer", "KVCache", "IncrementalDecoder"]

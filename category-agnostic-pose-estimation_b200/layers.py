@@ -208,3 +208,109 @@ class TransformerDecoderLayer(nn.Module):
                                 use_cache=(first_pos is not None and first_pos != 0))         # :360-363
         tgt = self.norm1(tgt + self.dropout1(cross))
         return self.forward_ffn(tgt), None
+
+
+class IncrementalDecoder:
+    """Token-by-token driver for a stack of :class:`TransformerDecoderLayer` with STATIC shapes, so that the whole
+    multi-layer decode step is one CUDA graph.
+
+    What the reference does per generated token (``RoomFormerV2.forward_inference`` loop, roomformer_v2.py:481-598, through
+    ``TransformerDecoderLayer.forward``, deformable_transformer_v2.py:320-370): grow the K/V prefix by slicing, run
+    value_proj over all S memory tokens in every layer, and read ``input_pos[0] != 0`` back to the host.  Here, per layer:
+    K/V are written into fixed ``(B, max_len, C)`` buffers at a device-resident position with ``index_copy_`` and the
+    self-attention runs over the full buffer under an additive mask derived from that position; the projected value of
+    the encoder memory is computed once in :meth:`reset`; the MSDeformAttn cross-attention is one fused
+    ``cape::ms_deform_attn_decode`` launch.  Same arithmetic as the eager layer (checked against the reference's own
+    incremental outputs in tests/test_msda_gpu.py); no host synchronisation inside a step.
+    """
+
+    def __init__(self, layers, max_batch_size: int, max_len: int, device, dtype=torch.float32):
+        self.layers = list(layers)
+        self.max_len = max_len
+        self.batch = max_batch_size
+        d_model = self.layers[0].d_model
+        self.device = torch.device(device)
+        z = lambda *shape: torch.zeros(*shape, device=self.device, dtype=dtype)
+        self.k_cache = [z(max_batch_size, max_len, d_model) for _ in self.layers]
+        self.v_cache = [z(max_batch_size, max_len, d_model) for _ in self.layers]
+        self.pos = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.positions = torch.arange(max_len, device=self.device)
+        self.tgt = z(max_batch_size, 1, d_model)
+        self.query_pos = z(max_batch_size, 1, d_model)
+        self.reference_points = None
+        self.values = None
+        self.graph = None
+        self.out = None
+        self._ctx = None
+
+    @torch.no_grad()
+    def reset(self, memory, spatial_shapes, level_start_index, support_features=None, support_mask=None,
+              padding_mask=None):
+        """Start a new batch of sequences: project the encoder memory once per layer (the role of the reference's dead
+        ``VCache``) and forget the previous graph's bindings."""
+        n, s, _ = memory.shape
+        self.values = []
+        for layer in self.layers:
+            ca = layer.cross_attn
+            v = ca.value_proj(memory)
+            if padding_mask is not None:
+                v = v.masked_fill(padding_mask[..., None], 0.0)
+            self.values.append(v.view(n, s, ca.n_heads, ca.d_model // ca.n_heads).contiguous())
+        n_levels = self.layers[0].cross_attn.n_levels
+        self.reference_points = torch.zeros(n, 1, n_levels, 2, device=self.device)
+        self._ctx = (spatial_shapes, level_start_index, support_features, support_mask)
+        self.pos.zero_()
+        self.graph = None
+
+    def _layer_step(self, i, layer, tgt, query_pos, mask):
+        shapes, starts, sup, sup_mask = self._ctx
+        n = tgt.shape[0]
+        q = layer.attn_q(tgt) + query_pos
+        self.k_cache[i][:n].index_copy_(1, self.pos, layer.attn_k(tgt))
+        self.v_cache[i][:n].index_copy_(1, self.pos, layer.attn_v(tgt))
+        attn = layer.self_attn(q.transpose(0, 1), self.k_cache[i][:n].transpose(0, 1),
+                               self.v_cache[i][:n].transpose(0, 1), attn_mask=mask, need_weights=False)[0]
+        tgt = layer.norm2(tgt + attn.transpose(0, 1))
+        if sup is not None:
+            tgt = layer.norm_support(tgt + layer.support_attn(tgt, sup, sup, key_padding_mask=sup_mask,
+                                                              need_weights=False)[0])
+        ca = layer.cross_attn
+        query = tgt + query_pos
+        offsets = ca.sampling_offsets(query).view(n, 1, ca.n_heads, ca.n_levels, ca.n_points, 2)
+        logits = ca.attention_weights(query).view(n, 1, ca.n_heads, ca.n_levels * ca.n_points)
+        sampled = torch.ops.cape.ms_deform_attn_decode(self.values[i], shapes, starts, self.reference_points, offsets,
+                                                       logits)
+        tgt = layer.norm1(tgt + ca.output_proj(sampled))
+        return layer.forward_ffn(tgt)
+
+    def _run(self):
+        n = self.reference_points.shape[0]
+        mask = torch.zeros(1, self.max_len, device=self.device).masked_fill_(
+            (self.positions > self.pos)[None], float("-inf"))
+        x = self.tgt[:n]
+        for i, layer in enumerate(self.layers):
+            x = self._layer_step(i, layer, x, self.query_pos[:n], mask)
+        return x
+
+    @torch.no_grad()
+    def step(self, pos: int, tgt, query_pos, reference_points, use_graph: bool = True):
+        """Decode token ``pos``: tgt / query_pos (B, 1, C), reference_points (B, 1, L, 2).  Returns (B, 1, C); the
+        returned tensor is overwritten by the next step when ``use_graph`` is on."""
+        n = tgt.shape[0]
+        self.tgt[:n].copy_(tgt)
+        self.query_pos[:n].copy_(query_pos)
+        self.reference_points.copy_(reference_points)
+        self.pos.fill_(pos)
+        if not use_graph:
+            return self._run()
+        if self.graph is None:
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                self._run()                       # warm-up outside capture (cuBLAS handles, autotuning)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.out = self._run()
+        self.graph.replay()
+        return self.out

@@ -488,6 +488,83 @@ def test_decoder_layer_mirror_teacher_forced_and_incremental():
     assert torch.allclose(static_out, eager, atol=1e-6, rtol=1e-5)
 
 
+def test_incremental_decoder_one_graph_per_step_matches_reference_incremental_outputs():
+    """IncrementalDecoder (static shapes, whole step in one CUDA graph) against the reference layer's own token-by-token
+    outputs (tests/golden/decoder_layer.npz, produced with the reference's KVCache), eager and graph-replayed, and a
+    2-layer stack against the eager mirror."""
+    g = np.load(os.path.join(GOLDEN, "decoder_layer.npz"))
+    layer = _load_params(cape_b200.TransformerDecoderLayer(**_layer_kwargs(g)), g).eval()
+    shapes, starts = _cuda(g["spatial_shapes"]), _cuda(g["level_start_index"])
+    sup, sup_mask = _cuda(g["support_features"]), _cuda(g["support_mask"])
+    qpos, refp, tgt, mem = _cuda(g["query_pos"]), _cuda(g["reference_points"]), _cuda(g["tgt"]), _cuda(g["memory"])
+    n, t_len = tgt.shape[:2]
+    for use_graph in (False, True):
+        dec = cape_b200.IncrementalDecoder([layer], n, t_len + 3, "cuda")     # max_len > sequence: masked tail
+        dec.reset(mem, shapes, starts, sup, sup_mask)
+        steps = []
+        for i in range(t_len):
+            before = cape_b200.launch_count()
+            o = dec.step(i, tgt[:, i:i + 1], qpos[:, i:i + 1], refp[:, i:i + 1], use_graph=use_graph)
+            steps.append(o.clone())
+            if not use_graph:
+                assert cape_b200.launch_count() == before + 1
+        inc = torch.cat(steps, 1)
+        assert rel_err(inc.cpu().numpy(), g["out_incremental"]) < FWD_TOL_F32, use_graph
+    # two layers: graph replay == eager mirror layers driven with python-int positions
+    layer2 = _load_params(cape_b200.TransformerDecoderLayer(**_layer_kwargs(g)), g).eval()
+    with torch.no_grad():
+        for prm in layer2.parameters():
+            prm.mul_(1.1)
+    stack = [layer, layer2]
+    dec = cape_b200.IncrementalDecoder(stack, n, t_len, "cuda")
+    dec.reset(mem, shapes, starts, sup, sup_mask)
+    for l in stack:
+        l.setup_caches(n, t_len, device="cuda")
+    with torch.no_grad():
+        for i in range(t_len):
+            got = dec.step(i, tgt[:, i:i + 1], qpos[:, i:i + 1], refp[:, i:i + 1])
+            x = tgt[:, i:i + 1]
+            for l in stack:
+                x, _ = l(x, qpos[:, i:i + 1], refp[:, i:i + 1], mem, shapes, starts, None,
+                         torch.zeros(1, i + 1, device="cuda"), input_pos=i, support_features=sup, support_mask=sup_mask)
+            assert torch.allclose(got, x, atol=2e-5, rtol=1e-4), i
+
+
+def test_nccl_flat_grad_allreduce_two_gpus():
+    """The one collective a data-parallel CAPE step needs, over NCCL (needs >= 2 GPUs; the CPU suite covers gloo)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import subprocess
+    import sys
+    code = (
+        "import os, torch, torch.distributed as dist, sys\n"
+        "sys.path.insert(0, os.environ['CAPE_REPO'])\n"
+        "from cape_b200 import dist as cdist\n"
+        "r, w, lr = cdist.init_from_env('nccl')\n"
+        "dev = torch.device('cuda', lr)\n"
+        "torch.manual_seed(0)\n"
+        "m = torch.nn.Linear(8, 4).to(dev)\n"
+        "unused = torch.nn.Parameter(torch.ones(3, device=dev))\n"
+        "m(torch.full((2, 8), float(r + 1), device=dev)).sum().backward()\n"
+        "local = m.weight.grad.clone()\n"
+        "cdist.FlatGradAllreduce(list(m.parameters()) + [unused])()\n"
+        "want = local.clone(); dist.all_reduce(want); want /= w\n"
+        "assert torch.allclose(m.weight.grad, want) and unused.grad is None\n"
+        "assert cdist.max_over_ranks(float(r), dev) == w - 1\n"
+        "cdist.barrier(dev); dist.destroy_process_group(); print('rank', r, 'ok')\n")
+    import tempfile
+    env = dict(os.environ, CAPE_REPO=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    with tempfile.NamedTemporaryFile("w", suffix="_nccl_worker.py", delete=False) as f:
+        f.write(code)
+        script = f.name
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", script], env=env,
+                         capture_output=True, text=True, timeout=300)
+    os.unlink(script)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("ok") == 2
+
+
 def test_opcheck_registration():
     inp = synthetic.make_inputs(1, 5, ((4, 4), (2, 2), (1, 1), (1, 1)), device="cuda", seed=3)
     args = (inp["value"].requires_grad_(True), inp["spatial_shapes"], inp["level_start_index"],
