@@ -247,20 +247,36 @@ class IncrementalDecoder:
     def reset(self, memory, spatial_shapes, level_start_index, support_features=None, support_mask=None,
               padding_mask=None):
         """Start a new batch of sequences: project the encoder memory once per layer (the role of the reference's dead
-        ``VCache``) and forget the previous graph's bindings."""
+        ``VCache``).  Everything a step reads lives in buffers owned by this object, so the captured graph survives
+        across batches of the same shape (only a change of batch size, memory length or support length re-captures)."""
         n, s, _ = memory.shape
-        self.values = []
-        for layer in self.layers:
+        n_levels = self.layers[0].cross_attn.n_levels
+        sig = (n, s, None if support_features is None else tuple(support_features.shape), support_mask is not None)
+        if sig != getattr(self, "_sig", None):
+            ca0 = self.layers[0].cross_attn
+            self.values = [torch.empty(n, s, ca0.n_heads, ca0.d_model // ca0.n_heads, device=self.device,
+                                       dtype=memory.dtype) for _ in self.layers]
+            self.reference_points = torch.zeros(n, 1, n_levels, 2, device=self.device)
+            self._shapes = torch.empty(n_levels, 2, dtype=torch.int64, device=self.device)
+            self._starts = torch.empty(n_levels, dtype=torch.int64, device=self.device)
+            self._sup = None if support_features is None else torch.empty_like(support_features)
+            self._sup_mask = None if support_mask is None else torch.empty_like(support_mask)
+            self._sig = sig
+            self.graph = None
+        for layer, dst in zip(self.layers, self.values):
             ca = layer.cross_attn
             v = ca.value_proj(memory)
             if padding_mask is not None:
                 v = v.masked_fill(padding_mask[..., None], 0.0)
-            self.values.append(v.view(n, s, ca.n_heads, ca.d_model // ca.n_heads).contiguous())
-        n_levels = self.layers[0].cross_attn.n_levels
-        self.reference_points = torch.zeros(n, 1, n_levels, 2, device=self.device)
-        self._ctx = (spatial_shapes, level_start_index, support_features, support_mask)
+            dst.copy_(v.view(dst.shape))
+        self._shapes.copy_(spatial_shapes)
+        self._starts.copy_(level_start_index)
+        if self._sup is not None:
+            self._sup.copy_(support_features)
+        if self._sup_mask is not None:
+            self._sup_mask.copy_(support_mask)
+        self._ctx = (self._shapes, self._starts, self._sup, self._sup_mask)
         self.pos.zero_()
-        self.graph = None
 
     def _layer_step(self, i, layer, tgt, query_pos, mask):
         shapes, starts, sup, sup_mask = self._ctx
