@@ -16,7 +16,7 @@ CPU, eager or Triton fallback: calling an op without the built library, or with 
 from . import _lib
 from ._lib import CapeLibraryError, available as library_available, launch_count
 from .functional import (MSDeformAttnFunction, level_start_index_from_shapes, ms_deform_attn,
-                         ms_deform_attn_core_pytorch, ms_deform_attn_decode)
+                         ms_deform_attn_core_pytorch, ms_deform_attn_decode, ms_deform_attn_fused)
 from .modules import MSDeformAttn, ValueCache
 from .patch import patch_reference, unpatch_reference
 from .layers import (DeformableTransformerEncoder, DeformableTransformerEncoderLayer, IncrementalDecoder, KVCache,
@@ -24,6 +24,6 @@ from .layers import (DeformableTransformerEncoder, DeformableTransformerEncoderL
 from . import synthetic
 
 __all__ = ["MSDeformAttn", "ValueCache", "MSDeformAttnFunction", "ms_deform_attn", "ms_deform_attn_core_pytorch",
-           "ms_deform_attn_decode", "level_start_index_from_shapes", "patch_reference", "unpatch_reference",
+           "ms_deform_attn_decode", "ms_deform_attn_fused", "level_start_index_from_shapes", "patch_reference", "unpatch_reference",
            "library_available", "launch_count", "CapeLibraryError", "synthetic", "DeformableTransformerEncoder",
            "DeformableTransformerEncoderLayer", "TransformerDecoderLayer", "KVCache", "IncrementalDecoder"]

@@ -40,6 +40,8 @@ _SIGNATURES = {
     "cape_msda_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(Dims), _i, _i, _vp]),
     "cape_msda_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(Dims), _i, _i, _i, _vp]),
     "cape_msda_decode": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(Dims), _i, _vp]),
+    "cape_msda_fused_supported": (_i, [ctypes.POINTER(Dims)]),
+    "cape_msda_fused_backward": (_i, [_vp] * 10 + [ctypes.POINTER(Dims), _i, _i, _vp]),
     "cape_msda_host_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(Dims), _i]),
     "cape_msda_forward_backward_host": (_i, [_vp] * 10 + [ctypes.POINTER(Dims), _vp, ctypes.c_size_t, _vp]),
 }

@@ -154,6 +154,8 @@ int cape_msda_backward(const void* grad_out, const void* value, const int64_t* s
     a.d = *dims;
     a.value_dtype = value_dtype;
     a.aux_dtype = aux_dtype;
+    a.fused = false;
+    a.ref_points = nullptr;
     const cudaError_t e = launch_backward(a, s);
     return e == cudaSuccess ? 0 : fail_cuda(e, "cape_msda_backward launch");
 }
@@ -167,7 +169,7 @@ int cape_msda_decode(const void* value_cache, const int64_t* spatial_shapes_dev,
     if ((rc = check_ptr(value_cache, "value_cache", empty || dims->S == 0)) ||
         (rc = check_ptr(spatial_shapes_dev, "spatial_shapes", false, 8)) ||
         (rc = check_ptr(level_start_index_dev, "level_start_index", false, 8)) ||
-        (rc = check_ptr(reference_points, "reference_points", empty)) ||
+        (rc = check_ptr(reference_points, "reference_points", empty, 8)) ||
         (rc = check_ptr(sampling_offsets, "sampling_offsets", empty)) ||
         (rc = check_ptr(attention_logits, "attention_logits", empty)) || (rc = check_ptr(out, "out", empty)))
         return rc;
@@ -186,6 +188,56 @@ int cape_msda_decode(const void* value_cache, const int64_t* spatial_shapes_dev,
     a.fused = true;
     const cudaError_t e = launch_forward(a, static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? 0 : fail_cuda(e, "cape_msda_decode launch");
+}
+
+int cape_msda_fused_supported(const cape_msda_dims* dims) {
+    return dims && dims->D == 32 && dims->P == 4 && dims->L >= 1 && dims->L <= 4;
+}
+
+int cape_msda_fused_backward(const void* grad_out, const void* value, const int64_t* spatial_shapes_dev,
+                             const int64_t* level_start_index_dev, const float* reference_points,
+                             const float* sampling_offsets, const float* attention_logits, float* grad_value,
+                             float* grad_offsets, float* grad_logits, const cape_msda_dims* dims, int value_dtype,
+                             int zero_grad_value, void* stream) {
+    int rc;
+    if ((rc = check_dims(dims)) || (rc = check_dtypes(value_dtype, CAPE_DTYPE_F32))) return rc;
+    if (!cape_msda_fused_supported(dims))
+        return fail(CAPE_ERR_BAD_DIMS, "the fused prologue needs D=32, P=4, L<=4 (got D=%d P=%d L=%d)", dims->D, dims->P,
+                    dims->L);
+    const bool empty = dims->N == 0 || dims->Lq == 0;
+    const bool no_value = dims->N == 0 || dims->S == 0;
+    if ((rc = check_ptr(grad_out, "grad_out", empty)) || (rc = check_ptr(value, "value", empty || no_value)) ||
+        (rc = check_ptr(spatial_shapes_dev, "spatial_shapes", false, 8)) ||
+        (rc = check_ptr(level_start_index_dev, "level_start_index", false, 8)) ||
+        (rc = check_ptr(reference_points, "reference_points", empty, 8)) ||
+        (rc = check_ptr(sampling_offsets, "sampling_offsets", empty)) ||
+        (rc = check_ptr(attention_logits, "attention_logits", empty)) || (rc = check_ptr(grad_value, "grad_value", no_value)) ||
+        (rc = check_ptr(grad_offsets, "grad_offsets", empty)) || (rc = check_ptr(grad_logits, "grad_logits", empty)))
+        return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (zero_grad_value && !no_value) {
+        const size_t bytes = static_cast<size_t>(dims->N) * dims->S * dims->M * dims->D * sizeof(float);
+        const cudaError_t e = cudaMemsetAsync(grad_value, 0, bytes, s);
+        if (e != cudaSuccess) return fail_cuda(e, "cape_msda_fused_backward memset(grad_value)");
+    }
+    if (empty) return 0;
+    BwdArgs a{};
+    a.grad_out = grad_out;
+    a.value = value;
+    a.shapes = spatial_shapes_dev;
+    a.starts = level_start_index_dev;
+    a.loc = sampling_offsets;
+    a.attn = attention_logits;
+    a.ref_points = reference_points;
+    a.grad_value = grad_value;
+    a.grad_loc = grad_offsets;
+    a.grad_attn = grad_logits;
+    a.d = *dims;
+    a.value_dtype = value_dtype;
+    a.aux_dtype = CAPE_DTYPE_F32;
+    a.fused = true;
+    const cudaError_t e = launch_backward(a, s);
+    return e == cudaSuccess ? 0 : fail_cuda(e, "cape_msda_fused_backward launch");
 }
 
 // ---- host-buffer round trip ------------------------------------------------------------------------------------

@@ -98,12 +98,18 @@ __device__ __forceinline__ void scatter_level(const VT* __restrict__ vbase, floa
     gy = hx * (d10 - d00) + lx * (d11 - d01);
 }
 
-template <typename VT, typename AT, int L, int MC>
+// FUSED = false: locp / attnp are sampling_locations / attention_weights, outputs grad_loc / grad_attn.
+// FUSED = true : the module prologue is part of the op (deformable_transformer.py:100-105): locp / attnp are the raw
+//                sampling offsets and attention logits (fp32), refp the reference points; the kernel recomputes
+//                attn = softmax(logits) and loc = ref + off / (W_l, H_l), and writes grad_offsets = grad_loc / (W_l, H_l)
+//                and grad_logits = attn * (grad_attn - sum_j attn_j grad_attn_j) instead, so sampling_locations,
+//                attention_weights and their gradients never exist in HBM.
+template <typename VT, typename AT, int L, int MC, bool FUSED>
 __global__ void __launch_bounds__(kBwdMaxThreads)
 msda_bwd_fast_kernel(const VT* __restrict__ gout, const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                      const int64_t* __restrict__ starts, const AT* __restrict__ locp, const AT* __restrict__ attnp,
-                     float* __restrict__ gvalue, AT* __restrict__ gloc, AT* __restrict__ gattn, int N, int S, int M_rt,
-                     int Lq, int q_per_cta, int q_tiles) {
+                     const float* __restrict__ refp, float* __restrict__ gvalue, AT* __restrict__ gloc,
+                     AT* __restrict__ gattn, int N, int S, int M_rt, int Lq, int q_per_cta, int q_tiles) {
     constexpr int D = 32;
     const int M = MC ? MC : M_rt;
     const int lane = threadIdx.x & 31, warp = uniform_warp_id(), nwarps = blockDim.x >> 5;
@@ -122,12 +128,24 @@ msda_bwd_fast_kernel(const VT* __restrict__ gout, const VT* __restrict__ value, 
     const int q_end = min(Lq, (qt + 1) * q_per_cta);
     for (int q = qt * q_per_cta + warp; q < q_end; q += nwarps) {
         const int64_t qm = (static_cast<int64_t>(n) * Lq + q) * M + m;
-        float locv = 0.f, attnv = 0.f;
+        float locv = 0.f, attnv = FUSED ? -INFINITY : 0.f;
         if (lane < L * 8) locv = to_f32(locp[qm * (L * 8) + lane]);
         if (lane < L * 4) attnv = to_f32(attnp[qm * (L * 4) + lane]);
         const float4 g = ld4(gout + qm * D + k * 4);
+        if (FUSED) {   // softmax over the 4L logits (lanes 0 .. 4L-1) and loc = ref + off / dim
+            float mx = attnv;
+#pragma unroll
+            for (int s = 8; s >= 1; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFullMask, mx, s));
+            const float e = (lane < L * 4) ? expf(attnv - mx) : 0.f;
+            float sum = e;
+#pragma unroll
+            for (int s = 8; s >= 1; s >>= 1) sum += __shfl_xor_sync(kFullMask, sum, s);
+            attnv = e / sum;
+            if (lane < L * 8)
+                locv = __ldg(refp + (static_cast<int64_t>(n) * Lq + q) * (L * 2) + (lane >> 3) * 2 + (lane & 1)) + locv / dimf;
+        }
         locv = pixel_coord(locv, dimf);
-        float r_ga = 0.f, r_gx = 0.f, r_gy = 0.f;
+        float r_ga = 0.f, r_gx = 0.f, r_gy = 0.f, r_a = 0.f;
 #pragma unroll
         for (int l = 0; l < L; ++l) {
             const float px = __shfl_sync(kFullMask, locv, l * 8 + p * 2);
@@ -143,9 +161,17 @@ msda_bwd_fast_kernel(const VT* __restrict__ gout, const VT* __restrict__ value, 
             }
             if (k == l) {
                 r_ga = ga;
-                r_gx = a * static_cast<float>(lv.W[l]) * gx;
-                r_gy = a * static_cast<float>(lv.H[l]) * gy;
+                r_a = a;
+                // d loc / d offset = 1 / dim cancels the dim factor of d pixel / d loc
+                r_gx = FUSED ? a * gx : a * static_cast<float>(lv.W[l]) * gx;
+                r_gy = FUSED ? a * gy : a * static_cast<float>(lv.H[l]) * gy;
             }
+        }
+        if (FUSED) {   // softmax backward over the (q, m)'s 4L samples, held by lanes (p, k < L)
+            float dot = (k < L) ? r_a * r_ga : 0.f;
+#pragma unroll
+            for (int s = 16; s >= 1; s >>= 1) dot += __shfl_xor_sync(kFullMask, dot, s);
+            r_ga = r_a * (r_ga - dot);
         }
         if (k < L) {   // lane (p, k) owns sample (level k, point p)
             const int si = k * 4 + p;
@@ -221,7 +247,7 @@ msda_bwd_generic_kernel(const VT* __restrict__ gout, const VT* __restrict__ valu
     }
 }
 
-template <typename VT, typename AT>
+template <typename VT, typename AT, bool FUSED>
 cudaError_t launch_typed(const BwdArgs& a, cudaStream_t stream) {
     const cape_msda_dims& d = a.d;
     const int64_t total_qm = static_cast<int64_t>(d.N) * d.Lq * d.M;
@@ -249,13 +275,13 @@ cudaError_t launch_typed(const BwdArgs& a, cudaStream_t stream) {
 #define CAPE_BWD_CASE(LL)                                                                                          \
     case LL:                                                                                                       \
         if (d.M == 8)                                                                                              \
-            msda_bwd_fast_kernel<VT, AT, LL, 8><<<gdim, b, 0, stream>>>(gout, value, a.shapes, a.starts, loc, attn, \
-                                                                        a.grad_value, gloc, gattn, d.N, d.S, d.M,  \
-                                                                        d.Lq, q_per_cta, q_tiles);                 \
+            msda_bwd_fast_kernel<VT, AT, LL, 8, FUSED><<<gdim, b, 0, stream>>>(                                     \
+                gout, value, a.shapes, a.starts, loc, attn, a.ref_points, a.grad_value, gloc, gattn, d.N, d.S, d.M,  \
+                d.Lq, q_per_cta, q_tiles);                                                                         \
         else                                                                                                       \
-            msda_bwd_fast_kernel<VT, AT, LL, 0><<<gdim, b, 0, stream>>>(gout, value, a.shapes, a.starts, loc, attn, \
-                                                                        a.grad_value, gloc, gattn, d.N, d.S, d.M,  \
-                                                                        d.Lq, q_per_cta, q_tiles);                 \
+            msda_bwd_fast_kernel<VT, AT, LL, 0, FUSED><<<gdim, b, 0, stream>>>(                                     \
+                gout, value, a.shapes, a.starts, loc, attn, a.ref_points, a.grad_value, gloc, gattn, d.N, d.S, d.M,  \
+                d.Lq, q_per_cta, q_tiles);                                                                         \
         break;
         switch (d.L) {
             CAPE_BWD_CASE(1)
@@ -265,6 +291,7 @@ cudaError_t launch_typed(const BwdArgs& a, cudaStream_t stream) {
         }
 #undef CAPE_BWD_CASE
     } else {
+        if (FUSED) return cudaErrorNotSupported;   // the fused prologue exists on the fast path only (ABI checks dims)
         const int warps = 4;
         const int64_t grid = (total_qm + warps - 1) / warps;
         if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
@@ -278,8 +305,9 @@ cudaError_t launch_typed(const BwdArgs& a, cudaStream_t stream) {
 
 template <typename VT>
 cudaError_t launch_value_typed(const BwdArgs& a, cudaStream_t stream) {
-    if (a.aux_dtype == CAPE_DTYPE_F32) return launch_typed<VT, float>(a, stream);
-    return launch_typed<VT, VT>(a, stream);
+    if (a.fused) return launch_typed<VT, float, true>(a, stream);
+    if (a.aux_dtype == CAPE_DTYPE_F32) return launch_typed<VT, float, false>(a, stream);
+    return launch_typed<VT, VT, false>(a, stream);
 }
 
 }  // namespace

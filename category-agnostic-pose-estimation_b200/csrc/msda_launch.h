@@ -34,14 +34,16 @@ struct BwdArgs {
     const void* value;
     const int64_t* shapes;
     const int64_t* starts;
-    const void* loc;
-    const void* attn;
+    const void* loc;          // direct: sampling_locations; fused: sampling_offsets
+    const void* attn;         // direct: attention_weights;  fused: attention_logits
+    const float* ref_points;  // fused only
     float* grad_value;
-    void* grad_loc;
-    void* grad_attn;
+    void* grad_loc;           // fused: grad_sampling_offsets
+    void* grad_attn;          // fused: grad_attention_logits
     cape_msda_dims d;
     int value_dtype;
     int aux_dtype;
+    bool fused;
 };
 
 // Each returns cudaGetLastError() after the launch and bumps the launch counter.

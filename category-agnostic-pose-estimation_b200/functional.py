@@ -11,7 +11,10 @@ import torch
 
 from . import ops  # noqa: F401  (registers torch.ops.cape.*)
 
-__all__ = ["ms_deform_attn", "ms_deform_attn_core_pytorch", "ms_deform_attn_decode", "MSDeformAttnFunction",
+ms_deform_attn_fused = None   # bound below: same callable as ms_deform_attn_decode, named for its training use
+
+__all__ = ["ms_deform_attn", "ms_deform_attn_core_pytorch", "ms_deform_attn_decode", "ms_deform_attn_fused",
+           "MSDeformAttnFunction",
            "level_start_index_from_shapes"]
 
 
@@ -49,13 +52,17 @@ def ms_deform_attn_core_pytorch(value, value_spatial_shapes, sampling_locations,
 
 def ms_deform_attn_decode(value_cache, spatial_shapes, level_start_index, reference_points, sampling_offsets,
                           attention_logits):
-    """Incremental decode on a cached projected value; fuses softmax and ``ref + off/(W,H)`` (:100-105) with the
-    sampling.  Inference only (no autograd)."""
+    """The module-level fused op: softmax over the logits and ``ref + off/(W,H)`` (:100-105) inside the sampling kernel.
+    Used for the decode step (cached projected value, one new token) and — it is differentiable w.r.t. value,
+    reference_points, sampling_offsets and attention_logits — for training."""
     spatial_shapes = _shapes_tensor(spatial_shapes, value_cache.device)
     if level_start_index is None:
         level_start_index = level_start_index_from_shapes(spatial_shapes)
     return torch.ops.cape.ms_deform_attn_decode(value_cache, spatial_shapes, level_start_index, reference_points,
                                                 sampling_offsets, attention_logits)
+
+
+ms_deform_attn_fused = ms_deform_attn_decode
 
 
 class MSDeformAttnFunction:

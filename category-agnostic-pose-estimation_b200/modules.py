@@ -11,8 +11,9 @@ Differences are confined to *how* the result is computed:
   held in the ``VCache`` the reference attaches as ``self.cache`` (``deformable_transformer_v2.py:259``,
   ``kv_cache.py:37-70``), or in a :class:`ValueCache` the caller attaches the same way.  The cross-attention memory is fixed during
   decoding, so this is exact (SURVEY.md Appendix C);
-* under ``torch.no_grad()`` with 2-d reference points the softmax / location arithmetic (:100-105) is fused into the
-  sampling kernel (``cape::ms_deform_attn_decode``).
+* with 2-d reference points the softmax / location arithmetic (:100-105) is fused into the sampling kernels, forward
+  and backward (``cape::ms_deform_attn_decode`` and its autograd), so ``sampling_locations`` / ``attention_weights``
+  never round-trip HBM; ``module.fuse_prologue = False`` restores the reference's materialised form.
 """
 from __future__ import annotations
 
@@ -65,6 +66,7 @@ class MSDeformAttn(nn.Module):
         self.value_proj = nn.Linear(d_model, d_model)
         self.output_proj = nn.Linear(d_model, d_model)
         self._value_cache = None       # identity of the cache holder we last filled (plain attribute, not a buffer)
+        self.fuse_prologue = True      # False: materialise sampling_locations / attention_weights like the reference
         self._reset_parameters()
 
     def _reset_parameters(self):
@@ -134,10 +136,10 @@ class MSDeformAttn(nn.Module):
         if reference_points.shape[-1] not in (2, 4):                                        # :109-111
             raise ValueError("Last dim of reference_points must be 2 or 4, but get {} instead.".format(
                 reference_points.shape[-1]))
-        if (reference_points.shape[-1] == 2 and not torch.is_grad_enabled() and value.is_cuda
-                and not torch.is_autocast_enabled()):
-            output = CF.ms_deform_attn_decode(value, input_spatial_shapes, input_level_start_index,
-                                              reference_points, sampling_offsets, attention_logits)
+        if reference_points.shape[-1] == 2 and value.is_cuda and self.fuse_prologue:
+            # softmax (:100-101) and ref + off / (W_l, H_l) (:102-105) run inside the sampling kernel, forward and backward
+            output = CF.ms_deform_attn_fused(value, input_spatial_shapes, input_level_start_index, reference_points,
+                                             sampling_offsets, attention_logits)
             return self.output_proj(output)
         attention_weights = F.softmax(attention_logits, -1).view(
             N, Len_q, self.n_heads, self.n_levels, self.n_points)                           # :101

@@ -5,6 +5,13 @@
                                   attention_weights) -> (grad_value, grad_sampling_loc, grad_attn_weight)
     cape::ms_deform_attn_decode(value_cache, spatial_shapes, level_start_index, reference_points,
                                 sampling_offsets, attention_logits) -> out
+    cape::ms_deform_attn_fused_backward(grad_out, value, spatial_shapes, level_start_index, reference_points,
+                                        sampling_offsets, attention_logits) -> (grad_value, grad_offsets, grad_logits)
+
+``ms_deform_attn_decode`` is the module-level fused op: softmax over the L*P logits and ``ref + off / (W_l, H_l)``
+(``/root/reference/models/deformable_transformer.py:100-105``) happen inside the sampling kernel.  It serves the decode
+step (one new token on a cached projected value) and, being differentiable, the training path of the module too —
+``sampling_locations`` / ``attention_weights`` and their gradients then never exist in HBM.
 
 The argument order is upstream Deformable-DETR's ``MSDeformAttnFunction`` (what the reference's vestigial
 ``im2col_step`` at ``/root/reference/models/deformable_transformer.py:51`` was for); semantics are those of
@@ -179,3 +186,66 @@ def ms_deform_attn_decode(value_cache: torch.Tensor, spatial_shapes: torch.Tenso
 def _(value_cache, spatial_shapes, level_start_index, reference_points, sampling_offsets, attention_logits):
     b, k = sampling_offsets.shape[:2]
     return value_cache.new_empty((b, k, value_cache.shape[2] * value_cache.shape[3]))
+
+
+@torch.library.custom_op("cape::ms_deform_attn_fused_backward", mutates_args=(), device_types="cuda")
+def ms_deform_attn_fused_backward(grad_out: torch.Tensor, value: torch.Tensor, spatial_shapes: torch.Tensor,
+                                  level_start_index: torch.Tensor, reference_points: torch.Tensor,
+                                  sampling_offsets: torch.Tensor, attention_logits: torch.Tensor
+                                  ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    lib = _lib.load()
+    b, k, m, l, p, _ = sampling_offsets.shape
+    value = value.contiguous()
+    dims = _lib.Dims(b, value.shape[1], m, value.shape[3], k, l, p)
+    shapes = _meta(spatial_shapes, value.device)
+    starts = _meta(level_start_index, value.device)
+    ref = reference_points.float().contiguous()
+    off = sampling_offsets.float().contiguous()
+    logits = attention_logits.float().contiguous()
+    grad_out = grad_out.to(value.dtype).contiguous()
+    if lib.cape_msda_fused_supported(ctypes.byref(dims)):
+        grad_value = torch.empty(value.shape, dtype=torch.float32, device=value.device)
+        grad_off = torch.empty_like(off)
+        grad_logits = torch.empty_like(logits)
+        with torch.cuda.device(value.device):
+            rc = lib.cape_msda_fused_backward(_ptr(grad_out), _ptr(value), _ptr(shapes), _ptr(starts), _ptr(ref),
+                                              _ptr(off), _ptr(logits), _ptr(grad_value), _ptr(grad_off),
+                                              _ptr(grad_logits), ctypes.byref(dims), _DTYPE_CODE[value.dtype], 1,
+                                              _stream(value.device))
+        _lib.check(rc, "cape_msda_fused_backward")
+    else:
+        # dimensions outside the fused fast path: same mathematics composed from the unfused backward
+        attn = torch.softmax(logits.reshape(b, k, m, l * p), -1)
+        wh = torch.stack([shapes[:, 1], shapes[:, 0]], -1).to(off.dtype)
+        loc = ref[:, :, None, :, None, :] + off / wh[None, None, None, :, None, :]
+        grad_value, grad_loc, grad_attn = torch.ops.cape.ms_deform_attn_backward(
+            grad_out, value, shapes, starts, loc.contiguous(), attn.view(b, k, m, l, p))
+        grad_off = grad_loc / wh[None, None, None, :, None, :]
+        ga = grad_attn.reshape(b, k, m, l * p)
+        grad_logits = attn * (ga - (attn * ga).sum(-1, keepdim=True))
+    return (grad_value.to(value.dtype), grad_off.to(sampling_offsets.dtype),
+            grad_logits.reshape(attention_logits.shape).to(attention_logits.dtype))
+
+
+@ms_deform_attn_fused_backward.register_fake
+def _(grad_out, value, spatial_shapes, level_start_index, reference_points, sampling_offsets, attention_logits):
+    return (torch.empty_like(value), torch.empty_like(sampling_offsets), torch.empty_like(attention_logits))
+
+
+def _fused_setup_context(ctx, inputs, output):
+    ctx.save_for_backward(*inputs)
+    ctx.needs_ref_grad = inputs[3].requires_grad
+
+
+def _fused_backward(ctx, grad_out):
+    value, shapes, starts, ref, off, logits = ctx.saved_tensors
+    gv, goff, glogits = torch.ops.cape.ms_deform_attn_fused_backward(grad_out, value, shapes, starts, ref, off, logits)
+    gref = None
+    if ctx.needs_ref_grad:   # d loc / d ref = 1: sum the location gradient over heads and points
+        wh = torch.stack([shapes[:, 1], shapes[:, 0]], -1).to(goff.dtype)
+        gref = (goff * wh[None, None, None, :, None, :]).sum(dim=(2, 4)).to(ref.dtype)
+    return gv, None, None, gref, goff, glogits
+
+
+ms_deform_attn_decode.register_autograd(_fused_backward, setup_context=_fused_setup_context)
+torch.library.register_autocast("cape::ms_deform_attn_decode", "cuda", torch.float32)

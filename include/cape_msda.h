@@ -113,6 +113,25 @@ CAPE_API int cape_msda_decode(const void* value_cache, const int64_t* spatial_sh
                      void* out, const cape_msda_dims* dims, int value_dtype, void* stream);
 
 /*
+ * Fused module path for training: cape_msda_decode is also the FORWARD of the op
+ *     out = core(value, softmax(attention_logits), reference_points + sampling_offsets / (W_l, H_l))
+ * for any number of queries (deformable_transformer.py:100-105 + :112), and this is its backward.  sampling_locations,
+ * attention_weights and their gradients never round-trip HBM.
+ *   grad_offsets   (N, Lq, M, L, P, 2) fp32   d out / d sampling_offsets         fully overwritten
+ *   grad_logits    (N, Lq, M, L*P)     fp32   d out / d attention_logits (through the softmax)   fully overwritten
+ *   grad_value     (N, S, M, D)        fp32   accumulated with atomics (zero_grad_value as in cape_msda_backward)
+ * The gradient w.r.t. reference_points is sum over (m, p) of grad_offsets * (W_l, H_l); callers that need it reduce
+ * grad_offsets themselves.  Fast-path dimensions only (cape_msda_fused_supported: D = 32, P = 4, L <= 4); other
+ * dimensions return CAPE_ERR_BAD_DIMS and the caller composes softmax / location arithmetic with cape_msda_backward.
+ */
+CAPE_API int cape_msda_fused_supported(const cape_msda_dims* dims);
+CAPE_API int cape_msda_fused_backward(const void* grad_out, const void* value, const int64_t* spatial_shapes_dev,
+                                      const int64_t* level_start_index_dev, const float* reference_points,
+                                      const float* sampling_offsets, const float* attention_logits, float* grad_value,
+                                      float* grad_offsets, float* grad_logits, const cape_msda_dims* dims,
+                                      int value_dtype, int zero_grad_value, void* stream);
+
+/*
  * Host-buffer round trip used for end-to-end measurement and for callers without device buffers:
  * copies the inputs from (ideally pinned) HOST memory into the caller-provided device workspace, runs forward and,
  * when grad_out_host != NULL, backward, and copies the results back to HOST memory — all enqueued on `stream`.

@@ -233,6 +233,49 @@ def test_decode_variant_matches_prologue_plus_core():
         assert rel_err(got16.float().cpu().numpy(), want16) < FWD_TOL_BF16
 
 
+@pytest.mark.parametrize("dims", [(8, 32, 4, 4), (2, 32, 3, 4), (3, 16, 2, 3)])
+def test_fused_op_gradients_match_the_composed_reference_form(dims):
+    """cape::ms_deform_attn_decode is differentiable (fused softmax / location prologue, forward AND backward): its
+    gradients w.r.t. value, reference_points, sampling_offsets and attention_logits must equal autograd through the
+    materialised form softmax -> ref + off/(W,H) -> cape::ms_deform_attn (deformable_transformer.py:100-112).  The
+    last case has dimensions outside the fused kernels and exercises the composed fallback."""
+    m, d, l, p = dims
+    shapes = ((12, 16), (6, 8), (3, 4), (2, 2))[:l]
+    s = sum(h * w for h, w in shapes)
+    g = torch.Generator().manual_seed(m * 10 + l)
+    n, lq = 2, 37
+    value = torch.randn(n, s, m, d, generator=g).cuda().requires_grad_(True)
+    ref = torch.rand(n, lq, l, 2, generator=g).cuda().requires_grad_(True)
+    off = (torch.randn(n, lq, m, l, p, 2, generator=g) * 2).cuda().requires_grad_(True)
+    logits = torch.randn(n, lq, m, l * p, generator=g).cuda().requires_grad_(True)
+    gout = torch.randn(n, lq, m * d, generator=g).cuda()
+    shapes_t = torch.tensor(shapes).cuda()
+    starts_t = cape_b200.level_start_index_from_shapes(shapes_t)
+    out = cape_b200.ms_deform_attn_fused(value, shapes_t, starts_t, ref, off, logits)
+    got = torch.autograd.grad(out, (value, ref, off, logits), gout)
+    attn = torch.softmax(logits, -1).view(n, lq, m, l, p)
+    wh = torch.stack([shapes_t[:, 1], shapes_t[:, 0]], -1).float()
+    loc = ref[:, :, None, :, None, :] + off / wh[None, None, None, :, None, :]
+    out2 = cape_b200.ms_deform_attn(value, shapes_t, starts_t, loc, attn)
+    want = torch.autograd.grad(out2, (value, ref, off, logits), gout)
+    assert rel_err(out.detach().cpu().numpy(), out2.detach().cpu().numpy()) < FWD_TOL_F32
+    for a, b, name in zip(got, want, ("value", "reference_points", "sampling_offsets", "attention_logits")):
+        assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < GRAD_TOL_F32, name
+
+
+def test_module_unfused_form_matches_fused():
+    g = np.load(os.path.join(GOLDEN, "module_forward.npz"))
+    mod = cape_b200.MSDeformAttn(int(g["d_model"]), int(g["n_levels"]), int(g["n_heads"]), int(g["n_points"])).cuda()
+    mod.load_state_dict({k[len("param."):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("param.")})
+    args = (_cuda(g["query"]), _cuda(g["reference_points"]), _cuda(g["input_flatten"]), _cuda(g["spatial_shapes"]),
+            _cuda(g["level_start_index"]), _cuda(g["padding_mask"]))
+    fused = mod(*args)
+    mod.fuse_prologue = False
+    plain = mod(*args)
+    assert rel_err(plain.detach().cpu().numpy(), g["out"]) < FWD_TOL_F32
+    assert rel_err(fused.detach().cpu().numpy(), plain.detach().cpu().numpy()) < FWD_TOL_F32
+
+
 def test_decode_generic_dims():
     g = torch.Generator().manual_seed(3)
     shapes = ((5, 7), (3, 2))
