@@ -253,6 +253,51 @@ def op_sweep(lib, dev):
     return rows
 
 
+def module_step(dev):
+    """one MSDeformAttn MODULE call of the encoder at the training shape (N=20, Lq=S=5440),
+    forward + backward: the mirror with the fused prologue, the mirror materialising sampling_locations /
+    attention_weights like the reference (our core op, torch prologue), and the reference's formulation run eagerly on
+    this GPU (oracle/msda_torch.py — baseline only)."""
+    import torch
+    import cape_b200
+    from oracle import msda_torch
+    w = WORKLOAD
+    torch.manual_seed(0)
+    mod = cape_b200.MSDeformAttn(256, 4, 8, 4).to(dev)
+    with torch.no_grad():
+        for prm in mod.parameters():
+            prm.add_(torch.randn_like(prm) * 0.02)
+    shapes = torch.tensor(cape_b200.synthetic.CAPE_PYRAMID, device=dev)
+    starts = cape_b200.level_start_index_from_shapes(shapes)
+    src = torch.randn(w["N"], w["S"], 256, device=dev, requires_grad=True)
+    pos = torch.randn(w["N"], w["S"], 256, device=dev)
+    ref = cape_b200.synthetic.pyramid_reference_points(cape_b200.synthetic.CAPE_PYRAMID, w["Lq"]).to(dev)
+    ref = ref[None, :, None, :].expand(w["N"], w["Lq"], 4, 2).contiguous()
+    gout = torch.randn(w["N"], w["Lq"], 256, device=dev)
+    weights = {k: v.detach() for k, v in mod.state_dict().items()}
+    shapes_l = shapes.tolist()
+
+    def run(fn):
+        def step():
+            out = fn()
+            out.backward(gout)
+            src.grad = None
+            mod.zero_grad(set_to_none=True)
+        return _time_us(step, 10) / 1e3
+
+    mod.fuse_prologue = True
+    fused = run(lambda: mod(src + pos, ref, src, shapes, starts, None))
+    mod.fuse_prologue = False
+    unfused = run(lambda: mod(src + pos, ref, src, shapes, starts, None))
+    mod.fuse_prologue = True
+    wreq = {k: v.clone().requires_grad_(True) for k, v in weights.items()}
+    eager = run(lambda: msda_torch.msda_module_forward(wreq, src + pos, ref, src, shapes_l, None))
+    return {"N": w["N"], "Lq": w["Lq"], "fwd_bwd_ms": {"mirror_fused_prologue": round(fused, 3),
+                                                         "mirror_materialised_prologue": round(unfused, 3),
+                                                         "reference_formulation_eager_gpu": round(eager, 3)},
+            "note": "includes the four nn.Linear projections (cuBLAS fp32) and their backward"}
+
+
 def decode_step(dev):
     """BASELINE.json configs[3]: one decoder-layer MSDeformAttn call while decoding, 64 episodes x 2 queries (N=128),
     Lq=1: the mirror module with the projected-value cache + fused prologue vs the same module recomputing the
@@ -497,6 +542,7 @@ def run_b200(args, rank, world, local_rank):
     }
     if world == 1 and not args.no_extras:
         line["sweep"] = op_sweep(lib, dev)
+        line["module"] = module_step(dev)
         line["decode"] = decode_step(dev)
         line["decode_loop"] = decode_loop(dev)
         line["gpu_eager_baseline"] = gpu_eager_baseline(dev, a_fwd + a_bwd)
