@@ -11,8 +11,6 @@ import torch
 
 from . import ops  # noqa: F401  (registers torch.ops.cape.*)
 
-ms_deform_attn_fused = None   # bound below: same callable as ms_deform_attn_decode, named for its training use
-
 __all__ = ["ms_deform_attn", "ms_deform_attn_core_pytorch", "ms_deform_attn_decode", "ms_deform_attn_fused",
            "MSDeformAttnFunction",
            "level_start_index_from_shapes"]
@@ -62,7 +60,7 @@ def ms_deform_attn_decode(value_cache, spatial_shapes, level_start_index, refere
                                                 sampling_offsets, attention_logits)
 
 
-ms_deform_attn_fused = ms_deform_attn_decode
+ms_deform_attn_fused = ms_deform_attn_decode   # same op, named for its use as the module's training forward
 
 
 class MSDeformAttnFunction:
