@@ -182,6 +182,48 @@ def test_empty_and_degenerate_inputs():
     assert float(out.abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("n,lq,shapes", [(2, 37, synthetic.CAPE_PYRAMID), (1, 1, synthetic.CAPE_PYRAMID),
+                                         (3, 130, ((9, 5), (4, 4), (2, 3))), (2, 19, ((7, 5), (4, 3)))])
+def test_guard_zones_stay_intact(n, lq, shapes):
+    """compute-sanitizer is closed on this pool, so out-of-bounds accesses are hunted with guard zones: every tensor the
+    kernels touch is carved out of one arena with NaN-filled guards on both sides.  After forward + backward (direct
+    and fused ops) the guards must be bit-identical (no stray write) and every result finite (no stray read that
+    mattered — a guard value reaching an output would be NaN)."""
+    generic = len(shapes) == 2
+    kw = dict(n_heads=3, head_dim=16, n_points=3) if generic else {}
+    inp = synthetic.make_inputs(n, lq, shapes, dist="uniform", seed=lq, **kw)
+    guard = 4096                                      # floats on each side
+    tensors = {k: inp[k] for k in ("value", "sampling_locations", "attention_weights", "grad_output")}
+    m, l, p = inp["sampling_locations"].shape[2:5]
+    tensors["ref"] = torch.rand(n, lq, l, 2)
+    tensors["logits"] = torch.randn(n, lq, m, l * p)
+    total = sum(t.numel() + 2 * guard for t in tensors.values())
+    arena = torch.full((total,), float("nan"), device="cuda")
+    views, off = {}, 0
+    for k, t in tensors.items():
+        off += guard
+        views[k] = arena[off:off + t.numel()].view(t.shape)
+        views[k].copy_(t)
+        off += t.numel() + guard
+    snapshot = arena.clone()
+    shapes_t, starts_t = inp["spatial_shapes"].cuda(), inp["level_start_index"].cuda()
+    v = views["value"].requires_grad_(True)
+    loc = views["sampling_locations"].requires_grad_(True)
+    attn = views["attention_weights"].requires_grad_(True)
+    out = cape_b200.ms_deform_attn(v, shapes_t, starts_t, loc, attn)
+    grads = torch.autograd.grad(out, (v, loc, attn), views["grad_output"])
+    ref = views["ref"].requires_grad_(True)
+    logits = views["logits"].requires_grad_(True)
+    out2 = cape_b200.ms_deform_attn_fused(v, shapes_t, starts_t, ref, loc, logits)   # loc reused as raw offsets
+    grads2 = torch.autograd.grad(out2, (v, ref, loc, logits), views["grad_output"])
+    torch.cuda.synchronize()
+    assert torch.equal(torch.isnan(arena), torch.isnan(snapshot))
+    same = (arena == snapshot) | torch.isnan(snapshot)
+    assert bool(same.all())
+    for t in (out, out2) + tuple(grads) + tuple(grads2):
+        assert bool(torch.isfinite(t).all())
+
+
 def test_error_behaviour():
     v = torch.randn(1, 4, 1, 4, device="cuda")
     shapes = torch.tensor([[2, 2]], device="cuda")
