@@ -220,7 +220,9 @@ class IncrementalDecoder:
     K/V are written into fixed ``(B, max_len, C)`` buffers at a device-resident position with ``index_copy_`` and the
     self-attention runs over the full buffer under an additive mask derived from that position; the projected value of
     the encoder memory is computed once in :meth:`reset`; the MSDeformAttn cross-attention is one fused
-    ``cape::ms_deform_attn_decode`` launch.  Same arithmetic as the eager layer (checked against the reference's own
+    ``cape::ms_deform_attn_decode`` launch.  K/V are cached already in-projected, the support keys / values are projected
+    once per batch, and the small projections of a step are issued as concatenated GEMMs (call ``invalidate()`` after
+    changing layer weights).  Same arithmetic as the eager layer (checked against the reference's own
     incremental outputs in tests/test_msda_gpu.py); no host synchronisation inside a step.
     """
 
@@ -276,24 +278,87 @@ class IncrementalDecoder:
         if self._sup_mask is not None:
             self._sup_mask.copy_(support_mask)
         self._ctx = (self._shapes, self._starts, self._sup, self._sup_mask)
+        if getattr(self, "_prep", None) is None:
+            self._prep = [self._prepare_layer(layer) for layer in self.layers]
+        if self._sup is not None:   # support keys / values are constant while decoding: project them once per batch
+            heads = self.layers[0].support_attn.num_heads
+            if getattr(self, "_sup_k", None) is None or self._sup_k[0].shape[0] != n \
+                    or self._sup_k[0].shape[2] != self._sup.shape[1]:
+                shape = (n, heads, self._sup.shape[1], self._sup.shape[2] // heads)
+                self._sup_k = [torch.empty(shape, device=self.device, dtype=self._sup.dtype) for _ in self.layers]
+                self._sup_v = [torch.empty(shape, device=self.device, dtype=self._sup.dtype) for _ in self.layers]
+                self._sup_bias = torch.zeros(n, 1, 1, self._sup.shape[1], device=self.device, dtype=self._sup.dtype)
+                self.graph = None
+            for prep, k_dst, v_dst in zip(self._prep, self._sup_k, self._sup_v):
+                k_dst.copy_(self._split_heads(F.linear(self._sup, prep["wk_s"], prep["bk_s"]), heads))
+                v_dst.copy_(self._split_heads(F.linear(self._sup, prep["wv_s"], prep["bv_s"]), heads))
+            self._sup_bias.zero_()
+            if self._sup_mask is not None:
+                self._sup_bias.masked_fill_(self._sup_mask[:, None, None, :], float("-inf"))
         self.pos.zero_()
+
+    def invalidate(self):
+        """Forget derived weights and the captured graph (call after the layers' parameters change)."""
+        self._prep = None
+        self.graph = None
+
+    def _prepare_layer(self, layer):
+        """Per-layer constants of a decode step, derived once per ``reset`` from the layer's own parameters:
+        concatenated / pre-multiplied projection weights so a step issues 9 small GEMMs instead of 14, with the cached
+        K/V stored already in-projected (the reference re-projects the whole prefix every step inside
+        ``nn.MultiheadAttention``; a Linear acts per token, so caching its output is exact)."""
+        c = layer.d_model
+        sa, xa, ca = layer.self_attn, layer.support_attn, layer.cross_attn
+        wq_in, wk_in, wv_in = sa.in_proj_weight.chunk(3)
+        bq_in, bk_in, bv_in = sa.in_proj_bias.chunk(3)
+        ident = torch.eye(c, device=self.device, dtype=wq_in.dtype)
+        wq = layer.attn_q.weight if isinstance(layer.attn_q, nn.Linear) else ident
+        wk = layer.attn_k.weight if isinstance(layer.attn_k, nn.Linear) else ident
+        wv = layer.attn_v.weight if isinstance(layer.attn_v, nn.Linear) else ident
+        prep = {
+            # tgt -> [attn_q(tgt) | in_proj_k(attn_k(tgt)) | in_proj_v(attn_v(tgt))]
+            "w_qkv": torch.cat([wq, wk_in @ wk, wv_in @ wv], 0).contiguous(),
+            "b_qkv": torch.cat([torch.zeros_like(bq_in), bk_in, bv_in], 0).contiguous(),
+            "wq_in": wq_in.contiguous(), "bq_in": bq_in.contiguous(),
+            # query -> [sampling_offsets | attention logits]
+            "w_ol": torch.cat([ca.sampling_offsets.weight, ca.attention_weights.weight], 0).contiguous(),
+            "b_ol": torch.cat([ca.sampling_offsets.bias, ca.attention_weights.bias], 0).contiguous(),
+            "n_off": ca.sampling_offsets.weight.shape[0],
+        }
+        wq_s, wk_s, wv_s = xa.in_proj_weight.chunk(3)
+        bq_s, bk_s, bv_s = xa.in_proj_bias.chunk(3)
+        prep.update(wq_s=wq_s.contiguous(), bq_s=bq_s.contiguous(), wk_s=wk_s, bk_s=bk_s, wv_s=wv_s, bv_s=bv_s)
+        return prep
+
+    def _split_heads(self, x, heads):
+        n, t, c = x.shape
+        return x.view(n, t, heads, c // heads).transpose(1, 2)            # (n, H, t, d)
 
     def _layer_step(self, i, layer, tgt, query_pos, mask):
         shapes, starts, sup, sup_mask = self._ctx
-        n = tgt.shape[0]
-        q = layer.attn_q(tgt) + query_pos
-        self.k_cache[i][:n].index_copy_(1, self.pos, layer.attn_k(tgt))
-        self.v_cache[i][:n].index_copy_(1, self.pos, layer.attn_v(tgt))
-        attn = layer.self_attn(q.transpose(0, 1), self.k_cache[i][:n].transpose(0, 1),
-                               self.v_cache[i][:n].transpose(0, 1), attn_mask=mask, need_weights=False)[0]
-        tgt = layer.norm2(tgt + attn.transpose(0, 1))
-        if sup is not None:
-            tgt = layer.norm_support(tgt + layer.support_attn(tgt, sup, sup, key_padding_mask=sup_mask,
-                                                              need_weights=False)[0])
-        ca = layer.cross_attn
-        query = tgt + query_pos
-        offsets = ca.sampling_offsets(query).view(n, 1, ca.n_heads, ca.n_levels, ca.n_points, 2)
-        logits = ca.attention_weights(query).view(n, 1, ca.n_heads, ca.n_levels * ca.n_points)
+        prep = self._prep[i]
+        n, c = tgt.shape[0], layer.d_model
+        heads = layer.self_attn.num_heads
+        # causal self-attention over the static K/V buffers (deformable_transformer_v2.py:322-341)
+        q0, k_in, v_in = F.linear(tgt, prep["w_qkv"], prep["b_qkv"]).split(c, dim=-1)
+        self.k_cache[i][:n].index_copy_(1, self.pos, k_in)
+        self.v_cache[i][:n].index_copy_(1, self.pos, v_in)
+        q_in = F.linear(q0 + query_pos, prep["wq_in"], prep["bq_in"])
+        attn = F.scaled_dot_product_attention(self._split_heads(q_in, heads),
+                                              self._split_heads(self.k_cache[i][:n], heads),
+                                              self._split_heads(self.v_cache[i][:n], heads), attn_mask=mask)
+        attn = layer.self_attn.out_proj(attn.transpose(1, 2).reshape(n, 1, c))
+        tgt = layer.norm2(tgt + attn)
+        if sup is not None:                                                # support cross-attention (:350-357)
+            q_s = F.linear(tgt, prep["wq_s"], prep["bq_s"])
+            xs = F.scaled_dot_product_attention(self._split_heads(q_s, heads), self._sup_k[i], self._sup_v[i],
+                                                attn_mask=self._sup_bias)
+            xs = layer.support_attn.out_proj(xs.transpose(1, 2).reshape(n, 1, c))
+            tgt = layer.norm_support(tgt + xs)
+        ca = layer.cross_attn                                              # MSDeformAttn on the cached value (:360-363)
+        ol = F.linear(tgt + query_pos, prep["w_ol"], prep["b_ol"])
+        offsets = ol[..., :prep["n_off"]].reshape(n, 1, ca.n_heads, ca.n_levels, ca.n_points, 2)
+        logits = ol[..., prep["n_off"]:].reshape(n, 1, ca.n_heads, ca.n_levels * ca.n_points)
         sampled = torch.ops.cape.ms_deform_attn_decode(self.values[i], shapes, starts, self.reference_points, offsets,
                                                        logits)
         tgt = layer.norm1(tgt + ca.output_proj(sampled))
@@ -301,8 +366,8 @@ class IncrementalDecoder:
 
     def _run(self):
         n = self.reference_points.shape[0]
-        mask = torch.zeros(1, self.max_len, device=self.device).masked_fill_(
-            (self.positions > self.pos)[None], float("-inf"))
+        mask = torch.zeros(1, 1, 1, self.max_len, device=self.device).masked_fill_(
+            (self.positions > self.pos)[None, None, None], float("-inf"))
         x = self.tgt[:n]
         for i, layer in enumerate(self.layers):
             x = self._layer_step(i, layer, x, self.query_pos[:n], mask)
