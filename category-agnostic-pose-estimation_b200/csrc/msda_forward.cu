@@ -188,6 +188,63 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
     }
 }
 
+// Latency-oriented variant for small problems (the decode step: Lq = 1 .. a few tokens): one warp per (n, q, m), lane =
+// (point p = lane>>3, channel quad k), so the 16 samples of a query are spread over the 4 lane groups and the 4 levels are
+// fully unrolled — all 16 corner loads of a lane are in flight at once.  At N = 128 the value cache (713 MB) does not
+// fit L2, every corner row is an HBM access, and the 4-queries-per-warp kernel above would walk its 16 samples one
+// dependent round trip after the other with three quarters of its lanes idle.  Costs 8 reduction shuffles per (q, m),
+// irrelevant at this size.
+template <typename VT, typename AT, int L, bool FUSED>
+__global__ void __launch_bounds__(128)
+msda_fwd_point_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
+                      const int64_t* __restrict__ starts, const void* __restrict__ locp,
+                      const void* __restrict__ attnp, const float* __restrict__ refp, VT* __restrict__ out,
+                      int64_t total_qm, int S, int M, int Lq) {
+    constexpr int D = 32;
+    using LT = typename std::conditional<FUSED, float, AT>::type;
+    const int lane = threadIdx.x & 31, warp = uniform_warp_id();
+    const int p = lane >> 3, k = lane & 7;
+    const int64_t qm = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + warp;
+    if (qm >= total_qm) return;
+    const int m = static_cast<int>(qm % M);
+    const int64_t nq = qm / M, n = nq / Lq;
+    const int rowStride = M * D;
+    FwdLevels<VT, L> lv;
+    lv.load(shapes, starts, value + (n * S * M + m) * D + k * 4, rowStride);
+    const float dimf = lv.lane_dim(lane);
+    float loc = 0.f, attn = FUSED ? -INFINITY : 0.f;
+    if (lane < L * 8) loc = to_f32(static_cast<const LT*>(locp)[qm * (L * 8) + lane]);
+    if (lane < L * 4) attn = to_f32(static_cast<const LT*>(attnp)[qm * (L * 4) + lane]);
+    if (FUSED) {   // softmax over the 4L logits and loc = ref + off / (W_l, H_l)  (deformable_transformer.py:100-105)
+        float mx = attn;
+#pragma unroll
+        for (int s = 8; s >= 1; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFullMask, mx, s));
+        const float e = (lane < L * 4) ? expf(attn - mx) : 0.f;
+        float sum = e;
+#pragma unroll
+        for (int s = 8; s >= 1; s >>= 1) sum += __shfl_xor_sync(kFullMask, sum, s);
+        attn = e / sum;
+        if (lane < L * 8) loc = __ldg(refp + nq * (L * 2) + (lane >> 3) * 2 + (lane & 1)) + loc / dimf;
+    }
+    loc = pixel_coord(loc, dimf);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+        const float px = __shfl_sync(kFullMask, loc, l * 8 + p * 2);
+        const float py = __shfl_sync(kFullMask, loc, l * 8 + p * 2 + 1);
+        const float a = __shfl_sync(kFullMask, attn, l * 4 + p);
+        gather_level(lv.base[l], rowStride, lv.H[l], lv.W[l], px, py, a, acc);
+    }
+#pragma unroll
+    for (int s = 8; s <= 16; s <<= 1) {
+        acc.x += __shfl_xor_sync(kFullMask, acc.x, s);
+        acc.y += __shfl_xor_sync(kFullMask, acc.y, s);
+        acc.z += __shfl_xor_sync(kFullMask, acc.z, s);
+        acc.w += __shfl_xor_sync(kFullMask, acc.w, s);
+    }
+    if (p == 0) st4(out + qm * D + k * 4, acc);
+}
+
 // Generic path: any D <= 256, L <= 8, P <= 8.  One warp per (n, q, m); lanes stride over d.
 template <typename VT, typename AT, bool FUSED>
 __global__ void __launch_bounds__(128)
@@ -308,7 +365,25 @@ cudaError_t launch_typed(const FwdArgs& a, cudaStream_t stream) {
     const cape_msda_dims& d = a.d;
     const int64_t total_qm = static_cast<int64_t>(d.N) * d.Lq * d.M;
     if (total_qm == 0) return cudaSuccess;
-    if (d.D == 32 && d.P == 4 && d.L >= 1 && d.L <= 4) {
+    if (d.D == 32 && d.P == 4 && d.L >= 1 && d.L <= 4 && total_qm <= env_int("CAPE_FWD_POINT_MAX_QM", 148 * 64)) {
+        // small problem (decode): one warp per (n, q, m), everything in flight at once
+        const int warps = 4;
+        const unsigned grid = static_cast<unsigned>((total_qm + warps - 1) / warps);
+        const VT* value = static_cast<const VT*>(a.value);
+        VT* out = static_cast<VT*>(a.out);
+#define CAPE_POINT_CASE(LL)                                                                                          \
+    case LL:                                                                                                         \
+        msda_fwd_point_kernel<VT, AT, LL, FUSED><<<grid, warps * 32, 0, stream>>>(                                   \
+            value, a.shapes, a.starts, a.loc, a.attn, a.ref_points, out, total_qm, d.S, d.M, d.Lq);                    \
+        break;
+        switch (d.L) {
+            CAPE_POINT_CASE(1)
+            CAPE_POINT_CASE(2)
+            CAPE_POINT_CASE(3)
+            CAPE_POINT_CASE(4)
+        }
+#undef CAPE_POINT_CASE
+    } else if (d.D == 32 && d.P == 4 && d.L >= 1 && d.L <= 4) {
         const FastGeometry g = fast_geometry(d, "CAPE_FWD_THREADS", "CAPE_FWD_QPC", 512, 512);
         if (g.grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
         switch (d.L) {
