@@ -208,6 +208,73 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+# ---- data-parallel training step of the deformable transformer (all N; BASELINE.json configs[2] and [4]) ---------
+def train_step(dev, rank, world, accumulation=4, steps=2):
+    """One optimizer step of the CAPE transformer body on every rank: 6 deformable encoder layers (Lq = S = 5440) +
+    6 decoder layers v1 (teacher-forced, 200 tokens, 17 support keypoints), micro-batch of 10 episodes x 2 queries
+    (N = 20), gradient accumulation 4, ONE flat-bucket gradient all-reduce over NCCL (dist.FlatGradAllreduce), clip 0.1,
+    AdamW — the loop of engine_cape.py:230-258 around the mirrors of layers.py.  Synthetic features / targets; backbone,
+    support encoder and heads are outside the hot path and not included.  episodes/s = world x 40 / max-over-ranks time."""
+    import torch
+    import cape_b200
+    from cape_b200 import dist as cdist
+    torch.manual_seed(1234)                       # same weights on every rank
+    kw = dict(d_model=256, d_ffn=1024, dropout=0.1, activation="relu", n_levels=4, n_heads=8, n_points=4)
+    enc = cape_b200.DeformableTransformerEncoder(cape_b200.DeformableTransformerEncoderLayer(**kw), 6).to(dev)
+    dec = torch.nn.ModuleList([cape_b200.TransformerDecoderLayer(**kw) for _ in range(6)]).to(dev)
+    params = list(enc.parameters()) + list(dec.parameters())
+    opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=1e-4)
+    allreduce = cdist.FlatGradAllreduce(params)
+    n, t_len, n_sup = WORKLOAD["N"], 200, 17
+    g = torch.Generator(device=dev).manual_seed(100 + rank)     # different episodes on every rank
+    shapes = torch.tensor(cape_b200.synthetic.CAPE_PYRAMID, device=dev)
+    starts = cape_b200.level_start_index_from_shapes(shapes)
+    valid = torch.ones(n, 4, 2, device=dev)
+    causal = torch.triu(torch.full((t_len, t_len), float("-inf"), device=dev), diagonal=1)
+    sup_mask = torch.zeros(n, n_sup, dtype=torch.bool, device=dev)
+    rnd = lambda *shape: torch.randn(*shape, device=dev, generator=g)
+
+    def micro_batch():
+        src, pos = rnd(n, WORKLOAD["S"], 256), rnd(n, WORKLOAD["S"], 256)
+        tgt, qpos, sup = rnd(n, t_len, 256), rnd(n, t_len, 256), rnd(n, n_sup, 256)
+        ref = torch.rand(n, t_len, 4, 2, device=dev, generator=g)
+        memory = enc(src, shapes, starts, valid, pos, None)
+        x = tgt
+        for layer in dec:
+            x, _ = layer(x, qpos, ref, memory, shapes, starts, None, causal, support_features=sup, support_mask=sup_mask)
+        return x.square().mean() / accumulation
+
+    def optimizer_step():
+        for _ in range(accumulation):
+            micro_batch().backward()
+        allreduce()                                # the only collective of the step
+        torch.nn.utils.clip_grad_norm_(params, 0.1)
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+
+    launches0 = cape_b200.launch_count()
+    optimizer_step()                               # warm-up (cuBLAS heuristics, allocator)
+    per_step_launches = cape_b200.launch_count() - launches0
+    cdist.barrier(dev)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        optimizer_step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = cdist.max_over_ranks(e0.elapsed_time(e1), dev) / steps
+    episodes = world * accumulation * (n // 2)
+    n_params = sum(p.numel() for p in params)
+    del enc, dec, opt, allreduce
+    torch.cuda.empty_cache()
+    return {"episodes_per_s": round(episodes / (ms * 1e-3), 2), "ms_per_optimizer_step": round(ms, 2),
+            "episodes_per_step": episodes, "accumulation": accumulation, "allreduce_mb": round(n_params * 4 / 2 ** 20, 1),
+            "msda_launches_per_step": int(per_step_launches), "dtype": "f32 (TF32 off)",
+            "scope": "6 encoder + 6 decoder (v1) layers of the deformable transformer, fwd + bwd + NCCL all-reduce + "
+                     "AdamW; synthetic features; no backbone / support encoder / heads"}
+
+
 # ---- side measurements (N=1 only; informational keys next to the contract's) -------------------------------------
 def _time_us(fn, reps):
     import torch
@@ -515,6 +582,7 @@ def run_b200(args, rank, world, local_rank):
     d2h = sum(t.numel() * t.element_size() for t in res.values())
     checksum = float(res["out"].double().sum())           # the result really is on the host
 
+    train = None if args.no_extras else train_step(dev, rank, world)
     if rank != 0:
         return
     peak, peak_src = measured_peak()
@@ -540,6 +608,8 @@ def run_b200(args, rank, world, local_rank):
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
+    if train is not None:
+        line["train_step"] = train
     if world == 1 and not args.no_extras:
         line["sweep"] = op_sweep(lib, dev)
         line["module"] = module_step(dev)
@@ -573,6 +643,8 @@ def main():
                os.path.abspath(__file__)] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
     from cape_b200 import dist as cdist
+    # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", NCCL_DEBUG output) goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     cdist.init_from_env()
     try:
         run_b200(args, rank, world, local_rank)
