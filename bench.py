@@ -643,9 +643,22 @@ def main():
                os.path.abspath(__file__)] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
     from cape_b200 import dist as cdist
-    # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", NCCL_DEBUG output) goes to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-    cdist.init_from_env()
+    # stdout carries exactly one JSON line: whatever NCCL prints while the communicator comes up ("NCCL version ...",
+    # NCCL_DEBUG output) is sent to stderr by pointing fd 1 at fd 2 until the first collective has completed
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        cdist.init_from_env()
+        if world > 1:
+            import torch
+            torch.cuda.set_device(local_rank)
+            cdist.barrier(torch.device("cuda", local_rank))
+            torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     try:
         run_b200(args, rank, world, local_rank)
     finally:
