@@ -582,7 +582,19 @@ def run_b200(args, rank, world, local_rank):
     d2h = sum(t.numel() * t.element_size() for t in res.values())
     checksum = float(res["out"].double().sum())           # the result really is on the host
 
-    train = None if args.no_extras else train_step(dev, rank, world)
+    def guarded(fn, *a):
+        """Side measurements must never take the contract line down with them."""
+        try:
+            return fn(*a)
+        except Exception as exc:                                   # noqa: BLE001
+            return {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
+    train = None
+    if not args.no_extras:
+        try:
+            train = train_step(dev, rank, world)
+        except Exception as exc:                                   # noqa: BLE001 - every rank must keep going
+            train = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     if rank != 0:
         return
     peak, peak_src = measured_peak()
@@ -611,13 +623,13 @@ def run_b200(args, rank, world, local_rank):
     if train is not None:
         line["train_step"] = train
     if world == 1 and not args.no_extras:
-        line["sweep"] = op_sweep(lib, dev)
-        line["module"] = module_step(dev)
-        line["decode"] = decode_step(dev)
-        line["decode_loop"] = decode_loop(dev)
-        line["gpu_eager_baseline"] = gpu_eager_baseline(dev, a_fwd + a_bwd)
+        line["sweep"] = guarded(op_sweep, lib, dev)
+        line["module"] = guarded(module_step, dev)
+        line["decode"] = guarded(decode_step, dev)
+        line["decode_loop"] = guarded(decode_loop, dev)
+        line["gpu_eager_baseline"] = guarded(gpu_eager_baseline, dev, a_fwd + a_bwd)
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline()
+        line["cpu_baseline"] = guarded(cpu_baseline)
     print(json.dumps(line), flush=True)
 
 

@@ -30,7 +30,7 @@ namespace cape {
 
 namespace {
 
-constexpr int kFwdMaxThreads = 1024;
+constexpr int kFwdMaxThreads = 512;
 
 // Per-level constants kept in registers for the whole CTA.
 template <typename VT, int L>
