@@ -494,6 +494,7 @@ def run_b200(args, rank, world, local_rank):
         raise SystemExit("bench.py: no CUDA device — the B200 arm has no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_node = cdist.bind_to_gpu_numa_node(local_rank) if world > 1 else None
     lib = _lib.load()
     w = WORKLOAD
     inp = cape_b200.synthetic.make_inputs(w["N"], w["Lq"], dist="encoder", seed=rank, device=dev)
@@ -616,6 +617,7 @@ def run_b200(args, rank, world, local_rank):
         "e2e": {"value": round(alg * e2e_steps / (e2e_ms * 1e-3) / 1e9, 2), "unit": UNIT,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "ms_per_step": round(e2e_ms / e2e_steps, 3), "api": "cape_msda_forward_backward_host (C ABI, pinned host buffers)",
+                "numa_node_rank0": numa_node,
                 "out_checksum": checksum},
         "gpu_launches": int(launches),
         "clocks": clocks,

@@ -116,3 +116,32 @@ class FlatGradAllreduce:
 def shard_sizes(total: int, world: int) -> Sequence[int]:
     """Per-rank item counts of a round-robin shard of ``total`` items."""
     return [len(range(r, total, world)) for r in range(world)]
+
+
+def bind_to_gpu_numa_node(device_index: int) -> int | None:
+    """Pin this process (and therefore its first-touch pinned host buffers) to the CPU cores of the NUMA node the GPU hangs
+    off, so that with one process per GPU the host<->device copies of different ranks do not all cross the socket
+    interconnect.  Best effort: returns the node number, or None when the topology cannot be read."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(device_index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:            # nvml reports an 8-digit PCI domain, sysfs uses 4
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
