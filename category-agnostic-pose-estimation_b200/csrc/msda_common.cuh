@@ -98,30 +98,12 @@ template <> __device__ __forceinline__ float from_f32<float>(float v) { return v
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
 
-// fp32 vector reduction into global memory (REDG.E.ADD.F32x4 on sm_90+); p must be 16-byte aligned.
-__device__ __forceinline__ void red_add4(float* p, float x, float y, float z, float w) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
-}
-
-// Same, executed only when `pred` (the predicate rides on the REDG itself: no branch).
+// fp32 vector reduction into global memory (REDG.E.ADD.F32x4 on sm_90+; p must be 16-byte aligned), executed only when
+// `pred`: the predicate rides on the REDG itself, no branch in the source.
 __device__ __forceinline__ void red_add4_if(float* p, bool pred, float x, float y, float z, float w) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t@p red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n\t}"
                  ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(w), "r"(static_cast<int>(pred)) : "memory");
 }
-
-// ---- per-level metadata held in registers --------------------------------------------------------------------
-template <int L>
-struct Levels {
-    int H[L], W[L], start[L];
-    __device__ __forceinline__ void load(const int64_t* __restrict__ shapes, const int64_t* __restrict__ starts) {
-#pragma unroll
-        for (int l = 0; l < L; ++l) {
-            H[l] = static_cast<int>(__ldg(shapes + 2 * l));
-            W[l] = static_cast<int>(__ldg(shapes + 2 * l + 1));
-            start[l] = static_cast<int>(__ldg(starts + l));
-        }
-    }
-};
 
 // Pixel coordinates of one sample.  Returns false when no corner can be in bounds (also for NaN / inf locations),
 // in which case x0/y0/lx/ly are not written.

@@ -82,14 +82,13 @@ __device__ __forceinline__ void gather_level(const VT* __restrict__ base, int ro
 
 // The sample table of one (q, m), spread over the 8 lanes of the query's group: lane k holds location floats
 // 4k .. 4k+3 (= samples 2k and 2k+1, both of level k >> 1) and weights 2k, 2k+1.
-template <typename AT>
 struct RawSamples {
     float4 loc;
     float2 attn;
 };
 
 __device__ __forceinline__ void load_raw(const float* locp, const float* attnp, int64_t qm, int k, int L, bool on,
-                                         RawSamples<float>& r, float pad) {
+                                         RawSamples& r, float pad) {
     r.loc = make_float4(0.f, 0.f, 0.f, 0.f);
     r.attn = make_float2(pad, pad);
     if (on && k < 2 * L) {
@@ -99,7 +98,7 @@ __device__ __forceinline__ void load_raw(const float* locp, const float* attnp, 
 }
 template <typename HT>   // bf16 / fp16 location + weight tensors
 __device__ __forceinline__ void load_raw(const HT* locp, const HT* attnp, int64_t qm, int k, int L, bool on,
-                                         RawSamples<float>& r, float pad) {
+                                         RawSamples& r, float pad) {
     r.loc = make_float4(0.f, 0.f, 0.f, 0.f);
     r.attn = make_float2(pad, pad);
     if (on && k < 2 * L) {
@@ -143,7 +142,7 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
     if (qw >= q_end) return;
     const float pad = FUSED ? -INFINITY : 0.f;
     const int grp = lane & 24;
-    RawSamples<float> cur, nxt;
+    RawSamples cur, nxt;
     load_raw(loc_t, attn_t, (static_cast<int64_t>(n) * Lq + qw + g) * M + m, k, L, qw + g < q_end, nxt, pad);
     for (; qw < q_end; qw += nwarps * 4) {
         const int q = qw + g;                            // this group's query

@@ -52,7 +52,7 @@ def timeit(fn, reps=20):
 
 which = sys.argv[1] if len(sys.argv) > 1 else "both"
 if which in ("fwd", "both"):
-    for th, qpc in itertools.product((256, 512, 1024), (32, 64, 128, 256, 512)):
+    for th, qpc in itertools.product((128, 256, 512), (128, 256, 512, 1024, 2048)):
         os.environ["CAPE_FWD_THREADS"], os.environ["CAPE_FWD_QPC"] = str(th), str(qpc)
         print(f"fwd threads={th:4d} qpc={qpc:4d}  {timeit(fwd):8.1f} us", flush=True)
 if which in ("bwd", "both"):
