@@ -248,4 +248,8 @@ def _fused_backward(ctx, grad_out):
 
 
 ms_deform_attn_decode.register_autograd(_fused_backward, setup_context=_fused_setup_context)
-torch.library.register_autocast("cape::ms_deform_attn_decode", "cuda", torch.float32)
+# No autocast rule for the fused op on purpose: it takes `value` in whatever dtype the caller holds it (fp32, or the
+# fp16 / bf16 that an autocast value_proj produced), converts on load, accumulates in fp32 and casts the small tensors
+# itself.  A blanket cast-to-fp32 rule would copy the whole (B, S, M, D) value — for the decode step that is the entire
+# projected-value cache — on every call.  The result equals the reference's AMP flow, whose fp32 sampling output is
+# rounded to half precision by the next autocast Linear anyway.

@@ -409,6 +409,26 @@ def test_autocast_runs_the_core_in_fp32_like_the_reference():
     assert out.dtype == torch.float32
 
 
+def test_fused_op_under_autocast_keeps_the_value_dtype_and_matches_fp32_math():
+    torch.manual_seed(5)
+    mod = cape_b200.MSDeformAttn(256, 4, 8, 4).cuda()
+    with torch.no_grad():
+        for prm in mod.parameters():
+            prm.add_(torch.randn_like(prm) * 0.05)
+    shapes = torch.tensor(((8, 8), (4, 4), (2, 2), (1, 1)), device="cuda")
+    starts = cape_b200.level_start_index_from_shapes(shapes)
+    q, src = torch.randn(2, 9, 256, device="cuda"), torch.randn(2, 85, 256, device="cuda")
+    ref = torch.rand(2, 9, 4, 2, device="cuda")
+    want = mod(q, ref, src, shapes, starts)
+    with torch.autocast("cuda", dtype=torch.float16):
+        got = mod(q, ref, src, shapes, starts)
+        v16 = torch.randn(2, 85, 8, 32, device="cuda", dtype=torch.float16)
+        raw = cape_b200.ms_deform_attn_fused(v16, shapes, starts, ref, torch.randn(2, 9, 8, 4, 4, 2, device="cuda"),
+                                             torch.randn(2, 9, 8, 16, device="cuda"))
+    assert got.dtype == torch.float16 and raw.dtype == torch.float16          # no fp32 copy of the value was made
+    assert rel_err(got.detach().float().cpu().numpy(), want.detach().cpu().numpy()) < FWD_TOL_BF16
+
+
 def test_backward_from_autograd_thread_and_side_stream():
     inp = synthetic.make_inputs(2, 64, ((8, 8), (4, 4), (2, 2), (1, 1)), seed=10)
     a = tuple(inp[k].numpy() for k in ("value", "spatial_shapes", "level_start_index", "sampling_locations",
