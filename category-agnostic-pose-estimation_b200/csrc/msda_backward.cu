@@ -8,11 +8,14 @@
 //     grad_loc.y     = A * H_l * sum_c (dy ? +wx_c : -wx_c) <G, v_c>
 //     grad_value[c] += A * w_c * G                 (in-bounds corners only)
 //
-// Fast path (D = 32, P = 4, L <= 4): same CTA / warp / lane mapping as the forward (lane = (point p, channel quad k)).
-// The three dot-product partials are folded over the 8 lanes of a point with xor-shuffles; every lane of a point then
-// holds the sums, lane k == l keeps level l's result, and after the level loop lanes k < L write the grad_loc /
-// grad_attn entries of the (q, m).  grad_value is scattered with 16-byte vector reductions (REDG.E.ADD.F32x4): 8 lanes
-// cover one 128 B corner row.
+// Fast path (D = 32, P = 4, L <= 4): CTA = one (n, head) and a run of consecutive queries; a warp takes one query at a
+// time, lane = (point p = lane>>3, channel quad k = lane&7).  Per level: 4 predicated corner loads (4 x 128 B rows per
+// warp instruction), 4 dot products with grad_out's 4 channels, 4 predicated vector reductions into grad_value
+// (REDG.E.ADD.F32x4: 8 lanes cover one 128 B corner row).  The 12 per-lane partials (4 levels x (grad_attn, grad_loc.x,
+// grad_loc.y)) are summed over the 8 lanes of a point with a 12-shuffle transpose-reduce after the level loop; lane
+// (p, k even) then owns sample (level k/2, point p) and writes its grad_loc / grad_attn entries.
+// The scatter is what bounds this kernel: 44 M corner rows per launch at the L2 reduction units' ~51 G rows/s
+// (DESIGN.md §5).
 #include <cstdlib>
 
 #include "msda_common.cuh"
@@ -98,6 +101,28 @@ __device__ __forceinline__ void scatter_level(const VT* __restrict__ vbase, floa
     gy = hx * (d10 - d00) + lx * (d11 - d01);
 }
 
+// Sum 12 per-lane partials over the 8 lanes of a point group with 12 shuffles instead of 36: two halving rounds
+// (xor 4, xor 2: each lane keeps the half it will own and sends the other), then one full round (xor 1).
+// v = [level][ga, gx, gy]; afterwards every lane holds the three complete sums of level (k >> 1) in out[0..2].
+__device__ __forceinline__ void transpose_reduce12(const float (&v)[12], int k, float (&out)[3]) {
+    const bool hi4 = k & 4, hi2 = k & 2;
+    float h[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const float keep = hi4 ? v[i + 6] : v[i];
+        const float send = hi4 ? v[i] : v[i + 6];
+        h[i] = keep + __shfl_xor_sync(kFullMask, send, 4);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float keep = hi2 ? h[i + 3] : h[i];
+        const float send = hi2 ? h[i] : h[i + 3];
+        out[i] = keep + __shfl_xor_sync(kFullMask, send, 2);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) out[i] += __shfl_xor_sync(kFullMask, out[i], 1);
+}
+
 // FUSED = false: locp / attnp are sampling_locations / attention_weights, outputs grad_loc / grad_attn.
 // FUSED = true : the module prologue is part of the op (deformable_transformer.py:100-105): locp / attnp are the raw
 //                sampling offsets and attention logits (fp32), refp the reference points; the kernel recomputes
@@ -145,7 +170,11 @@ msda_bwd_fast_kernel(const VT* __restrict__ gout, const VT* __restrict__ value, 
                 locv = __ldg(refp + (static_cast<int64_t>(n) * Lq + q) * (L * 2) + (lane >> 3) * 2 + (lane & 1)) + locv / dimf;
         }
         locv = pixel_coord(locv, dimf);
-        float r_ga = 0.f, r_gx = 0.f, r_gy = 0.f, r_a = 0.f;
+        float part[12], a_lvl[4];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) part[i] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a_lvl[i] = 0.f;
 #pragma unroll
         for (int l = 0; l < L; ++l) {
             const float px = __shfl_sync(kFullMask, locv, l * 8 + p * 2);
@@ -153,31 +182,31 @@ msda_bwd_fast_kernel(const VT* __restrict__ gout, const VT* __restrict__ value, 
             const float a = __shfl_sync(kFullMask, attnv, l * 4 + p);
             float ga, gx, gy;
             scatter_level(vbase, gbase, rowStride, lv.off[l], lv.H[l], lv.W[l], px, py, a, g, ga, gx, gy);
-#pragma unroll
-            for (int s = 1; s <= 4; s <<= 1) {
-                ga += __shfl_xor_sync(kFullMask, ga, s);
-                gx += __shfl_xor_sync(kFullMask, gx, s);
-                gy += __shfl_xor_sync(kFullMask, gy, s);
-            }
-            if (k == l) {
-                r_ga = ga;
-                r_a = a;
-                // d loc / d offset = 1 / dim cancels the dim factor of d pixel / d loc
-                r_gx = FUSED ? a * gx : a * static_cast<float>(lv.W[l]) * gx;
-                r_gy = FUSED ? a * gy : a * static_cast<float>(lv.H[l]) * gy;
-            }
+            part[l * 3] = ga;
+            // d loc / d offset = 1 / dim cancels the dim factor of d pixel / d loc in the fused form
+            part[l * 3 + 1] = FUSED ? a * gx : a * static_cast<float>(lv.W[l]) * gx;
+            part[l * 3 + 2] = FUSED ? a * gy : a * static_cast<float>(lv.H[l]) * gy;
+            a_lvl[l] = a;
         }
-        if (FUSED) {   // softmax backward over the (q, m)'s 4L samples, held by lanes (p, k < L)
-            float dot = (k < L) ? r_a * r_ga : 0.f;
+        float sum[3];
+        transpose_reduce12(part, k, sum);      // every lane now holds (ga, gx, gy) of level k >> 1 for its point
+        const int lvl = k >> 1;
+        const bool owner = !(k & 1) && lvl < L;
+        if (FUSED) {   // softmax backward over the (q, m)'s 4L samples, held by the owner lanes
+            float r_a = 0.f;
+#pragma unroll
+            for (int l = 0; l < L; ++l)
+                if (lvl == l) r_a = a_lvl[l];
+            float dot = owner ? r_a * sum[0] : 0.f;
 #pragma unroll
             for (int s = 16; s >= 1; s >>= 1) dot += __shfl_xor_sync(kFullMask, dot, s);
-            r_ga = r_a * (r_ga - dot);
+            sum[0] = r_a * (sum[0] - dot);
         }
-        if (k < L) {   // lane (p, k) owns sample (level k, point p)
-            const int si = k * 4 + p;
-            gattn[qm * (L * 4) + si] = from_f32<AT>(r_ga);
-            gloc[(qm * (L * 4) + si) * 2] = from_f32<AT>(r_gx);
-            gloc[(qm * (L * 4) + si) * 2 + 1] = from_f32<AT>(r_gy);
+        if (owner) {   // lane (p, k even) owns sample (level k / 2, point p)
+            const int si = lvl * 4 + p;
+            gattn[qm * (L * 4) + si] = from_f32<AT>(sum[0]);
+            gloc[(qm * (L * 4) + si) * 2] = from_f32<AT>(sum[1]);
+            gloc[(qm * (L * 4) + si) * 2 + 1] = from_f32<AT>(sum[2]);
         }
     }
 }
