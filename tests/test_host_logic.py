@@ -152,3 +152,38 @@ def test_kv_cache_update_returns_prefix():
         assert k.shape == (2, i + 1, 4) and float(k[0, i, 0]) == i and float(v[1, i, 3]) == -i
     k, _ = kv.update(1, torch.full((2, 1, 4), 9.0), torch.zeros(2, 1, 4))      # python-int position
     assert k.shape == (2, 2, 4) and float(k[0, 1, 0]) == 9.0
+
+
+def test_patch_reference_routes_the_real_reference_module_to_the_op():
+    """With the actual reference checked out (build container only), rebinding the seam makes the reference's own
+    MSDeformAttn.forward (models/deformable_transformer.py:76-114) dispatch to cape::ms_deform_attn: on CPU tensors
+    that shows as the dispatcher's NotImplementedError (there is no CPU path), and unpatching restores eager."""
+    ref_root = "/root/reference"
+    path = os.path.join(ref_root, "models", "deformable_transformer.py")
+    if not os.path.exists(path):
+        pytest.skip("reference checkout not present (GPU box)")
+    import importlib.util
+    import sys
+    sys.path.insert(0, ref_root)
+    try:
+        spec = importlib.util.spec_from_file_location("ref_dt_for_patch_test", path)
+        ref = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref)
+    finally:
+        sys.path.remove(ref_root)
+    torch.manual_seed(0)
+    mod = ref.MSDeformAttn(64, 2, 2, 4)
+    mine = cape_b200.MSDeformAttn(64, 2, 2, 4)
+    assert list(mod.state_dict()) == list(mine.state_dict())                      # checkpoint-compatible
+    mine.load_state_dict(mod.state_dict())
+    q, src = torch.randn(1, 3, 64), torch.randn(1, 20, 64)
+    refp = torch.rand(1, 3, 2, 2)
+    shapes, starts = torch.tensor([[4, 4], [2, 2]]), torch.tensor([0, 16])
+    eager = mod(q, refp, src, shapes, starts)
+    cape_b200.patch_reference(ref)
+    try:
+        with pytest.raises(NotImplementedError):
+            mod(q, refp, src, shapes, starts)
+    finally:
+        cape_b200.unpatch_reference(ref)
+    assert torch.equal(mod(q, refp, src, shapes, starts), eager)
