@@ -42,6 +42,10 @@ _SIGNATURES = {
     "cape_msda_decode": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(Dims), _i, _vp]),
     "cape_msda_fused_supported": (_i, [ctypes.POINTER(Dims)]),
     "cape_msda_fused_backward": (_i, [_vp] * 10 + [ctypes.POINTER(Dims), _i, _i, _vp]),
+    "cape_msda_query_pool_forward": (_i, [_vp] * 6 + [ctypes.POINTER(Dims), _vp]),
+    "cape_msda_query_pool_backward": (_i, [_vp] * 9 + [ctypes.POINTER(Dims), _i, _vp]),
+    "cape_points_sample_forward": (_i, [_vp] * 3 + [_i] * 7 + [_vp]),
+    "cape_points_sample_backward": (_i, [_vp] * 5 + [_i] * 8 + [_vp]),
     "cape_msda_host_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(Dims), _i]),
     "cape_msda_forward_backward_host": (_i, [_vp] * 10 + [ctypes.POINTER(Dims), _vp, ctypes.c_size_t, _vp]),
 }

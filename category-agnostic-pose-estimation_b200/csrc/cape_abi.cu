@@ -240,6 +240,114 @@ int cape_msda_fused_backward(const void* grad_out, const void* value, const int6
     return e == cudaSuccess ? 0 : fail_cuda(e, "cape_msda_fused_backward launch");
 }
 
+// ---- variant samplers (fp32) ---------------------------------------------------------------------------------------
+
+int cape_msda_query_pool_forward(const float* value, const int64_t* spatial_shapes_dev,
+                                 const int64_t* level_start_index_dev, const float* sampling_locations,
+                                 const float* attention_weights, float* out, const cape_msda_dims* dims, void* stream) {
+    int rc;
+    if ((rc = check_dims(dims))) return rc;
+    const bool empty = dims->N == 0;
+    if ((rc = check_ptr(value, "value", empty || dims->S == 0)) ||
+        (rc = check_ptr(spatial_shapes_dev, "spatial_shapes", false, 8)) ||
+        (rc = check_ptr(level_start_index_dev, "level_start_index", false, 8)) ||
+        (rc = check_ptr(sampling_locations, "sampling_locations", empty || dims->Lq == 0)) ||
+        (rc = check_ptr(attention_weights, "attention_weights", empty || dims->Lq == 0)) ||
+        (rc = check_ptr(out, "out", empty)))
+        return rc;
+    if (empty) return 0;
+    FwdArgs a{};
+    a.value = value;
+    a.shapes = spatial_shapes_dev;
+    a.starts = level_start_index_dev;
+    a.loc = sampling_locations;
+    a.attn = attention_weights;
+    a.out = out;
+    a.d = *dims;
+    const cudaError_t e = launch_query_pool_forward(a, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? 0 : fail_cuda(e, "cape_msda_query_pool_forward launch");
+}
+
+int cape_msda_query_pool_backward(const float* grad_out, const float* value, const int64_t* spatial_shapes_dev,
+                                  const int64_t* level_start_index_dev, const float* sampling_locations,
+                                  const float* attention_weights, float* grad_value, float* grad_loc, float* grad_attn,
+                                  const cape_msda_dims* dims, int zero_grad_value, void* stream) {
+    int rc;
+    if ((rc = check_dims(dims))) return rc;
+    const bool empty = dims->N == 0 || dims->Lq == 0;
+    const bool no_value = dims->N == 0 || dims->S == 0;
+    if ((rc = check_ptr(grad_out, "grad_out", dims->N == 0)) || (rc = check_ptr(value, "value", empty || no_value)) ||
+        (rc = check_ptr(spatial_shapes_dev, "spatial_shapes", false, 8)) ||
+        (rc = check_ptr(level_start_index_dev, "level_start_index", false, 8)) ||
+        (rc = check_ptr(sampling_locations, "sampling_locations", empty)) ||
+        (rc = check_ptr(attention_weights, "attention_weights", empty)) || (rc = check_ptr(grad_value, "grad_value", no_value)) ||
+        (rc = check_ptr(grad_loc, "grad_loc", empty)) || (rc = check_ptr(grad_attn, "grad_attn", empty)))
+        return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (zero_grad_value && !no_value) {
+        const size_t bytes = static_cast<size_t>(dims->N) * dims->S * dims->M * dims->D * sizeof(float);
+        const cudaError_t e = cudaMemsetAsync(grad_value, 0, bytes, s);
+        if (e != cudaSuccess) return fail_cuda(e, "cape_msda_query_pool_backward memset(grad_value)");
+    }
+    if (empty) return 0;
+    BwdArgs a{};
+    a.grad_out = grad_out;
+    a.value = value;
+    a.shapes = spatial_shapes_dev;
+    a.starts = level_start_index_dev;
+    a.loc = sampling_locations;
+    a.attn = attention_weights;
+    a.grad_value = grad_value;
+    a.grad_loc = grad_loc;
+    a.grad_attn = grad_attn;
+    a.d = *dims;
+    const cudaError_t e = launch_query_pool_backward(a, s);
+    return e == cudaSuccess ? 0 : fail_cuda(e, "cape_msda_query_pool_backward launch");
+}
+
+namespace {
+int check_points_dims(int B, int G, int c, int H, int W, int Hk, int Wk) {
+    if (B < 0 || G <= 0 || c <= 0 || H <= 0 || W <= 0 || Hk < 0 || Wk < 0)
+        return fail(CAPE_ERR_BAD_DIMS, "bad point-sampling dimensions (B=%d G=%d c=%d H=%d W=%d Hk=%d Wk=%d)", B, G, c, H, W,
+                    Hk, Wk);
+    if (static_cast<int64_t>(B) * G * c * H * W > 0x7fffffffffffLL) return fail(CAPE_ERR_BAD_DIMS, "tensor too large");
+    return 0;
+}
+}  // namespace
+
+int cape_points_sample_forward(const float* x, const float* pos, float* out, int B, int G, int c, int H, int W, int Hk,
+                               int Wk, void* stream) {
+    int rc;
+    if ((rc = check_points_dims(B, G, c, H, W, Hk, Wk))) return rc;
+    const bool empty = B == 0 || Hk == 0 || Wk == 0;
+    if ((rc = check_ptr(x, "x", B == 0, 4)) || (rc = check_ptr(pos, "pos", empty, 8)) || (rc = check_ptr(out, "out", empty, 4)))
+        return rc;
+    if (empty) return 0;
+    const PointsDims p{B, G, c, H, W, Hk, Wk};
+    const cudaError_t e = launch_points_sample_forward(x, pos, out, p, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? 0 : fail_cuda(e, "cape_points_sample_forward launch");
+}
+
+int cape_points_sample_backward(const float* grad_out, const float* x, const float* pos, float* grad_x, float* grad_pos,
+                                int B, int G, int c, int H, int W, int Hk, int Wk, int zero_grad_x, void* stream) {
+    int rc;
+    if ((rc = check_points_dims(B, G, c, H, W, Hk, Wk))) return rc;
+    const bool empty = B == 0 || Hk == 0 || Wk == 0;
+    if ((rc = check_ptr(grad_out, "grad_out", empty, 4)) || (rc = check_ptr(x, "x", B == 0, 4)) ||
+        (rc = check_ptr(pos, "pos", empty, 8)) || (rc = check_ptr(grad_x, "grad_x", B == 0, 4)) ||
+        (rc = check_ptr(grad_pos, "grad_pos", empty, 8)))
+        return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (zero_grad_x && B > 0) {
+        const cudaError_t e = cudaMemsetAsync(grad_x, 0, static_cast<size_t>(B) * G * c * H * W * sizeof(float), s);
+        if (e != cudaSuccess) return fail_cuda(e, "cape_points_sample_backward memset(grad_x)");
+    }
+    if (empty) return 0;
+    const PointsDims p{B, G, c, H, W, Hk, Wk};
+    const cudaError_t e = launch_points_sample_backward(grad_out, x, pos, grad_x, grad_pos, p, s);
+    return e == cudaSuccess ? 0 : fail_cuda(e, "cape_points_sample_backward launch");
+}
+
 // ---- host-buffer round trip ------------------------------------------------------------------------------------
 
 namespace {

@@ -46,9 +46,20 @@ struct BwdArgs {
     bool fused;
 };
 
+// Planar point sampling (MSDeformablePoints): x viewed (B*G, c, H, W), positions (B*G, Hk, Wk, 2), out (B, Hk*Wk, G*c).
+struct PointsDims {
+    int B, G, c, H, W, Hk, Wk;
+};
+
 // Each returns cudaGetLastError() after the launch and bumps the launch counter.
 cudaError_t launch_forward(const FwdArgs& a, cudaStream_t stream);
 cudaError_t launch_backward(const BwdArgs& a, cudaStream_t stream);
+cudaError_t launch_query_pool_forward(const FwdArgs& a, cudaStream_t stream);     // fp32 only
+cudaError_t launch_query_pool_backward(const BwdArgs& a, cudaStream_t stream);    // fp32 only
+cudaError_t launch_points_sample_forward(const float* x, const float* pos, float* out, const PointsDims& p,
+                                         cudaStream_t stream);
+cudaError_t launch_points_sample_backward(const float* gout, const float* x, const float* pos, float* gx, float* gpos,
+                                          const PointsDims& p, cudaStream_t stream);
 
 void count_launch();
 

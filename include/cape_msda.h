@@ -132,6 +132,35 @@ CAPE_API int cape_msda_fused_backward(const void* grad_out, const void* value, c
                                       int value_dtype, int zero_grad_value, void* stream);
 
 /*
+ * Variant samplers (fp32 only; non-default paths of the reference, small problems).
+ *
+ * Query-pooled deformable sampling — TransformerDecoderLayerV4._sample_reference_points,
+ * models/deformable_transformer_v2.py:661-687: the sampling of :115-141, but the weighted sum runs over the queries:
+ *     out[n, l*P+p, m*D+d] = sum_q attention_weights[n,q,m,l,p] * bilinear(V_l[n,:,m,d], sampling_locations[n,q,m,l,p])
+ *   out / grad_out (N, L*P, M*D); every other tensor as in cape_msda_forward / cape_msda_backward.
+ *
+ * Planar point sampling — MSDeformablePoints.forward, models/deformable_points.py:118-128:
+ * F.grid_sample(bilinear, zeros padding, align_corners=True) of a level whose contiguous (B, H*W, C) block is VIEWED as
+ * (B*G, c, H, W) (the reference's reshape at :125, C = G*c), at positions pos (B*G, Hk, Wk, 2) given as (y, x) in
+ * [-1, 1]; out (B, Hk*Wk, G*c) is the layout of :128.  grad_x (same shape as x) is accumulated with atomics
+ * (zero_grad_x = 1 lets the library zero it first); grad_pos (B*G, Hk, Wk, 2) is fully overwritten.
+ */
+CAPE_API int cape_msda_query_pool_forward(const float* value, const int64_t* spatial_shapes_dev,
+                                          const int64_t* level_start_index_dev, const float* sampling_locations,
+                                          const float* attention_weights, float* out, const cape_msda_dims* dims,
+                                          void* stream);
+CAPE_API int cape_msda_query_pool_backward(const float* grad_out, const float* value, const int64_t* spatial_shapes_dev,
+                                           const int64_t* level_start_index_dev, const float* sampling_locations,
+                                           const float* attention_weights, float* grad_value, float* grad_loc,
+                                           float* grad_attn, const cape_msda_dims* dims, int zero_grad_value,
+                                           void* stream);
+CAPE_API int cape_points_sample_forward(const float* x, const float* pos, float* out, int B, int G, int c, int H, int W,
+                                        int Hk, int Wk, void* stream);
+CAPE_API int cape_points_sample_backward(const float* grad_out, const float* x, const float* pos, float* grad_x,
+                                         float* grad_pos, int B, int G, int c, int H, int W, int Hk, int Wk,
+                                         int zero_grad_x, void* stream);
+
+/*
  * Host-buffer round trip used for end-to-end measurement and for callers without device buffers:
  * copies the inputs from (ideally pinned) HOST memory into the caller-provided device workspace, runs forward and,
  * when grad_out_host != NULL, backward, and copies the results back to HOST memory — all enqueued on `stream`.

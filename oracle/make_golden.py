@@ -161,6 +161,77 @@ def record_layer_cases(syn):
           f"{float((out.detach() - torch.cat(steps, 1)).abs().max()):.2e}")
 
 
+def record_variant_cases(syn):
+    """Decoder V4's inline sampler (deformable_transformer_v2.py:661-687) and MSDeformablePoints
+    (deformable_points.py:31-130), run from the reference's own code."""
+    import types
+    import importlib
+    dt, v2, _ = load_reference_v2()
+    dp = importlib.import_module("models.deformable_points")
+    torch.manual_seed(777)
+    # ---- V4 sampler: call the reference method on a stand-in object that carries the attributes it reads
+    d_model, n_heads, n_levels, n_points = 64, 2, 3, 4
+    shapes = ((6, 8), (3, 4), (2, 2))
+    s = sum(h * w for h, w in shapes)
+    shapes_t = torch.tensor(shapes, dtype=torch.int64)
+    starts_t = torch.tensor(syn.level_start_index(shapes), dtype=torch.int64)
+    holder = types.SimpleNamespace(
+        sampling_offsets=torch.nn.Linear(d_model, n_heads * n_levels * n_points * 2),
+        attention_weights=torch.nn.Linear(d_model, n_heads * n_levels * n_points),
+        source_proj=torch.nn.Linear(d_model, d_model), n_heads=n_heads, n_levels=n_levels, n_points=n_points,
+        d_model=d_model)
+    with torch.no_grad():
+        holder.sampling_offsets.weight.mul_(3.0)          # spread the samples over the maps (incl. out of bounds)
+        holder.sampling_offsets.bias.add_(torch.rand_like(holder.sampling_offsets.bias) * 4)
+    n, lq = 2, 7
+    query = torch.randn(n, lq, d_model, requires_grad=True)
+    src = torch.randn(n, s, d_model, requires_grad=True)
+    out = v2.TransformerDecoderLayerV4._sample_reference_points(holder, query, src, shapes_t, starts_t)
+    gout = torch.randn_like(out)
+    mods = [holder.sampling_offsets, holder.attention_weights, holder.source_proj]
+    params = [p for m_ in mods for p in m_.parameters()]
+    grads = torch.autograd.grad(out, [query, src] + params, gout)
+    rec = {"query": query.detach().numpy(), "src": src.detach().numpy(), "spatial_shapes": shapes_t.numpy(),
+           "level_start_index": starts_t.numpy(), "out": out.detach().numpy(), "grad_output": gout.numpy(),
+           "grad_query": grads[0].numpy(), "grad_src": grads[1].numpy(), "d_model": d_model, "n_heads": n_heads,
+           "n_levels": n_levels, "n_points": n_points}
+    names = ["sampling_offsets", "attention_weights", "source_proj"]
+    gi = 2
+    for name, m_ in zip(names, mods):
+        for pn, p in m_.named_parameters():
+            rec[f"param.{name}.{pn}"] = p.detach().numpy()
+            rec[f"grad_param.{name}.{pn}"] = grads[gi].numpy()
+            gi += 1
+    path = os.path.join(OUT_DIR, "v4_sampler.npz")
+    np.savez_compressed(path, **rec)
+    print(f"v4_sampler: {os.path.getsize(path) / 1024:.1f} KiB")
+
+    # ---- MSDeformablePoints
+    embed, n_levels, n_heads = 64, 4, 2
+    shapes = ((32, 16), (16, 8), (8, 4), (4, 2))
+    s = sum(h * w for h, w in shapes)
+    shapes_l = [list(hw) for hw in shapes]
+    for tag, factor in (("clamp", -1), ("tanh", 2.0)):
+        mod = dp.MSDeformablePoints(embed, n_levels, n_heads, offset_range_factor=factor)
+        with torch.no_grad():
+            for p in mod.parameters():
+                p.add_(torch.randn_like(p) * 0.3)
+        x = torch.randn(2, s, embed, requires_grad=True)
+        out = mod(x, shapes_l, None)
+        gout = torch.randn_like(out)
+        params = dict(mod.named_parameters())
+        grads = torch.autograd.grad(out, [x] + list(params.values()), gout)
+        rec = {"x": x.detach().numpy(), "spatial_shapes": np.array(shapes, dtype=np.int64), "out": out.detach().numpy(),
+               "grad_output": gout.numpy(), "grad_x": grads[0].numpy(), "embed_dim": embed, "n_levels": n_levels,
+               "n_heads": n_heads, "offset_range_factor": factor}
+        for (k, v), g_ in zip(params.items(), grads[1:]):
+            rec["param." + k] = v.detach().numpy()
+            rec["grad_param." + k] = g_.numpy()
+        path = os.path.join(OUT_DIR, f"deformable_points_{tag}.npz")
+        np.savez_compressed(path, **rec)
+        print(f"deformable_points_{tag}: {os.path.getsize(path) / 1024:.1f} KiB, out {tuple(out.shape)}")
+
+
 def run_reference(ref, value, shapes, loc, attn, gout, dtype):
     v = value.to(dtype).clone().requires_grad_(True)
     l = loc.to(dtype).clone().requires_grad_(True)
@@ -289,6 +360,7 @@ def main():
         1, 5, ((4, 4), (2, 2), (1, 1)), n_heads=2, head_dim=64, n_points=8, dist="uniform", seed=5))
     record_module_case(ref, syn)
     record_layer_cases(syn)
+    record_variant_cases(syn)
 
 
 if __name__ == "__main__":

@@ -25,7 +25,7 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["level_start_index", "msda_forward", "msda_backward", "msda_decode"]
+__all__ = ["level_start_index", "msda_forward", "msda_backward", "msda_decode", "query_pool_forward", "points_sample"]
 
 
 def level_start_index(spatial_shapes) -> np.ndarray:
@@ -178,3 +178,62 @@ def msda_decode(value_cache, spatial_shapes, level_start, reference_points, samp
     normalizer = np.stack([shapes[:, 1], shapes[:, 0]], -1).astype(dtype)  # (L, 2) = (W, H)
     loc = ref[:, :, None, :, None, :] + off / normalizer[None, None, None, :, None, :]
     return msda_forward(value_cache, shapes, level_start, loc, attn, dtype=dtype)
+
+
+def query_pool_forward(value, spatial_shapes, level_start, sampling_locations, attention_weights,
+                       dtype=np.float64) -> np.ndarray:
+    """Closed form of decoder V4's inline sampler, /root/reference/models/deformable_transformer_v2.py:670-687:
+    the per-sample bilinear values of :func:`msda_forward`, but weighted and summed over the QUERIES (``:686``), one
+    output row per (level, point).  Returns (N, L*P, M*D)."""
+    dtype = np.dtype(dtype).type
+    value = np.asarray(value, dtype=dtype)
+    loc = np.asarray(sampling_locations, dtype=dtype)
+    attn = np.asarray(attention_weights, dtype=dtype)
+    shapes = np.asarray(spatial_shapes, dtype=np.int64).reshape(-1, 2)
+    starts = np.asarray(level_start, dtype=np.int64).reshape(-1)
+    N, S, M, D = value.shape
+    _, Lq, _, L, P, _ = loc.shape
+    out = np.zeros((N, L, P, M, D), dtype=dtype)
+    n_idx = np.arange(N).reshape(N, 1, 1, 1)
+    m_idx = np.arange(M).reshape(1, 1, M, 1)
+    for l in range(L):
+        H, W = int(shapes[l, 0]), int(shapes[l, 1])
+        x0, y0, lx, ly = _corner_terms(loc[:, :, :, l], H, W, dtype)
+        a = attn[:, :, :, l]                                      # (N, Lq, M, P)
+        for dy, dx in _CORNERS:
+            xi, yi = x0 + dx, y0 + dy
+            valid = (xi >= 0) & (xi < W) & (yi >= 0) & (yi < H)
+            w = np.where(valid, a * (lx if dx else dtype(1) - lx) * (ly if dy else dtype(1) - ly), dtype(0))
+            rows = starts[l] + np.clip(yi, 0, H - 1) * W + np.clip(xi, 0, W - 1)
+            v = value[n_idx, rows, m_idx]                         # (N, Lq, M, P, D)
+            out[:, l] += np.einsum("nqmp,nqmpd->npmd", w, v)
+    return out.reshape(N, L * P, M * D)
+
+
+def points_sample(x, pos, n_heads, height, width, dtype=np.float64) -> np.ndarray:
+    """Closed form of MSDeformablePoints' resampling, /root/reference/models/deformable_points.py:124-128:
+    ``grid_sample(bilinear, zeros padding, align_corners=True)`` — pixel coordinate ``(g + 1) / 2 * (size - 1)`` — of the
+    contiguous ``(B, H*W, C)`` block viewed as ``(B*G, c, H, W)`` at ``pos`` (B*G, Hk, Wk, 2) given as (y, x).
+    Returns (B, Hk*Wk, C)."""
+    dtype = np.dtype(dtype).type
+    x = np.ascontiguousarray(np.asarray(x, dtype=dtype))
+    pos = np.asarray(pos, dtype=dtype)
+    B, _, C = x.shape
+    c = C // n_heads
+    img = x.reshape(B * n_heads, c, height, width)
+    BG, Hk, Wk, _ = pos.shape
+    py = (pos[..., 0] + dtype(1)) * dtype(0.5) * dtype(height - 1)
+    px = (pos[..., 1] + dtype(1)) * dtype(0.5) * dtype(width - 1)
+    x0f, y0f = np.floor(px), np.floor(py)
+    lx, ly = px - x0f, py - y0f
+    x0 = np.clip(x0f, -2, width + 1).astype(np.int64)
+    y0 = np.clip(y0f, -2, height + 1).astype(np.int64)
+    out = np.zeros((BG, c, Hk, Wk), dtype=dtype)
+    bg = np.arange(BG).reshape(BG, 1, 1)
+    for dy, dx in _CORNERS:
+        xi, yi = x0 + dx, y0 + dy
+        valid = (xi >= 0) & (xi < width) & (yi >= 0) & (yi < height)
+        w = np.where(valid, (lx if dx else dtype(1) - lx) * (ly if dy else dtype(1) - ly), dtype(0))
+        v = img[bg, :, np.clip(yi, 0, height - 1), np.clip(xi, 0, width - 1)]      # (BG, Hk, Wk, c)
+        out += (w[..., None] * v).transpose(0, 3, 1, 2)
+    return out.reshape(B, n_heads, c, Hk * Wk).transpose(0, 3, 1, 2).reshape(B, Hk * Wk, C)

@@ -15,7 +15,7 @@ from __future__ import annotations
 import torch
 import torch.nn.functional as F
 
-__all__ = ["msda_core", "msda_core_fwd_bwd", "msda_module_forward", "msda_decode"]
+__all__ = ["msda_core", "msda_core_fwd_bwd", "msda_module_forward", "msda_decode", "query_pool_core", "points_sample"]
 
 
 def _as_hw_list(spatial_shapes):
@@ -102,3 +102,84 @@ def msda_decode(value_cache, spatial_shapes, reference_points, sampling_offsets,
     wh = torch.tensor([[w, h] for h, w in hw], dtype=sampling_offsets.dtype, device=sampling_offsets.device)
     loc = reference_points[:, :, None, :, None, :] + sampling_offsets / wh[None, None, None, :, None, :]
     return msda_core(value_cache, hw, loc, attn)
+
+
+def query_pool_core(value, spatial_shapes, sampling_locations, attention_weights):
+    """The sampling of TransformerDecoderLayerV4._sample_reference_points
+    (/root/reference/models/deformable_transformer_v2.py:670-687): per-level grid_sample as in :115-141, then the weighted
+    sum over the QUERIES (dim -2 of the stacked samples).  Returns (N, L*P, M*D)."""
+    n, _, m, d = value.shape
+    lq, n_levels, n_points = sampling_locations.shape[1], sampling_locations.shape[3], sampling_locations.shape[4]
+    hw = _as_hw_list(spatial_shapes)
+    per_level = torch.split(value, [h * w for h, w in hw], dim=1)
+    grid_all = sampling_locations * 2 - 1                                                          # :673
+    sampled = []
+    for lvl in range(n_levels):
+        h, w = hw[lvl]
+        img = per_level[lvl].permute(0, 2, 3, 1).reshape(n * m, d, h, w)                           # :677
+        grid = grid_all[:, :, :, lvl].permute(0, 2, 1, 3, 4).reshape(n * m, lq, n_points, 2)        # :679
+        sampled.append(F.grid_sample(img, grid, mode="bilinear", padding_mode="zeros", align_corners=False))
+    weights = attention_weights.permute(0, 2, 1, 3, 4).reshape(n * m, 1, lq, n_levels * n_points)   # :685
+    stacked = torch.stack(sampled, dim=3).reshape(n * m, d, lq, n_levels * n_points)
+    out = (stacked * weights).sum(dim=2)                                                            # :686 sum over queries
+    return out.reshape(n, m * d, n_levels * n_points).permute(0, 2, 1).contiguous()
+
+
+def points_sample(x, pos, n_heads, height, width):
+    """MSDeformablePoints' resampling (/root/reference/models/deformable_points.py:124-128): the contiguous (B, H*W, C)
+    block is viewed as (B*G, c, H, W), sampled with align_corners=True at pos given as (y, x), and laid out
+    (B, Hk*Wk, G*c)."""
+    b, _, c_total = x.shape
+    c = c_total // n_heads
+    img = x.contiguous().reshape(b * n_heads, c, height, width)
+    s = F.grid_sample(img, pos[..., (1, 0)], mode="bilinear", align_corners=True)                   # (B*G, c, Hk, Wk)
+    hk, wk = s.shape[2], s.shape[3]
+    return s.reshape(b, n_heads, c, hk * wk).permute(0, 3, 1, 2).reshape(b, hk * wk, c_total)
+
+
+def v4_sample_reference_points(w, query, src, spatial_shapes, n_heads, n_levels, n_points):
+    """TransformerDecoderLayerV4._sample_reference_points (/root/reference/models/deformable_transformer_v2.py:661-687)
+    with the three Linear layers given as a dict ``w`` of ``{sampling_offsets,attention_weights,source_proj}.{weight,bias}``."""
+    n, lq, _ = query.shape
+    hw = _as_hw_list(spatial_shapes)
+    off = F.linear(query, w["sampling_offsets.weight"], w["sampling_offsets.bias"]).view(
+        n, lq, n_heads, n_levels, n_points, 2)                                                      # :663
+    wh = torch.tensor([[w_, h_] for h_, w_ in hw], dtype=query.dtype)                               # :664
+    loc = off / wh[None, None, None, :, None, :]                                                    # :665
+    attn = F.linear(query, w["attention_weights.weight"], w["attention_weights.bias"]).view(
+        n, lq, n_heads, n_levels * n_points)
+    attn = F.softmax(attn, 1).view(n, lq, n_heads, n_levels, n_points)                              # :667 (over queries)
+    value = F.linear(src, w["source_proj.weight"], w["source_proj.bias"]).view(n, src.shape[1], n_heads, -1)   # :669
+    return query_pool_core(value, hw, loc, attn)
+
+
+def deformable_points_forward(w, x, spatial_shapes, n_heads, offset_range_factor):
+    """MSDeformablePoints.forward (/root/reference/models/deformable_points.py:91-130) with the parameters given as a dict
+    keyed like the reference's state_dict (``conv_offset.{i}.{0,1.norm,3}.*``, ``proj_q.{i}.*``)."""
+    b, _, c_total = x.shape
+    c = c_total // n_heads
+    hw = _as_hw_list(spatial_shapes)
+    n_levels = len(hw)
+    out = []
+    for i, cur in enumerate(x.split([h * w_ for h, w_ in hw], dim=1)):
+        h, w_ = hw[i]
+        ksz, stride = (n_levels - 1 - i) * 2 + 1, 2 ** (n_levels - i)                               # :54-55
+        q = F.conv2d(cur.permute(0, 2, 1).reshape(b, c_total, h, w_), w[f"proj_q.{i}.weight"], w[f"proj_q.{i}.bias"])
+        q_off = q.reshape(b * n_heads, c, h, w_)                                                    # :113
+        t = F.conv2d(q_off, w[f"conv_offset.{i}.0.weight"], w[f"conv_offset.{i}.0.bias"], stride, ksz // 2, 1, n_heads)
+        t = F.layer_norm(t.permute(0, 2, 3, 1), (c,), w[f"conv_offset.{i}.1.norm.weight"],
+                         w[f"conv_offset.{i}.1.norm.bias"]).permute(0, 3, 1, 2)
+        offset = F.conv2d(F.gelu(t), w[f"conv_offset.{i}.3.weight"])                                # (B*G, 2, Hk, Wk)
+        hk, wk = offset.shape[2], offset.shape[3]
+        if offset_range_factor >= 0:                                                                # :117-119
+            rng = torch.tensor([1.0 / hk, 1.0 / wk]).reshape(1, 2, 1, 1)
+            offset = offset.tanh().mul(rng).mul(offset_range_factor)
+        offset = offset.permute(0, 2, 3, 1)
+        ys = torch.linspace(0.5, hk - 0.5, hk, dtype=x.dtype) / hk * 2 - 1                          # :77-87
+        xs = torch.linspace(0.5, wk - 0.5, wk, dtype=x.dtype) / wk * 2 - 1
+        gy, gx = torch.meshgrid(ys, xs, indexing="ij")
+        pos = offset + torch.stack((gy, gx), -1)[None]
+        if offset_range_factor < 0:
+            pos = pos.clamp(-1.0, 1.0)                                                              # :122
+        out.append(points_sample(cur, pos, n_heads, h, w_))
+    return torch.cat(out, dim=1)

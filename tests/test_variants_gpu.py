@@ -1,0 +1,129 @@
+"""Parity of the variant samplers on the GPU: decoder V4's query-pooled sampler and
+MSDeformablePoints, against fixtures recorded from the reference's own code (oracle/make_golden.py) and against the
+oracle's closed forms on seeded inputs.  Tolerances as in test_msda_gpu.py."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cape_b200
+from cape_b200 import synthetic, variants
+from oracle import msda_numpy, msda_torch
+from tests.conftest import GOLDEN, rel_err
+
+pytestmark = pytest.mark.gpu
+
+FWD_TOL_F32 = 1e-5
+GRAD_TOL_F32 = 1e-4
+
+
+def _cuda(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def _linear(g, name):
+    w, b = g[f"param.{name}.weight"], g[f"param.{name}.bias"]
+    lin = torch.nn.Linear(w.shape[1], w.shape[0])
+    lin.load_state_dict({"weight": torch.from_numpy(w), "bias": torch.from_numpy(b)})
+    return lin.cuda()
+
+
+def test_v4_sampler_matches_reference_method_fixture():
+    g = np.load(os.path.join(GOLDEN, "v4_sampler.npz"))
+    mods = {k: _linear(g, k) for k in ("sampling_offsets", "attention_weights", "source_proj")}
+    query, src = _cuda(g["query"]).requires_grad_(True), _cuda(g["src"]).requires_grad_(True)
+    before = cape_b200.launch_count()
+    out = cape_b200.sample_reference_points(query, src, _cuda(g["spatial_shapes"]), _cuda(g["level_start_index"]),
+                                            mods["sampling_offsets"], mods["attention_weights"], mods["source_proj"],
+                                            int(g["n_heads"]), int(g["n_levels"]), int(g["n_points"]))
+    assert cape_b200.launch_count() == before + 1
+    assert rel_err(out.detach().cpu().numpy(), g["out"]) < FWD_TOL_F32
+    params = [p for m in mods.values() for p in m.parameters()]
+    grads = torch.autograd.grad(out, [query, src] + params, _cuda(g["grad_output"]))
+    assert rel_err(grads[0].cpu().numpy(), g["grad_query"]) < GRAD_TOL_F32
+    assert rel_err(grads[1].cpu().numpy(), g["grad_src"]) < GRAD_TOL_F32
+    i = 2
+    for name, m in mods.items():
+        for pn, _ in m.named_parameters():
+            assert rel_err(grads[i].cpu().numpy(), g[f"grad_param.{name}.{pn}"]) < GRAD_TOL_F32, (name, pn)
+            i += 1
+
+
+@pytest.mark.parametrize("n,lq,shapes,m,d,p", [(2, 200, synthetic.CAPE_PYRAMID, 8, 32, 4), (1, 1, ((5, 3), (2, 2)), 3, 16, 2),
+                                               (3, 17, ((9, 7),), 2, 64, 8)])
+def test_query_pool_op_vs_oracle(n, lq, shapes, m, d, p):
+    inp = synthetic.make_inputs(n, lq, shapes, n_heads=m, head_dim=d, n_points=p, dist="uniform", seed=11)
+    # weights soft-maxed over the queries, as the V4 layer does
+    logits = torch.randn(n, lq, m, len(shapes), p, generator=torch.Generator().manual_seed(5))
+    attn = logits.softmax(1)
+    v = inp["value"].cuda().requires_grad_(True)
+    loc = inp["sampling_locations"].cuda().requires_grad_(True)
+    a = attn.cuda().requires_grad_(True)
+    out = cape_b200.ms_deform_attn_query_pool(v, inp["spatial_shapes"].cuda(), inp["level_start_index"].cuda(), loc, a)
+    want = msda_numpy.query_pool_forward(inp["value"].numpy(), inp["spatial_shapes"].numpy(),
+                                         inp["level_start_index"].numpy(), inp["sampling_locations"].numpy(), attn.numpy())
+    assert rel_err(out.detach().cpu().numpy(), want) < FWD_TOL_F32
+    gout = torch.randn(out.shape, generator=torch.Generator().manual_seed(6))
+    gv, gl, ga = torch.autograd.grad(out, (v, loc, a), gout.cuda())
+    vr, lr, ar = (t.clone().requires_grad_(True) for t in (inp["value"], inp["sampling_locations"], attn))
+    ref = msda_torch.query_pool_core(vr, inp["spatial_shapes"].tolist(), lr, ar)
+    rv, rl, ra = torch.autograd.grad(ref, (vr, lr, ar), gout)
+    assert rel_err(gv.cpu().numpy(), rv.numpy()) < GRAD_TOL_F32
+    assert rel_err(gl.cpu().numpy(), rl.numpy()) < GRAD_TOL_F32
+    assert rel_err(ga.cpu().numpy(), ra.numpy()) < GRAD_TOL_F32
+
+
+@pytest.mark.parametrize("tag", ["clamp", "tanh"])
+def test_deformable_points_mirror_matches_reference_module_fixture(tag):
+    g = np.load(os.path.join(GOLDEN, f"deformable_points_{tag}.npz"))
+    mod = cape_b200.MSDeformablePoints(int(g["embed_dim"]), int(g["n_levels"]), int(g["n_heads"]),
+                                       offset_range_factor=float(g["offset_range_factor"]))
+    state = {k[len("param."):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("param.")}
+    assert sorted(state) == sorted(mod.state_dict())           # same parameter names as the reference module
+    mod.load_state_dict(state)
+    mod = mod.cuda()
+    x = _cuda(g["x"]).requires_grad_(True)
+    before = cape_b200.launch_count()
+    out = mod(x, g["spatial_shapes"].tolist(), None)
+    assert cape_b200.launch_count() == before + int(g["n_levels"])
+    assert rel_err(out.detach().cpu().numpy(), g["out"]) < FWD_TOL_F32
+    names = [k for k, _ in mod.named_parameters()]
+    grads = torch.autograd.grad(out, [x] + list(mod.parameters()), _cuda(g["grad_output"]))
+    assert rel_err(grads[0].cpu().numpy(), g["grad_x"]) < GRAD_TOL_F32
+    for name, gr in zip(names, grads[1:]):
+        assert rel_err(gr.cpu().numpy(), g["grad_param." + name]) < GRAD_TOL_F32, name
+
+
+def test_points_sample_op_vs_oracle_incl_borders():
+    gen = torch.Generator().manual_seed(9)
+    b, heads, c, h, w = 3, 4, 8, 16, 12
+    x = torch.randn(b, h * w, heads * c, generator=gen)
+    pos = torch.rand(b * heads, 5, 6, 2, generator=gen) * 2.6 - 1.3       # some positions beyond [-1, 1]
+    pos[0, 0, 0] = torch.tensor([-1.0, 1.0])
+    pos[0, 0, 1] = torch.tensor([1.0, -1.0])
+    xc, pc = x.cuda().requires_grad_(True), pos.cuda().requires_grad_(True)
+    out = cape_b200.points_sample(xc, pc, heads, h, w)
+    want = msda_numpy.points_sample(x.numpy(), pos.numpy(), heads, h, w)
+    assert rel_err(out.detach().cpu().numpy(), want) < FWD_TOL_F32
+    gout = torch.randn(out.shape, generator=gen)
+    gx, gp = torch.autograd.grad(out, (xc, pc), gout.cuda())
+    xr, pr = x.clone().requires_grad_(True), pos.clone().requires_grad_(True)
+    rx, rp = torch.autograd.grad(msda_torch.points_sample(xr, pr, heads, h, w), (xr, pr), gout)
+    assert rel_err(gx.cpu().numpy(), rx.numpy()) < GRAD_TOL_F32
+    assert rel_err(gp.cpu().numpy(), rp.numpy()) < GRAD_TOL_F32
+
+
+def test_variant_ops_reject_cpu_tensors_and_register_cleanly():
+    inp = synthetic.make_inputs(1, 3, ((4, 4), (2, 2)), n_heads=2, head_dim=8, n_points=2, seed=1)
+    with pytest.raises((RuntimeError, NotImplementedError)):
+        cape_b200.ms_deform_attn_query_pool(inp["value"], inp["spatial_shapes"], inp["level_start_index"],
+                                            inp["sampling_locations"], inp["attention_weights"])
+    args = (inp["value"].cuda().requires_grad_(True), inp["spatial_shapes"].cuda(), inp["level_start_index"].cuda(),
+            inp["sampling_locations"].cuda().requires_grad_(True), inp["attention_weights"].cuda().requires_grad_(True))
+    torch.library.opcheck(torch.ops.cape.ms_deform_attn_query_pool.default, args,
+                          test_utils=("test_schema", "test_faketensor", "test_autograd_registration"))
+    x = torch.randn(1, 12, 4, device="cuda", requires_grad=True)
+    pos = (torch.rand(2, 2, 2, 2, device="cuda") * 2 - 1).requires_grad_(True)
+    torch.library.opcheck(torch.ops.cape.points_sample.default, (x, pos, 2, 4, 3),
+                          test_utils=("test_schema", "test_faketensor", "test_autograd_registration"))
