@@ -22,10 +22,15 @@ from .patch import patch_reference, unpatch_reference
 from .layers import (DeformableTransformerEncoder, DeformableTransformerEncoderLayer, IncrementalDecoder, KVCache,
                      TransformerDecoderLayer)
 from .variants import MSDeformablePoints, ms_deform_attn_query_pool, points_sample, sample_reference_points
+from .sequence import TokenState, TokenizerSpec, seq_embed
+from .transformer import (MLP, AutoregressiveGenerator, DeformableTransformer, TransformerDecoder, build_prediction_heads,
+                          generate_eager)
 from . import synthetic
 
 __all__ = ["MSDeformAttn", "ValueCache", "MSDeformAttnFunction", "ms_deform_attn", "ms_deform_attn_core_pytorch",
            "ms_deform_attn_decode", "ms_deform_attn_fused", "level_start_index_from_shapes", "patch_reference", "unpatch_reference",
            "library_available", "launch_count", "CapeLibraryError", "synthetic", "DeformableTransformerEncoder",
            "DeformableTransformerEncoderLayer", "TransformerDecoderLayer", "KVCache", "IncrementalDecoder", "MSDeformablePoints",
-           "ms_deform_attn_query_pool", "points_sample", "sample_reference_points"]
+           "ms_deform_attn_query_pool", "points_sample", "sample_reference_points", "seq_embed", "TokenizerSpec", "TokenState",
+           "TransformerDecoder", "DeformableTransformer", "MLP", "build_prediction_heads", "AutoregressiveGenerator",
+           "generate_eager"]

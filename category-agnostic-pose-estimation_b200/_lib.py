@@ -28,6 +28,21 @@ class Dims(ctypes.Structure):
                 ("Lq", ctypes.c_int32), ("L", ctypes.c_int32), ("P", ctypes.c_int32)]
 
 
+class Tokenizer(ctypes.Structure):
+    """``cape_tokenizer`` (include/cape_msda.h)."""
+    _fields_ = [("num_bins", ctypes.c_int32), ("min_len", ctypes.c_int32), ("bos", ctypes.c_int64),
+                ("eos", ctypes.c_int64), ("sep", ctypes.c_int64), ("pad", ctypes.c_int64), ("cls", ctypes.c_int64),
+                ("type_coord", ctypes.c_int32), ("type_sep", ctypes.c_int32), ("type_eos", ctypes.c_int32),
+                ("type_cls", ctypes.c_int32)]
+
+
+class TokenState(ctypes.Structure):
+    """``cape_token_state`` (include/cape_msda.h): device pointers of the per-sample generation buffers."""
+    _fields_ = [(name, ctypes.c_void_p) for name in (
+        "unfinished", "finish_step", "seq11", "seq12", "seq21", "seq22", "delta_x1", "delta_x2", "delta_y1", "delta_y2",
+        "pred_logits", "pred_coords", "gen_kind", "gen_xy")] + [("max_len", ctypes.c_int64)]
+
+
 _lock = threading.Lock()
 _lib = None
 _load_error = None
@@ -46,6 +61,9 @@ _SIGNATURES = {
     "cape_msda_query_pool_backward": (_i, [_vp] * 9 + [ctypes.POINTER(Dims), _i, _vp]),
     "cape_points_sample_forward": (_i, [_vp] * 3 + [_i] * 7 + [_vp]),
     "cape_points_sample_backward": (_i, [_vp] * 5 + [_i] * 8 + [_vp]),
+    "cape_seq_embed_forward": (_i, [_vp] * 10 + [ctypes.c_int64, _i, _i, _vp]),
+    "cape_seq_embed_backward": (_i, [_vp] * 10 + [ctypes.c_int64, _i, _i, ctypes.c_int64, _i, _vp]),
+    "cape_token_step": (_i, [_vp, _vp, _vp, ctypes.POINTER(TokenState), ctypes.POINTER(Tokenizer), _i, _i, _vp]),
     "cape_msda_host_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(Dims), _i]),
     "cape_msda_forward_backward_host": (_i, [_vp] * 10 + [ctypes.POINTER(Dims), _vp, ctypes.c_size_t, _vp]),
 }

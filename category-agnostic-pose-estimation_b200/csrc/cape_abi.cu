@@ -348,6 +348,91 @@ int cape_points_sample_backward(const float* grad_out, const float* x, const flo
     return e == cudaSuccess ? 0 : fail_cuda(e, "cape_points_sample_backward launch");
 }
 
+// ---- sequence side of the decoder ---------------------------------------------------------------------------------
+
+namespace {
+int check_seq_embed(const int64_t* const* seqs, const float* const* deltas, int64_t tokens, int C, int V) {
+    if (tokens < 0 || C <= 0 || C % 4 != 0 || V <= 0)
+        return fail(CAPE_ERR_BAD_DIMS, "bad token-embedding dimensions (tokens=%lld C=%d V=%d; C must be a multiple of 4)",
+                    static_cast<long long>(tokens), C, V);
+    static const char* const seq_names[4] = {"seq11", "seq12", "seq21", "seq22"};
+    static const char* const delta_names[4] = {"delta_x1", "delta_x2", "delta_y1", "delta_y2"};
+    int rc;
+    for (int k = 0; k < 4; ++k) {
+        if ((rc = check_ptr(seqs[k], seq_names[k], tokens == 0, 8))) return rc;
+        if ((rc = check_ptr(deltas[k], delta_names[k], tokens == 0, 4))) return rc;
+    }
+    return 0;
+}
+}  // namespace
+
+int cape_seq_embed_forward(const float* table, const int64_t* seq11, const int64_t* seq12, const int64_t* seq21,
+                           const int64_t* seq22, const float* delta_x1, const float* delta_x2, const float* delta_y1,
+                           const float* delta_y2, float* out, int64_t tokens, int C, int V, void* stream) {
+    const int64_t* seqs[4] = {seq11, seq12, seq21, seq22};
+    const float* deltas[4] = {delta_x1, delta_x2, delta_y1, delta_y2};
+    int rc;
+    if ((rc = check_seq_embed(seqs, deltas, tokens, C, V))) return rc;
+    if ((rc = check_ptr(table, "table", false)) || (rc = check_ptr(out, "out", tokens == 0))) return rc;
+    if (tokens == 0) return 0;
+    SeqEmbedArgs a{};
+    a.table = table;
+    a.seq11 = seq11, a.seq12 = seq12, a.seq21 = seq21, a.seq22 = seq22;
+    a.dx1 = delta_x1, a.dx2 = delta_x2, a.dy1 = delta_y1, a.dy2 = delta_y2;
+    a.out = out;
+    a.tokens = tokens, a.C = C, a.V = V;
+    const cudaError_t e = launch_seq_embed_forward(a, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? 0 : fail_cuda(e, "cape_seq_embed_forward launch");
+}
+
+int cape_seq_embed_backward(const float* grad_out, const int64_t* seq11, const int64_t* seq12, const int64_t* seq21,
+                            const int64_t* seq22, const float* delta_x1, const float* delta_x2, const float* delta_y1,
+                            const float* delta_y2, float* grad_table, int64_t tokens, int C, int V, int64_t padding_idx,
+                            int zero_grad_table, void* stream) {
+    const int64_t* seqs[4] = {seq11, seq12, seq21, seq22};
+    const float* deltas[4] = {delta_x1, delta_x2, delta_y1, delta_y2};
+    int rc;
+    if ((rc = check_seq_embed(seqs, deltas, tokens, C, V))) return rc;
+    if ((rc = check_ptr(grad_out, "grad_out", tokens == 0)) || (rc = check_ptr(grad_table, "grad_table", false))) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (zero_grad_table) {
+        const cudaError_t e = cudaMemsetAsync(grad_table, 0, static_cast<size_t>(V) * C * sizeof(float), s);
+        if (e != cudaSuccess) return fail_cuda(e, "cape_seq_embed_backward memset(grad_table)");
+    }
+    if (tokens == 0) return 0;
+    SeqEmbedArgs a{};
+    a.grad_out = grad_out;
+    a.seq11 = seq11, a.seq12 = seq12, a.seq21 = seq21, a.seq22 = seq22;
+    a.dx1 = delta_x1, a.dx2 = delta_x2, a.dy1 = delta_y1, a.dy2 = delta_y2;
+    a.grad_table = grad_table;
+    a.tokens = tokens, a.C = C, a.V = V, a.padding_idx = padding_idx;
+    const cudaError_t e = launch_seq_embed_backward(a, s);
+    return e == cudaSuccess ? 0 : fail_cuda(e, "cape_seq_embed_backward launch");
+}
+
+int cape_token_step(const float* cls_logits, const float* reg, int64_t* step_dev, const cape_token_state* st,
+                    const cape_tokenizer* tk, int B, int n_classes, void* stream) {
+    if (!st || !tk) return fail(CAPE_ERR_NULL_PTR, "%s is NULL", !st ? "state" : "tokenizer");
+    if (B < 0 || n_classes <= 0 || st->max_len <= 0 || tk->num_bins < 2)
+        return fail(CAPE_ERR_BAD_DIMS, "bad token-step dimensions (B=%d n_classes=%d max_len=%lld num_bins=%d)", B, n_classes,
+                    static_cast<long long>(st->max_len), tk->num_bins);
+    int rc;
+    const bool empty = B == 0;
+    if ((rc = check_ptr(step_dev, "step_dev", false, 8)) || (rc = check_ptr(cls_logits, "cls_logits", empty, 4)) ||
+        (rc = check_ptr(reg, "reg", empty, 4)) || (rc = check_ptr(st->unfinished, "state.unfinished", empty, 4)) ||
+        (rc = check_ptr(st->finish_step, "state.finish_step", empty, 8)) ||
+        (rc = check_ptr(st->seq11, "state.seq11", empty, 8)) || (rc = check_ptr(st->seq12, "state.seq12", empty, 8)) ||
+        (rc = check_ptr(st->seq21, "state.seq21", empty, 8)) || (rc = check_ptr(st->seq22, "state.seq22", empty, 8)) ||
+        (rc = check_ptr(st->delta_x1, "state.delta_x1", empty, 4)) || (rc = check_ptr(st->delta_x2, "state.delta_x2", empty, 4)) ||
+        (rc = check_ptr(st->delta_y1, "state.delta_y1", empty, 4)) || (rc = check_ptr(st->delta_y2, "state.delta_y2", empty, 4)) ||
+        (rc = check_ptr(st->pred_logits, "state.pred_logits", empty, 4)) ||
+        (rc = check_ptr(st->pred_coords, "state.pred_coords", empty, 4)) ||
+        (rc = check_ptr(st->gen_kind, "state.gen_kind", empty, 4)) || (rc = check_ptr(st->gen_xy, "state.gen_xy", empty, 4)))
+        return rc;
+    const cudaError_t e = launch_token_step(cls_logits, reg, step_dev, *st, *tk, B, n_classes, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? 0 : fail_cuda(e, "cape_token_step launch");
+}
+
 // ---- host-buffer round trip ------------------------------------------------------------------------------------
 
 namespace {

@@ -51,6 +51,19 @@ struct PointsDims {
     int B, G, c, H, W, Hk, Wk;
 };
 
+// Bilinear token embedding (TransformerDecoder._seq_embed); forward uses table / out, backward grad_out / grad_table.
+struct SeqEmbedArgs {
+    const float* table;
+    const float* grad_out;
+    const int64_t *seq11, *seq12, *seq21, *seq22;
+    const float *dx1, *dx2, *dy1, *dy2;
+    float* out;
+    float* grad_table;
+    int64_t tokens;
+    int C, V;
+    int64_t padding_idx;
+};
+
 // Each returns cudaGetLastError() after the launch and bumps the launch counter.
 cudaError_t launch_forward(const FwdArgs& a, cudaStream_t stream);
 cudaError_t launch_backward(const BwdArgs& a, cudaStream_t stream);
@@ -60,6 +73,10 @@ cudaError_t launch_points_sample_forward(const float* x, const float* pos, float
                                          cudaStream_t stream);
 cudaError_t launch_points_sample_backward(const float* gout, const float* x, const float* pos, float* gx, float* gpos,
                                           const PointsDims& p, cudaStream_t stream);
+cudaError_t launch_seq_embed_forward(const SeqEmbedArgs& a, cudaStream_t stream);
+cudaError_t launch_seq_embed_backward(const SeqEmbedArgs& a, cudaStream_t stream);
+cudaError_t launch_token_step(const float* cls_logits, const float* reg, int64_t* step_dev, const cape_token_state& st,
+                              const cape_tokenizer& tk, int B, int n_classes, cudaStream_t stream);
 
 void count_launch();
 

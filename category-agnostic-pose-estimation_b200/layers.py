@@ -334,8 +334,10 @@ class IncrementalDecoder:
         n, t, c = x.shape
         return x.view(n, t, heads, c // heads).transpose(1, 2)            # (n, H, t, d)
 
-    def _layer_step(self, i, layer, tgt, query_pos, mask):
+    def _layer_step(self, i, layer, tgt, query_pos, mask, reference_points=None):
         shapes, starts, sup, sup_mask = self._ctx
+        if reference_points is None:
+            reference_points = self.reference_points
         prep = self._prep[i]
         n, c = tgt.shape[0], layer.d_model
         heads = layer.self_attn.num_heads
@@ -359,8 +361,7 @@ class IncrementalDecoder:
         ol = F.linear(tgt + query_pos, prep["w_ol"], prep["b_ol"])
         offsets = ol[..., :prep["n_off"]].reshape(n, 1, ca.n_heads, ca.n_levels, ca.n_points, 2)
         logits = ol[..., prep["n_off"]:].reshape(n, 1, ca.n_heads, ca.n_levels * ca.n_points)
-        sampled = torch.ops.cape.ms_deform_attn_decode(self.values[i], shapes, starts, self.reference_points, offsets,
-                                                       logits)
+        sampled = torch.ops.cape.ms_deform_attn_decode(self.values[i], shapes, starts, reference_points, offsets, logits)
         tgt = layer.norm1(tgt + ca.output_proj(sampled))
         return layer.forward_ffn(tgt)
 

@@ -104,3 +104,48 @@ def algorithmic_bytes(n: int, lq: int, s: int, n_heads: int = 8, head_dim: int =
     a_bwd = (e_value * n * lq * c + e_value * n * s * c + e_aux * 3 * n * lq * mlp
              + e_grad * n * s * c + e_aux * 3 * n * lq * mlp)
     return a_fwd, a_bwd
+
+
+# ---- name-keyed deterministic arrays (model-level fixtures) ------------------------------------------------------
+# Model-level fixtures would need megabytes of weights; instead both sides (the reference model inside
+# oracle/make_golden.py, the mirror inside the tests) are filled from the same recipe, keyed by parameter NAME, so the
+# fixture only stores outputs plus a checksum of what the recipe produced.  Integer hashing only — no libm — so the
+# values are identical on every machine.
+def seeded_array(name: str, shape, seed: int = 0, low: float = -1.0, high: float = 1.0):
+    """float32 array U(low, high), a pure function of (name, shape, seed)."""
+    import zlib
+
+    import numpy as np
+    count = 1
+    for s in shape:
+        count *= int(s)
+    key = np.uint64(zlib.crc32(name.encode()) ^ (int(seed) * 0x9E3779B1 & 0xFFFFFFFF))
+    x = np.arange(count, dtype=np.uint64) + (key << np.uint64(32)) + np.uint64(0x9E3779B97F4A7C15)
+    # splitmix64 finaliser
+    x ^= x >> np.uint64(30)
+    x *= np.uint64(0xBF58476D1CE4E5B9)
+    x ^= x >> np.uint64(27)
+    x *= np.uint64(0x94D049BB133111EB)
+    x ^= x >> np.uint64(31)
+    u = (x >> np.uint64(40)).astype(np.float64) / float(1 << 24)            # 24-bit uniform in [0, 1)
+    return (low + (high - low) * u).astype(np.float32).reshape(tuple(int(s) for s in shape))
+
+
+def fill_parameters_(module, seed: int = 0, gain: float = 1.0) -> float:
+    """Overwrite every parameter of ``module`` from :func:`seeded_array`, keyed by its ``named_parameters`` name:
+    matrices U(+-gain*sqrt(3/fan_in)), LayerNorm / GroupNorm weights 1 + U(+-0.1), other vectors U(+-0.1).
+    Returns a checksum (sum of |w|) the fixtures record."""
+    total = 0.0
+    with torch.no_grad():
+        for name, p in module.named_parameters():
+            if p.dim() >= 2:
+                fan_in = p.shape[1] if p.dim() == 2 else p[0].numel()
+                a = gain * math.sqrt(3.0 / max(fan_in, 1))
+                w = seeded_array(name, p.shape, seed, -a, a)
+            elif "norm" in name and name.endswith("weight"):
+                w = seeded_array(name, p.shape, seed, 0.9, 1.1)
+            else:
+                w = seeded_array(name, p.shape, seed, -0.1, 0.1)
+            p.copy_(torch.from_numpy(w).to(p.device, p.dtype))
+            total += float(abs(w.astype("float64")).sum())
+    return total

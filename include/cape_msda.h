@@ -161,6 +161,63 @@ CAPE_API int cape_points_sample_backward(const float* grad_out, const float* x, 
                                          int zero_grad_x, void* stream);
 
 /*
+ * Sequence side of the decoder: the data formats either side of the decode step, kept on the device.
+ *
+ * Bilinear token embedding — TransformerDecoder._seq_embed, models/deformable_transformer_v2.py:984-997:
+ *     out[t, :] = E[seq11[t]]*dx2[t]*dy2[t] + E[seq21[t]]*dx1[t]*dy2[t] + E[seq12[t]]*dx2[t]*dy1[t] + E[seq22[t]]*dx1[t]*dy1[t]
+ *   table (V, C) fp32, C % 4 == 0; seq* (tokens,) int64; d* (tokens,) fp32; out (tokens, C) fp32.
+ *   A token id outside [0, V) yields a NaN row (the reference raises an IndexError; a kernel cannot).
+ *   Backward accumulates into grad_table (V, C) with atomics (zero_grad_table = 1 zero-fills it first) and skips
+ *   padding_idx (pass -1 for none), like nn.Embedding(padding_idx=...).
+ */
+CAPE_API int cape_seq_embed_forward(const float* table, const int64_t* seq11, const int64_t* seq12, const int64_t* seq21,
+                                    const int64_t* seq22, const float* delta_x1, const float* delta_x2,
+                                    const float* delta_y1, const float* delta_y2, float* out, int64_t tokens, int C,
+                                    int V, void* stream);
+CAPE_API int cape_seq_embed_backward(const float* grad_out, const int64_t* seq11, const int64_t* seq12,
+                                     const int64_t* seq21, const int64_t* seq22, const float* delta_x1,
+                                     const float* delta_x2, const float* delta_y1, const float* delta_y2,
+                                     float* grad_table, int64_t tokens, int C, int V, int64_t padding_idx,
+                                     int zero_grad_table, void* stream);
+
+/*
+ * Token bookkeeping of one autoregressive step — the `for j in range(bs)` body of RoomFormerV2.forward_inference,
+ * models/roomformer_v2.py:548-597, for every sample at once and without leaving the device:
+ *   cls_logits (B, n_classes), reg (B, 2): this step's head outputs (fp32);
+ *   step_dev: device-resident step counter i, incremented by the call (so a captured CUDA graph can be replayed);
+ *   state: per-sample buffers the call reads and updates (all device memory, caller-owned):
+ *     unfinished (B) int32 in/out; finish_step (B) int64, written when a sample emits its terminating <eos>;
+ *     seq11..seq22 (B) int64 and delta_x1..delta_y2 (B) fp32: OUTPUT, the next step's _seq_embed inputs;
+ *     pred_logits (B, max_len, n_classes), pred_coords (B, max_len, 2): column i receives cls_logits / reg;
+ *     gen_kind (B, max_len) int32 and gen_xy (B, max_len, 2): the reference's gen_out entry of column i
+ *       (kind 0 = [x, y], 2 = separator, -1 = everything else);
+ *   tokenizer: DiscreteTokenizer constants (datasets/discrete_tokenizer.py:7-28) and TokenType values
+ *     (datasets/token_types.py), min_len = 6 (roomformer_v2.py:456).
+ * A step counter outside [0, max_len) makes the call a no-op (the counter is still advanced).
+ */
+typedef struct cape_tokenizer {
+    int32_t num_bins;
+    int32_t min_len;
+    int64_t bos, eos, sep, pad, cls;
+    int32_t type_coord, type_sep, type_eos, type_cls;
+} cape_tokenizer;
+
+typedef struct cape_token_state {
+    int32_t* unfinished;
+    int64_t* finish_step;
+    int64_t *seq11, *seq12, *seq21, *seq22;
+    float *delta_x1, *delta_x2, *delta_y1, *delta_y2;
+    float* pred_logits;
+    float* pred_coords;
+    int32_t* gen_kind;
+    float* gen_xy;
+    int64_t max_len;
+} cape_token_state;
+
+CAPE_API int cape_token_step(const float* cls_logits, const float* reg, int64_t* step_dev, const cape_token_state* state,
+                             const cape_tokenizer* tokenizer, int B, int n_classes, void* stream);
+
+/*
  * Host-buffer round trip used for end-to-end measurement and for callers without device buffers:
  * copies the inputs from (ideally pinned) HOST memory into the caller-provided device workspace, runs forward and,
  * when grad_out_host != NULL, backward, and copies the results back to HOST memory — all enqueued on `stream`.

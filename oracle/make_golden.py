@@ -232,6 +232,171 @@ def record_variant_cases(syn):
         print(f"deformable_points_{tag}: {os.path.getsize(path) / 1024:.1f} KiB, out {tuple(out.shape)}")
 
 
+def build_reference_model(syn, seq_len, num_bins, feats, masks_full, seed):
+    """The reference's RoomFormerV2 (roomformer_v2.py:149-270) around its v2 DeformableTransformer with CAPE's defaults
+    (poly_refine, sine query positions, aux loss, decoder layer v1; train_cape_episodic.py:182-225), on a stub backbone
+    that hands back pre-made 256-channel feature maps — the backbone and ``input_proj`` are not on the path under test."""
+    import importlib
+    load_reference_v2()
+    rf = importlib.import_module("models.roomformer_v2")
+    v2 = importlib.import_module("models.deformable_transformer_v2")
+    misc = importlib.import_module("util.misc")
+    pe = importlib.import_module("models.position_encoding")
+    tok_mod = importlib.import_module("datasets.discrete_tokenizer")
+    tokenizer = tok_mod.DiscreteTokenizerV2(num_bins=num_bins, seq_len=seq_len, add_cls=False)
+
+    class StubBody(torch.nn.Module):
+        strides = [8, 16, 32, 64]
+        num_channels = [256, 256, 256, 256]
+
+        def forward(self, tensor_list):
+            out = {}
+            for i, f in enumerate(feats):
+                m = torch.nn.functional.interpolate(tensor_list.mask[None].float(), size=f.shape[-2:]).to(torch.bool)[0]
+                out[str(i)] = misc.NestedTensor(f, m)
+            return out
+
+    class StubJoiner(torch.nn.Sequential):
+        def __init__(self):
+            super().__init__(StubBody(), pe.PositionEmbeddingSine(128, normalize=True))
+            self.strides = StubBody.strides
+            self.num_channels = StubBody.num_channels
+
+        def forward(self, tensor_list):
+            xs = self[0](tensor_list)
+            out = [x for _, x in sorted(xs.items())]
+            return out, [self[1](x).to(x.tensors.dtype) for x in out]
+
+    transformer = v2.DeformableTransformer(
+        d_model=256, nhead=8, num_encoder_layers=1, num_decoder_layers=2, dim_feedforward=64, dropout=0.0,
+        activation="relu", poly_refine=True, return_intermediate_dec=True, aux_loss=True, num_feature_levels=4,
+        dec_n_points=4, enc_n_points=4, query_pos_type="sine", vocab_size=len(tokenizer), seq_len=seq_len,
+        pre_decoder_pos_embed=False, learnable_dec_pe=False, dec_attn_concat_src=False, dec_qkv_proj=True,
+        dec_layer_type="v1", pad_idx=tokenizer.pad)
+    model = rf.RoomFormerV2(StubJoiner(), transformer, num_classes=3, num_queries=seq_len, num_polys=1,
+                            num_feature_levels=4, aux_loss=True, with_poly_refine=True, seq_len=seq_len,
+                            tokenizer=tokenizer)
+    model.input_proj = torch.nn.ModuleList([torch.nn.Identity() for _ in range(4)])
+    checksum = syn.fill_parameters_(model.transformer, seed)
+    with torch.no_grad():
+        model.query_embed.weight.copy_(torch.from_numpy(syn.seeded_array("query_embed.weight", (seq_len, 2), seed, -2, 2)))
+        # class logits: make all three token types win somewhere so the generated sequences are ragged
+        for i, head in enumerate(model.class_embed):
+            head.weight.mul_(6.0)
+            head.bias.copy_(torch.tensor([0.8, 0.0, -0.3]))
+    model.eval()
+    return model, tokenizer, checksum
+
+
+def record_model_cases(syn):
+    """DeformableTransformer.forward (deformable_transformer_v2.py:177-254) + TransformerDecoder.forward (:1024-1131)
+    teacher-forced with gradients, and RoomFormerV2.forward_inference's autoregressive loop (roomformer_v2.py:381-676)
+    with the KV cache, both from the reference's own classes.  Weights / feature maps come from synthetic.seeded_array
+    (keyed by name), so the fixture stores only masks, positional encodings, outputs and a weight checksum."""
+    import importlib
+    seed, seq_len, num_bins, n_sup = 31, 20, 6, 5
+    sizes = ((64, 96), (48, 80))                              # second image is padded by the nested-tensor batching
+    level_shapes = ((8, 12), (4, 6), (2, 3), (1, 2))
+    n = len(sizes)
+    feats = [torch.from_numpy(syn.seeded_array(f"feat{i}", (n, 256, h, w), seed)) for i, (h, w) in enumerate(level_shapes)]
+    model, tokenizer, checksum = build_reference_model(syn, seq_len, num_bins, feats, None, seed)
+    misc = importlib.import_module("util.misc")
+    images = [torch.zeros(3, h, w) for h, w in sizes]
+    samples = misc.nested_tensor_from_tensor_list(images)
+    sup = torch.from_numpy(syn.seeded_array("support_features", (n, n_sup, 256), seed))
+    sup_mask = torch.zeros(n, n_sup, dtype=torch.bool)
+    sup_mask[1, -2:] = True
+    dec = model.transformer.decoder
+
+    # capture what the transformer is fed (masks and positional encodings come from the stub backbone)
+    captured = {}
+    orig_forward = model.transformer.forward
+
+    def spy(srcs, masks, pos_embeds, *a, **k):
+        captured.setdefault("masks", [m.clone() for m in masks])
+        captured.setdefault("pos", [p.clone() for p in pos_embeds])
+        return orig_forward(srcs, masks, pos_embeds, *a, **k)
+    model.transformer.forward = spy
+
+    # ---- teacher-forced forward + backward (RoomFormerV2.forward, :283-361)
+    vocab_coords = num_bins * num_bins
+    rng = np.random.default_rng(seed)
+    seqs = rng.integers(0, vocab_coords, size=(4, n, seq_len))
+    seqs[:, :, 0] = tokenizer.bos
+    seqs[:, 0, 7] = tokenizer.sep
+    seqs[:, 0, 15:] = tokenizer.pad
+    seqs[:, 0, 14] = tokenizer.eos
+    seqs[:, 1, -1] = tokenizer.eos
+    dx = rng.random((n, seq_len)).astype(np.float32)
+    dy = rng.random((n, seq_len)).astype(np.float32)
+    seq_kwargs = {"seq11": torch.from_numpy(seqs[0]), "seq12": torch.from_numpy(seqs[1]),
+                  "seq21": torch.from_numpy(seqs[2]), "seq22": torch.from_numpy(seqs[3]),
+                  "delta_x1": torch.from_numpy(dx), "delta_x2": torch.from_numpy(1 - dx),
+                  "delta_y1": torch.from_numpy(dy), "delta_y2": torch.from_numpy(1 - dy)}
+    dec.support_features, dec.support_mask = sup, sup_mask             # what CAPEModel.forward does (cape_model.py:123-126)
+    for f in feats:
+        f.requires_grad_(True)
+    out = model(samples, seq_kwargs=seq_kwargs)
+    logits = torch.stack([a["pred_logits"] for a in out["aux_outputs"]] + [out["pred_logits"]])
+    coords = torch.stack([a["pred_coords"] for a in out["aux_outputs"]] + [out["pred_coords"]])
+    g_logits = torch.from_numpy(syn.seeded_array("grad_logits", logits.shape, seed))
+    g_coords = torch.from_numpy(syn.seeded_array("grad_coords", coords.shape, seed))
+    loss = (logits * g_logits).sum() + (coords * g_coords).sum()
+    grad_names = ["decoder.token_embed.weight", "level_embed", "decoder.pos_trans.weight",
+                  "encoder.layers.0.self_attn.value_proj.weight", "encoder.layers.0.self_attn.sampling_offsets.bias",
+                  "decoder.layers.0.cross_attn.sampling_offsets.weight", "decoder.layers.1.cross_attn.attention_weights.bias",
+                  "decoder.layers.0.attn_k.weight", "decoder.layers.1.support_attn.in_proj_weight",
+                  "decoder.coords_embed.0.layers.2.weight", "decoder.class_embed.1.weight", "decoder.layers.1.linear2.weight"]
+    params = dict(model.transformer.named_parameters())
+    grads = torch.autograd.grad(loss, [params[k] for k in grad_names] + [model.query_embed.weight] + feats)
+    rec = {"seed": seed, "seq_len": seq_len, "num_bins": num_bins, "n_sup": n_sup, "weight_checksum": checksum,
+           "level_shapes": np.array(level_shapes, dtype=np.int64), "support_mask": sup_mask.numpy(),
+           "pred_logits": logits.detach().numpy(), "pred_coords": coords.detach().numpy(),
+           "grad_query_embed": grads[len(grad_names)].numpy()}
+    for k in ("seq11", "seq12", "seq21", "seq22", "delta_x1", "delta_x2", "delta_y1", "delta_y2"):
+        rec[k] = seq_kwargs[k].numpy()
+    for i in range(4):
+        rec[f"mask{i}"] = captured["masks"][i].numpy()
+        rec[f"pos{i}"] = captured["pos"][i].numpy()
+        rec[f"grad_feat{i}"] = grads[len(grad_names) + 1 + i].numpy()
+    for k, g_ in zip(grad_names, grads):
+        rec["grad_param." + k] = g_.numpy()[:8]               # first 8 rows: enough to pin the gradient, keeps the file small
+    rec["state_dict_keys"] = np.array(sorted(model.transformer.state_dict().keys()))
+    for f in feats:
+        f.requires_grad_(False)
+
+    # ---- autoregressive generation with the KV cache (RoomFormerV2.forward_inference, :381-676)
+    with torch.no_grad():
+        gen = model.forward_inference(samples, use_cache=True)
+    dec.support_features = dec.support_mask = None
+    steps = gen["pred_logits"].shape[1]
+    kind = np.full((n, steps), -1, dtype=np.int64)             # gen_out: [x, y] -> 0, sep -> 2, everything else -1
+    xy = np.zeros((n, steps, 2), dtype=np.float32)
+    for j, row in enumerate(gen["gen_out"]):
+        assert len(row) == steps
+        for t, item in enumerate(row):
+            if isinstance(item, list):
+                kind[j, t] = 0
+                xy[j, t] = item
+            else:
+                kind[j, t] = int(item)
+    rec.update(gen_logits=gen["pred_logits"].numpy(), gen_coords=gen["pred_coords"].numpy(), gen_kind=kind, gen_xy=xy)
+    # second run with the class bias tilted towards <eos>: every sequence finishes early, so the loop stops before max_len
+    with torch.no_grad():
+        for head in model.class_embed:
+            head.bias.copy_(torch.tensor([0.0, 0.0, 7.0]))
+        dec.support_features, dec.support_mask = sup, sup_mask
+        gen2 = model.forward_inference(samples, use_cache=True)
+        dec.support_features = dec.support_mask = None
+    rec.update(gen2_logits=gen2["pred_logits"].numpy(), gen2_coords=gen2["pred_coords"].numpy(),
+               gen2_bias=np.array([0.0, 0.0, 7.0], dtype=np.float32))
+    print("second run:", gen2["pred_logits"].shape[1], "steps", gen2["pred_logits"].argmax(-1).tolist())
+    path = os.path.join(OUT_DIR, "transformer_model.npz")
+    np.savez_compressed(path, **rec)
+    print(f"transformer_model: {os.path.getsize(path) / 1024:.1f} KiB; generated {steps} steps; token types per sample:",
+          gen["pred_logits"].argmax(-1).tolist())
+
+
 def run_reference(ref, value, shapes, loc, attn, gout, dtype):
     v = value.to(dtype).clone().requires_grad_(True)
     l = loc.to(dtype).clone().requires_grad_(True)
@@ -346,6 +511,13 @@ def main():
     ref = load_reference()
     syn = load_synthetic()
     torch.set_num_threads(1)      # fixed summation order inside ATen
+    only = set(sys.argv[1:])      # e.g. `python -m oracle.make_golden model` regenerates one group
+    if only:
+        groups = {"module": lambda: record_module_case(ref, syn), "layers": lambda: record_layer_cases(syn),
+                  "variants": lambda: record_variant_cases(syn), "model": lambda: record_model_cases(syn)}
+        for name in sorted(only):
+            groups[name]()
+        return
     record_core_case(ref, "core_uniform", syn.make_inputs(
         2, 37, ((8, 8), (4, 4), (2, 2), (1, 1)), dist="uniform", seed=1))
     enc_shapes = ((6, 8), (3, 4), (2, 2), (1, 2))
@@ -361,6 +533,7 @@ def main():
     record_module_case(ref, syn)
     record_layer_cases(syn)
     record_variant_cases(syn)
+    record_model_cases(syn)
 
 
 if __name__ == "__main__":

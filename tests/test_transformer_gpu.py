@@ -1,0 +1,193 @@
+"""Model-level parity on the GPU (§8c iv): the DeformableTransformer / TransformerDecoder
+mirrors teacher-forced (outputs of every decoder layer + gradients) and the device-resident autoregressive generation,
+against outputs of the reference's own RoomFormerV2 + DeformableTransformer classes (tests/golden/transformer_model.npz,
+made by oracle/make_golden.py).  Weights and feature maps are regenerated from synthetic.seeded_array; the fixture's
+checksum guards that both sides saw the same numbers."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cape_b200
+from cape_b200 import synthetic
+from tests.conftest import GOLDEN, rel_err
+
+pytestmark = pytest.mark.gpu
+
+FWD_TOL_F32 = 1e-5
+GRAD_TOL_F32 = 1e-4
+SEQ_KEYS = ("seq11", "seq12", "seq21", "seq22", "delta_x1", "delta_x2", "delta_y1", "delta_y2")
+
+
+@pytest.fixture(scope="module")
+def fx():
+    g = np.load(os.path.join(GOLDEN, "transformer_model.npz"))
+    seed = int(g["seed"])
+    spec = cape_b200.TokenizerSpec(int(g["num_bins"]), int(g["seq_len"]))
+    tr = cape_b200.DeformableTransformer(
+        d_model=256, nhead=8, num_encoder_layers=1, num_decoder_layers=2, dim_feedforward=64, dropout=0.0,
+        poly_refine=True, return_intermediate_dec=True, aux_loss=True, num_feature_levels=4, dec_n_points=4,
+        enc_n_points=4, query_pos_type="sine", vocab_size=spec.vocab_size, seq_len=spec.seq_len, pad_idx=spec.pad)
+    tr.attach_heads(*cape_b200.build_prediction_heads(256, 3, 2, with_poly_refine=True))
+    assert sorted(tr.state_dict().keys()) == list(g["state_dict_keys"])           # checkpoint layout of the reference
+    assert synthetic.fill_parameters_(tr, seed) == pytest.approx(float(g["weight_checksum"]), rel=1e-12)
+    with torch.no_grad():                                                          # the generator script's head recipe
+        for head in tr.decoder.class_embed:
+            head.weight.mul_(6.0)
+            head.bias.copy_(torch.tensor([0.8, 0.0, -0.3]))
+    tr = tr.cuda().eval()
+    shapes = [tuple(int(v) for v in hw) for hw in g["level_shapes"]]
+    n = g["mask0"].shape[0]
+    feats = [torch.from_numpy(synthetic.seeded_array(f"feat{i}", (n, 256, h, w), seed)).cuda()
+             for i, (h, w) in enumerate(shapes)]
+    masks = [torch.from_numpy(g[f"mask{i}"]).cuda() for i in range(4)]
+    pos = [torch.from_numpy(g[f"pos{i}"]).cuda() for i in range(4)]
+    query_embed = torch.from_numpy(synthetic.seeded_array("query_embed.weight", (spec.seq_len, 2), seed, -2, 2)).cuda()
+    sup = torch.from_numpy(synthetic.seeded_array("support_features", (n, int(g["n_sup"]), 256), seed)).cuda()
+    sup_mask = torch.from_numpy(g["support_mask"]).cuda()
+    return dict(g=g, seed=seed, spec=spec, tr=tr, feats=feats, masks=masks, pos=pos, query_embed=query_embed, sup=sup,
+                sup_mask=sup_mask)
+
+
+def test_teacher_forced_forward_and_gradients_match_reference_model(fx):
+    g, tr = fx["g"], fx["tr"]
+    seq_kwargs = {k: torch.from_numpy(g[k]).cuda() for k in SEQ_KEYS}
+    feats = [f.clone().requires_grad_(True) for f in fx["feats"]]
+    qe = fx["query_embed"].clone().requires_grad_(True)
+    causal = tr._create_causal_attention_mask(fx["spec"].seq_len).cuda()             # RoomFormerV2.attention_mask (:266)
+    hs, init_ref, refs, classes = tr(feats, fx["masks"], fx["pos"], qe, None, causal, seq_kwargs,
+                                     support_features=fx["sup"], support_mask=fx["sup_mask"])
+    assert hs.shape == (2, 2, fx["spec"].seq_len, 256)
+    assert rel_err(init_ref.detach().cpu().numpy()[0], torch.from_numpy(
+        synthetic.seeded_array("query_embed.weight", (fx["spec"].seq_len, 2), fx["seed"], -2, 2)).sigmoid().numpy()) < 1e-6
+    assert rel_err(classes.detach().cpu().numpy(), g["pred_logits"]) < FWD_TOL_F32
+    assert rel_err(refs.detach().cpu().numpy(), g["pred_coords"]) < FWD_TOL_F32
+    seed = fx["seed"]
+    loss = (classes * torch.from_numpy(synthetic.seeded_array("grad_logits", classes.shape, seed)).cuda()).sum() \
+        + (refs * torch.from_numpy(synthetic.seeded_array("grad_coords", refs.shape, seed)).cuda()).sum()
+    names = [k[len("grad_param."):] for k in g.files if k.startswith("grad_param.")]
+    params = dict(tr.named_parameters())
+    grads = torch.autograd.grad(loss, [params[k] for k in names] + [qe] + feats)
+    errs = {k: rel_err(gr.cpu().numpy()[:8], g["grad_param." + k]) for k, gr in zip(names, grads)}
+    errs["query_embed"] = rel_err(grads[len(names)].cpu().numpy(), g["grad_query_embed"])
+    for i in range(4):
+        errs[f"feat{i}"] = rel_err(grads[len(names) + 1 + i].cpu().numpy(), g[f"grad_feat{i}"])
+    assert max(errs.values()) < GRAD_TOL_F32, errs
+
+
+def _check_generation(out, g, prefix):
+    want_logits, want_coords = g[prefix + "_logits"], g[prefix + "_coords"]
+    assert out["pred_logits"].shape == want_logits.shape, (out["pred_logits"].shape, want_logits.shape)
+    assert np.array_equal(out["sequences"].cpu().numpy(), want_logits.argmax(-1))    # same generated token types
+    assert rel_err(out["pred_logits"].cpu().numpy(), want_logits) < 1e-4             # 20 chained steps of fp32 GEMMs
+    assert rel_err(out["pred_coords"].cpu().numpy(), want_coords) < 1e-4
+
+
+def test_device_resident_generation_matches_reference_forward_inference(fx):
+    g, tr, spec = fx["g"], fx["tr"], fx["spec"]
+    gen = cape_b200.AutoregressiveGenerator(tr, spec, max_batch_size=2, device="cuda")
+    before = cape_b200.launch_count()
+    out = gen.generate(fx["feats"], fx["masks"], fx["pos"], fx["query_embed"], fx["sup"], fx["sup_mask"], poll_every=4)
+    assert cape_b200.launch_count() > before
+    _check_generation(out, g, "gen")
+    kind = np.array([[0 if isinstance(e, list) else e for e in row] for row in out["gen_out"]])
+    assert np.array_equal(kind, g["gen_kind"])
+    xy = np.array([[e if isinstance(e, list) else [0.0, 0.0] for e in row] for row in out["gen_out"]], dtype=np.float32)
+    assert rel_err(xy, g["gen_xy"]) < 1e-4
+    # same object, next batch (graph reused), eager stepping: identical tokens
+    out2 = gen.generate(fx["feats"], fx["masks"], fx["pos"], fx["query_embed"], fx["sup"], fx["sup_mask"], use_graph=False)
+    assert torch.equal(out2["sequences"], out["sequences"])
+    assert rel_err(out2["pred_coords"].cpu().numpy(), out["pred_coords"].cpu().numpy()) < 1e-5
+
+
+def test_generation_stops_when_every_sequence_emitted_eos(fx):
+    g, tr, spec = fx["g"], fx["tr"], fx["spec"]
+    saved = [h.bias.detach().clone() for h in tr.decoder.class_embed]
+    try:
+        with torch.no_grad():
+            for h in tr.decoder.class_embed:
+                h.bias.copy_(torch.from_numpy(g["gen2_bias"]).cuda())
+        gen = cape_b200.AutoregressiveGenerator(tr, spec, max_batch_size=2, device="cuda")
+        for poll in (1, 3, 16):                      # polling granularity must not change the result
+            out = gen.generate(fx["feats"], fx["masks"], fx["pos"], fx["query_embed"], fx["sup"], fx["sup_mask"],
+                               poll_every=poll)
+            assert out["steps"] == g["gen2_logits"].shape[1] < spec.seq_len
+            _check_generation(out, g, "gen2")
+        eager = cape_b200.generate_eager(tr, spec, fx["feats"], fx["masks"], fx["pos"], fx["query_embed"], fx["sup"],
+                                         fx["sup_mask"])
+        _check_generation(eager, g, "gen2")
+    finally:
+        with torch.no_grad():
+            for h, b in zip(tr.decoder.class_embed, saved):
+                h.bias.copy_(b)
+
+
+def test_seq_embed_op_matches_the_eager_expression_bitwise_and_in_gradient():
+    gen = torch.Generator().manual_seed(2)
+    v, c, b, t, pad = 40, 256, 3, 17, 39
+    table = torch.randn(v, c, generator=gen)
+    seqs = [torch.randint(0, v, (b, t), generator=gen) for _ in range(4)]
+    seqs[0][0, 3] = pad
+    dx, dy = torch.rand(b, t, generator=gen), torch.rand(b, t, generator=gen)
+    deltas = [dx, 1 - dx, dy, 1 - dy]                                    # x1, x2, y1, y2
+    emb = torch.nn.Embedding(v, c, padding_idx=pad)
+    with torch.no_grad():
+        emb.weight.copy_(table)
+    e11, e12, e21, e22 = (emb(s) for s in seqs)
+    x1, x2, y1, y2 = (d[..., None] for d in deltas)
+    want = e11 * x2 * y2 + e21 * x1 * y2 + e12 * x2 * y1 + e22 * x1 * y1   # deformable_transformer_v2.py:991-995
+    gout = torch.randn(b, t, c, generator=gen)
+    (want_grad,) = torch.autograd.grad(want, emb.weight, gout)
+    tab = table.cuda().requires_grad_(True)
+    got = cape_b200.seq_embed(tab, *[s.cuda() for s in seqs], *[d.cuda() for d in deltas], pad)
+    assert torch.equal(got.detach().cpu(), want.detach())
+    (grad,) = torch.autograd.grad(got, tab, gout.cuda())
+    assert rel_err(grad.cpu().numpy(), want_grad.numpy()) < 1e-6
+    assert float(grad[pad].abs().max()) == 0.0
+    torch.library.opcheck(torch.ops.cape.seq_embed.default,
+                          (tab, *[s.cuda() for s in seqs], *[d.cuda() for d in deltas], pad),
+                          test_utils=("test_schema", "test_faketensor", "test_autograd_registration"))
+
+
+def test_token_step_follows_the_reference_bookkeeping_rules():
+    """Scripted head outputs through cape_token_step vs a literal Python transcription of roomformer_v2.py:548-597."""
+    import math
+    spec = cape_b200.TokenizerSpec(num_bins=44, seq_len=12)
+    b = 5
+    state = cape_b200.TokenState(b, spec, 3, "cuda")
+    rng = np.random.default_rng(0)
+    unfinished = np.ones(b)
+    for i in range(spec.seq_len):
+        logits = rng.standard_normal((b, 1, 3)).astype(np.float32)
+        reg = rng.random((b, 1, 2)).astype(np.float32)
+        reg[0, 0] = (1.0, 0.0)
+        state.advance(torch.from_numpy(logits).cuda(), torch.from_numpy(reg).cuda())
+        torch.cuda.synchronize()
+        seq = [s.cpu().numpy()[:, 0] for s in state.seq]
+        delta = [d.cpu().numpy()[:, 0] for d in state.delta]
+        for j in range(b):
+            cls = int(np.argmax(logits[j, 0]))
+            dx = dy = 0
+            if unfinished[j] == 1:
+                if cls == 0 or (cls == 2 and i < 6):
+                    x, y = reg[j, 0]
+                    x, y = min(x, 1) * (spec.num_bins - 1), min(y, 1) * (spec.num_bins - 1)
+                    want = [math.floor(x) * 44 + math.floor(y), math.floor(x) * 44 + math.ceil(y),
+                            math.ceil(x) * 44 + math.floor(y), math.ceil(x) * 44 + math.ceil(y)]
+                    dx, dy = x - math.floor(x), y - math.floor(y)
+                elif cls == 1:
+                    want = [spec.sep] * 4
+                else:
+                    unfinished[j] = 0
+                    want = [spec.eos] * 4
+            else:
+                want = [spec.pad] * 4
+            assert [int(s[j]) for s in seq] == want, (i, j)
+            assert [float(d[j]) for d in delta] == [np.float32(dx), np.float32(1 - np.float32(dx)), np.float32(dy),
+                                                    np.float32(1 - np.float32(dy))], (i, j)
+        assert np.array_equal(state.unfinished.cpu().numpy(), unfinished.astype(np.int32))
+    assert int(state.step.item()) == spec.seq_len
+    state.advance(torch.zeros(b, 1, 3).cuda(), torch.zeros(b, 1, 2).cuda())        # past max_len: a no-op
+    torch.cuda.synchronize()
+    assert int(state.step.item()) == spec.seq_len + 1
