@@ -462,6 +462,65 @@ def decode_loop(dev, episodes=64, tokens=100):
                      "graph capture and per-batch value projection included; no backbone / encoder / tokenizer"}
 
 
+def generation(dev, episodes=64, keypoints=100):
+    """BASELINE.json configs[3] end to end on the transformer: encoder (6 layers, once) + autoregressive decoding of
+    `keypoints` coordinate tokens + <eos> for 64 episodes x 2 queries, from projected feature maps to the result dict of
+    RoomFormerV2.forward_inference.  Device-resident generator (one CUDA graph per token, token bookkeeping kernel,
+    cached projected value) vs the reference's loop shape (one transformer.forward per token, a host read of the
+    unfinished flags per step), same mirror weights.  The class head is biased so every step emits a coordinate
+    (random weights would stop at arbitrary points); the backbone / input_proj / support encoder are not on the path."""
+    import torch
+    import cape_b200
+    n, n_sup = episodes * 2, 17
+    spec = cape_b200.TokenizerSpec(num_bins=44, seq_len=keypoints + 1)
+    torch.manual_seed(0)
+    tr = cape_b200.DeformableTransformer(
+        d_model=256, nhead=8, num_encoder_layers=6, num_decoder_layers=6, dim_feedforward=1024, dropout=0.1,
+        poly_refine=True, return_intermediate_dec=True, aux_loss=True, num_feature_levels=4, query_pos_type="sine",
+        vocab_size=spec.vocab_size, seq_len=spec.seq_len, pad_idx=spec.pad)
+    tr.attach_heads(*cape_b200.build_prediction_heads(256, 3, 6, True))
+    with torch.no_grad():
+        for head in tr.decoder.class_embed:
+            head.bias.copy_(torch.tensor([50.0, 0.0, 0.0]))
+    tr = tr.to(dev).eval()
+    feats = [torch.randn(n, 256, h, w, device=dev) for h, w in cape_b200.synthetic.CAPE_PYRAMID]
+    masks = [torch.zeros(n, h, w, dtype=torch.bool, device=dev) for h, w in cape_b200.synthetic.CAPE_PYRAMID]
+    pos = [torch.randn(n, 256, h, w, device=dev) for h, w in cape_b200.synthetic.CAPE_PYRAMID]
+    query_embed = torch.randn(spec.seq_len, 2, device=dev)
+    sup = torch.randn(n, n_sup, 256, device=dev)
+    sup_mask = torch.zeros(n, n_sup, dtype=torch.bool, device=dev)
+
+    def timed(fn):
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        out = fn()
+        torch.cuda.synchronize(dev)
+        return time.perf_counter() - t0, out
+
+    with torch.no_grad():
+        t_enc, enc_cache = timed(lambda: tr.encode(feats, masks, pos))
+        t_enc, enc_cache = timed(lambda: tr.encode(feats, masks, pos))
+    gen = cape_b200.AutoregressiveGenerator(tr, spec, n, dev)
+    run = lambda: gen.generate(feats, masks, pos, query_embed, sup, sup_mask, enc_cache=enc_cache)
+    run()                                                    # captures the graph
+    t_dec, out = timed(run)
+    steps = out["steps"]
+    few = 6
+    short = cape_b200.TokenizerSpec(num_bins=44, seq_len=few)
+    cape_b200.generate_eager(tr, short, feats, masks, pos, query_embed[:few], sup, sup_mask)
+    t_eager, _ = timed(lambda: cape_b200.generate_eager(tr, short, feats, masks, pos, query_embed[:few], sup, sup_mask))
+    t_eager_tok = (t_eager - t_enc) / few
+    total = t_enc + t_dec
+    return {"episodes": episodes, "queries_per_episode": 2, "tokens": steps, "encoder_layers": 6, "decoder_layers": 6,
+            "encoder_s": round(t_enc, 4), "decode_s": round(t_dec, 4), "us_per_token_step": round(t_dec / steps * 1e6, 1),
+            "episodes_per_s": round(episodes / total, 2), "tokens_per_s": round(n * steps / t_dec, 1),
+            "eager_loop": {"us_per_token_step": round(t_eager_tok * 1e6, 1),
+                           "episodes_per_s": round(episodes / (t_enc + t_eager_tok * steps), 2),
+                           "note": f"mirror transformer.forward per token with KV + value caches, extrapolated from {few} tokens"},
+            "scope": "DeformableTransformer.encode + AutoregressiveGenerator.generate (seq_embed, 6 decoder layers, "
+                     "refinement, heads, token bookkeeping); no backbone / input_proj / support encoder"}
+
+
 def gpu_eager_baseline(dev, alg_bytes):
     """The reference's formulation (oracle/msda_torch.py: per-level grid_sample, stack, multiply, sum) run eagerly on this
     GPU through ATen's CUDA kernels — what a user of the reference sees on the same box.  Baseline only."""
@@ -629,6 +688,7 @@ def run_b200(args, rank, world, local_rank):
         line["module"] = guarded(module_step, dev)
         line["decode"] = guarded(decode_step, dev)
         line["decode_loop"] = guarded(decode_loop, dev)
+        line["generation"] = guarded(generation, dev)
         line["gpu_eager_baseline"] = guarded(gpu_eager_baseline, dev, a_fwd + a_bwd)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = guarded(cpu_baseline)

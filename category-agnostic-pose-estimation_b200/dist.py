@@ -145,3 +145,72 @@ def bind_to_gpu_numa_node(device_index: int) -> int | None:
         return node
     except Exception:
         return None
+
+
+# ---- checkpoints in the reference's layout ----------------------------------------------------
+CHECKPOINT_KEYS = ("model", "optimizer", "lr_scheduler", "scaler", "epoch", "args", "train_stats", "val_stats", "best_pck",
+                   "epochs_without_improvement", "rng_state", "np_rng_state", "py_rng_state")
+
+
+def checkpoint_name(epoch: int, lr: float, batch_size: int, accumulation_steps: int, queries_per_episode: int) -> str:
+    """File name of ``/root/reference/models/train_cape_episodic.py:853-859``."""
+    return f"checkpoint_e{epoch:03d}_lr{lr:.0e}_bs{batch_size}_acc{accumulation_steps}_qpe{queries_per_episode}.pth"
+
+
+def save_checkpoint(path, model, optimizer, lr_scheduler, epoch: int, args=None, scaler=None, train_stats=None,
+                    val_stats=None, best_pck: float = 0.0, epochs_without_improvement: int = 0) -> bool:
+    """Write the dict of ``train_cape_episodic.py:863-888`` (same keys, same meaning) so either code base resumes from the
+    other's file.  Data-parallel runs hold identical replicas: rank 0 alone writes (atomically: temp file + rename), then
+    every rank meets at a barrier.  Returns True on the rank that wrote."""
+    import random
+
+    import numpy as np
+    wrote = False
+    rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+    if rank == 0:
+        state = {
+            "model": model.state_dict(), "optimizer": optimizer.state_dict(), "lr_scheduler": lr_scheduler.state_dict(),
+            "scaler": scaler.state_dict() if scaler is not None else None, "epoch": epoch, "args": args,
+            "train_stats": train_stats, "val_stats": val_stats, "best_pck": best_pck,
+            "epochs_without_improvement": epochs_without_improvement, "rng_state": torch.get_rng_state(),
+            "np_rng_state": np.random.get_state(), "py_rng_state": random.getstate(),
+        }
+        if torch.cuda.is_available():
+            state["cuda_rng_state"] = torch.cuda.get_rng_state_all()
+        tmp = f"{path}.tmp.{os.getpid()}"
+        torch.save(state, tmp)
+        os.replace(tmp, path)
+        wrote = True
+    barrier()
+    return wrote
+
+
+def load_checkpoint(path, model, optimizer=None, lr_scheduler=None, scaler=None, restore_rng: bool = True) -> dict:
+    """Resume as ``train_cape_episodic.py:633-696`` does: non-strict model load (old checkpoints carry the KV-cache buffers
+    and duplicated support-layer keys the reference leaks into ``state_dict()``), optimizer /
+    scheduler / scaler state, best-model tracking and the four RNG streams.  Every rank reads the same file.  Returns
+    ``{"start_epoch", "best_pck", "epochs_without_improvement", "missing_keys", "unexpected_keys"}``."""
+    import random
+
+    import numpy as np
+    ckpt = torch.load(path, map_location="cpu", weights_only=False)
+    missing, unexpected = model.load_state_dict(ckpt["model"], strict=False)
+    if optimizer is not None and ckpt.get("optimizer") is not None:
+        optimizer.load_state_dict(ckpt["optimizer"])
+    if lr_scheduler is not None and ckpt.get("lr_scheduler") is not None:
+        lr_scheduler.load_state_dict(ckpt["lr_scheduler"])
+    if scaler is not None and ckpt.get("scaler") is not None:
+        scaler.load_state_dict(ckpt["scaler"])
+    if restore_rng:
+        if "rng_state" in ckpt:
+            torch.set_rng_state(ckpt["rng_state"].cpu())
+        if "cuda_rng_state" in ckpt and torch.cuda.is_available() \
+                and len(ckpt["cuda_rng_state"]) == torch.cuda.device_count():
+            torch.cuda.set_rng_state_all(ckpt["cuda_rng_state"])
+        if "np_rng_state" in ckpt:
+            np.random.set_state(ckpt["np_rng_state"])
+        if "py_rng_state" in ckpt:
+            random.setstate(ckpt["py_rng_state"])
+    return {"start_epoch": int(ckpt["epoch"]) + 1, "best_pck": ckpt.get("best_pck", 0.0),
+            "epochs_without_improvement": ckpt.get("epochs_without_improvement", 0),
+            "missing_keys": list(missing), "unexpected_keys": list(unexpected)}

@@ -70,3 +70,82 @@ def test_single_process_helpers():
     assert cdist.max_over_ranks(3.5) == 3.5
     with pytest.raises(ValueError):
         cdist.shard_episodes(5, 2, 2)
+
+
+def _ckpt_worker(rank, world, port, path, out):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from cape_b200 import dist as cdist
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    cdist.init_from_env("gloo")
+    torch.manual_seed(3)                                     # replicas start identical
+    model = torch.nn.Linear(4, 2)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3)
+    sched = torch.optim.lr_scheduler.StepLR(opt, 2)
+    model(torch.ones(1, 4) * (rank + 1)).sum().backward()
+    cdist.FlatGradAllreduce(model.parameters())()
+    opt.step()
+    sched.step()
+    wrote = cdist.save_checkpoint(path, model, opt, sched, epoch=4, best_pck=0.25, epochs_without_improvement=1)
+    exists_after_barrier = os.path.exists(path)             # the barrier inside save_checkpoint orders this read
+    fresh = torch.nn.Linear(4, 2)
+    info = cdist.load_checkpoint(path, fresh, restore_rng=False)
+    same = all(torch.equal(a, b) for a, b in zip(model.state_dict().values(), fresh.state_dict().values()))
+    out.put((rank, wrote, exists_after_barrier, same, info["start_epoch"]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_checkpoint_is_written_by_rank_zero_only_and_loads_on_every_rank(tmp_path):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    path = str(tmp_path / "ckpt.pth")
+    procs = [ctx.Process(target=_ckpt_worker, args=(r, 2, port, path, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = sorted(q.get(timeout=150) for _ in procs)
+    for p in procs:
+        p.join(30)
+        assert p.exitcode == 0
+    assert results == [(0, True, True, True, 5), (1, False, True, True, 5)]
+    assert [f for f in os.listdir(tmp_path) if ".tmp." in f] == []
+
+
+def test_checkpoint_layout_is_the_reference_dict_and_resume_restores_everything(tmp_path):
+    """Keys of train_cape_episodic.py:863-888; resume semantics of :633-696 (non-strict model load, RNG streams)."""
+    import random
+
+    import numpy as np
+    from cape_b200 import dist as cdist
+    assert cdist.checkpoint_name(10, 1e-4, 2, 4, 2) == "checkpoint_e010_lr1e-04_bs2_acc4_qpe2.pth"
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(3, 3), torch.nn.Linear(3, 1))
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-4)
+    sched = torch.optim.lr_scheduler.StepLR(opt, 3)
+    for _ in range(2):
+        opt.zero_grad()
+        model(torch.randn(5, 3)).sum().backward()
+        opt.step()
+        sched.step()
+    path = str(tmp_path / cdist.checkpoint_name(1, 1e-4, 2, 4, 2))
+    assert cdist.save_checkpoint(path, model, opt, sched, epoch=1, args={"lr": 1e-4}, train_stats={"loss": 1.0},
+                                 val_stats={"pck": 0.5}, best_pck=0.5, epochs_without_improvement=2)
+    expect = (torch.rand(3), np.random.rand(3), random.random())            # what the RNG streams produce next
+    raw = torch.load(path, weights_only=False)
+    assert set(cdist.CHECKPOINT_KEYS) <= set(raw) and raw["scaler"] is None and raw["epoch"] == 1
+    # a reference-made checkpoint carries leaked cache buffers (Appendix A.2): they must not break the load
+    raw["model"]["0.kv_cache.k_cache"] = torch.zeros(1)
+    torch.save(raw, path)
+    model2 = torch.nn.Sequential(torch.nn.Linear(3, 3), torch.nn.Linear(3, 1))
+    opt2 = torch.optim.AdamW(model2.parameters(), lr=1.0)
+    sched2 = torch.optim.lr_scheduler.StepLR(opt2, 3)
+    torch.rand(10), np.random.rand(10), random.random()                      # disturb the streams
+    info = cdist.load_checkpoint(path, model2, opt2, sched2)
+    assert info["start_epoch"] == 2 and info["best_pck"] == 0.5 and info["epochs_without_improvement"] == 2
+    assert info["unexpected_keys"] == ["0.kv_cache.k_cache"] and info["missing_keys"] == []
+    assert all(torch.equal(a, b) for a, b in zip(model.state_dict().values(), model2.state_dict().values()))
+    assert opt2.param_groups[0]["lr"] == opt.param_groups[0]["lr"] and sched2.last_epoch == sched.last_epoch
+    got = (torch.rand(3), np.random.rand(3), random.random())
+    assert torch.equal(got[0], expect[0]) and np.array_equal(got[1], expect[1]) and got[2] == expect[2]

@@ -187,3 +187,74 @@ def test_patch_reference_routes_the_real_reference_module_to_the_op():
     finally:
         cape_b200.unpatch_reference(ref)
     assert torch.equal(mod(q, refp, src, shapes, starts), eager)
+
+
+# ---- transformer-level mirrors and the generation state --------------------------
+def _small_transformer(spec, **kw):
+    args = dict(d_model=256, nhead=8, num_encoder_layers=1, num_decoder_layers=2, dim_feedforward=64, dropout=0.0,
+                poly_refine=True, return_intermediate_dec=True, aux_loss=True, num_feature_levels=4,
+                query_pos_type="sine", vocab_size=spec.vocab_size, seq_len=spec.seq_len, pad_idx=spec.pad)
+    args.update(kw)
+    return cape_b200.DeformableTransformer(**args)
+
+
+def test_transformer_mirror_has_the_reference_state_dict_layout_and_seeded_weights():
+    g = np.load(os.path.join(GOLDEN, "transformer_model.npz"))
+    spec = cape_b200.TokenizerSpec(int(g["num_bins"]), int(g["seq_len"]))
+    tr = _small_transformer(spec).attach_heads(*cape_b200.build_prediction_heads(256, 3, 2, True))
+    assert sorted(tr.state_dict().keys()) == list(g["state_dict_keys"])
+    assert synthetic.fill_parameters_(tr, int(g["seed"])) == pytest.approx(float(g["weight_checksum"]), rel=1e-12)
+    # pos_embed is a frozen parameter unless learnable_dec_pe (deformable_transformer_v2.py:132)
+    assert not tr.pos_embed.requires_grad and _small_transformer(spec, learnable_dec_pe=True).pos_embed.requires_grad
+
+
+def test_transformer_mirror_rejects_configurations_the_reference_cannot_run_in_cape():
+    spec = cape_b200.TokenizerSpec(6, 20)
+    with pytest.raises(ValueError, match="v1"):
+        _small_transformer(spec, dec_layer_type="v4")
+    with pytest.raises(NotImplementedError):
+        _small_transformer(spec, inject_cls_embed=True)
+    tr = _small_transformer(spec, poly_refine=False, query_pos_type="none")
+    assert tr.decoder.pos_trans is None
+    with pytest.raises(NotImplementedError):                   # the one-graph generator covers the CAPE configuration only
+        cape_b200.AutoregressiveGenerator(tr, spec, 1, "cpu")
+
+
+def test_prediction_heads_follow_roomformer_initialisation():
+    cls, coords = cape_b200.build_prediction_heads(256, 3, 6, with_poly_refine=True)
+    assert len(cls) == len(coords) == 6 and cls[0] is not cls[1]                     # clones (roomformer_v2.py:231-233)
+    assert torch.allclose(cls[0].bias, torch.full((3,), -math.log(99.0)))            # prior 0.01 (:219-221)
+    assert float(coords[0].layers[-1].weight.abs().max()) == 0.0 and float(coords[0].layers[-1].bias.abs().max()) == 0.0
+    cls, coords = cape_b200.build_prediction_heads(256, 3, 6, with_poly_refine=False)
+    assert cls[0] is cls[5] and coords[0] is coords[5]                               # shared (:236-237)
+
+
+def test_tokenizer_spec_matches_the_reference_vocabulary():
+    spec = cape_b200.TokenizerSpec(num_bins=44, seq_len=200)                         # train_cape_episodic defaults
+    assert (spec.bos, spec.eos, spec.sep, spec.pad, spec.vocab_size) == (1936, 1937, 1938, 1939, 1940)
+    assert spec.min_len == 6 and spec.cls == -1
+    with_cls = cape_b200.TokenizerSpec(num_bins=44, seq_len=200, add_cls=True)
+    assert with_cls.cls == 1940 and with_cls.vocab_size == 1941
+    ref_like = types.SimpleNamespace(num_bins=6, seq_len=20, add_cls=False)
+    assert cape_b200.TokenizerSpec.from_tokenizer(ref_like).pad == 39
+
+
+def test_sincos_table_and_query_pos_embedding_shapes():
+    from cape_b200.transformer import sincos_position_table, inverse_sigmoid
+    tab = sincos_position_table(256, 200)
+    assert tab.shape == (200, 256) and np.allclose(tab[0, :128], 0.0) and np.allclose(tab[0, 128:], 1.0)
+    pos = cape_b200.TransformerDecoder.get_query_pos_embed(torch.rand(2, 5, 2))
+    assert pos.shape == (2, 5, 256)
+    x = torch.tensor([0.0, 0.25, 1.0])
+    assert torch.allclose(inverse_sigmoid(x), torch.log(torch.tensor([1e-5 / 1.0, 0.25 / 0.75, 1.0 / 1e-5])))
+
+
+def test_seeded_array_is_a_pure_function_of_name_shape_seed():
+    a = synthetic.seeded_array("decoder.layers.0.linear1.weight", (4, 3), 7)
+    assert a.dtype == np.float32 and np.array_equal(a, synthetic.seeded_array("decoder.layers.0.linear1.weight", (4, 3), 7))
+    assert not np.array_equal(a, synthetic.seeded_array("decoder.layers.1.linear1.weight", (4, 3), 7))
+    assert not np.array_equal(a, synthetic.seeded_array("decoder.layers.0.linear1.weight", (4, 3), 8))
+    big = synthetic.seeded_array("x", (1000, 100), 0, -2.0, 2.0)
+    assert -2.0 <= big.min() < -1.99 and 1.99 < big.max() < 2.0 and abs(float(big.mean())) < 0.02
+    # a fixed known answer so a change of the recipe cannot go unnoticed
+    assert synthetic.seeded_array("x.weight", (3, 4), 1)[0, 0] == np.float32(0.62825286)
