@@ -433,6 +433,68 @@ int cape_token_step(const float* cls_logits, const float* reg, int64_t* step_dev
     return e == cudaSuccess ? 0 : fail_cuda(e, "cape_token_step launch");
 }
 
+// ---- decode-step kernels ------------------------------------------------------------------------------------------
+
+int cape_decode_attention(const float* q, int q_stride, const float* k_new, const float* v_new, int new_stride,
+                          float* k_cache, float* v_cache, const int64_t* pos_dev, const float* key_bias, float* out, int B,
+                          int T, int H, int D, void* stream) {
+    if (B < 0 || T <= 0 || H <= 0 || D != 32 || T > 1024 || q_stride % 4 != 0 || new_stride % 4 != 0)
+        return fail(CAPE_ERR_BAD_DIMS, "bad attention dimensions (B=%d T=%d H=%d D=%d; D must be 32, T <= 1024)", B, T, H, D);
+    if ((k_new == nullptr) != (v_new == nullptr) || (pos_dev != nullptr) != (k_new != nullptr))
+        return fail(CAPE_ERR_NULL_PTR, "k_new, v_new and pos_dev must be given together (self-attention) or all be NULL");
+    int rc;
+    const bool empty = B == 0;
+    if ((rc = check_ptr(q, "q", empty)) || (rc = check_ptr(k_cache, "k_cache", empty)) ||
+        (rc = check_ptr(v_cache, "v_cache", empty)) || (rc = check_ptr(out, "out", empty, 4)) ||
+        (rc = check_ptr(k_new, "k_new", true)) || (rc = check_ptr(v_new, "v_new", true)) ||
+        (rc = check_ptr(pos_dev, "pos_dev", true, 8)) || (rc = check_ptr(key_bias, "key_bias", true, 4)))
+        return rc;
+    const cudaError_t e = launch_decode_attention(q, k_new, v_new, k_cache, v_cache, pos_dev, key_bias, out, B, T, H,
+                                                  q_stride, new_stride, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? 0 : fail_cuda(e, "cape_decode_attention launch");
+}
+
+int cape_skinny_linear(const float* x, int x_stride, const float* x2, int x2_stride, const float* wt, const float* bias,
+                       const float* residual, int residual_stride, const float* gamma, const float* beta, float eps,
+                       const float* sine_dim_t, float* y, int y_stride, int rows, int K, int N, int epilogue, void* stream) {
+    if (rows < 0 || K <= 0 || N <= 0 || K % 16 != 0 || N % 4 != 0 || K > 4096)
+        return fail(CAPE_ERR_BAD_DIMS, "bad linear dimensions (rows=%d K=%d N=%d; K %% 16 == 0, K <= 4096, N %% 4 == 0)", rows, K, N);
+    if (epilogue < 0 || epilogue > 2) return fail(CAPE_ERR_BAD_DIMS, "unknown epilogue %d", epilogue);
+    if (epilogue == 2 && (N > 256 || !gamma || !beta))
+        return fail(CAPE_ERR_BAD_DIMS, "the LayerNorm epilogue needs N <= 256 (got %d) and gamma / beta", N);
+    if (sine_dim_t && K != 256) return fail(CAPE_ERR_BAD_DIMS, "the sine-embedding input has K = 256, got %d", K);
+    int rc;
+    const bool empty = rows == 0;
+    if ((rc = check_ptr(x, "x", empty, sine_dim_t ? 4 : 16)) || (rc = check_ptr(x2, "x2", true, 4)) ||
+        (rc = check_ptr(wt, "wt", false)) || (rc = check_ptr(bias, "bias", true, 4)) ||
+        (rc = check_ptr(residual, "residual", true, 4)) || (rc = check_ptr(gamma, "gamma", true, 4)) ||
+        (rc = check_ptr(beta, "beta", true, 4)) || (rc = check_ptr(sine_dim_t, "sine_dim_t", true, 4)) ||
+        (rc = check_ptr(y, "y", empty, 4)))
+        return rc;
+    SkinnyArgs a{};
+    a.x = x, a.x2 = x2, a.wt = wt, a.bias = bias, a.res = residual, a.gamma = gamma, a.beta = beta;
+    a.sine_dim_t = sine_dim_t, a.y = y;
+    a.rows = rows, a.K = K, a.N = N;
+    a.x_stride = x_stride, a.x2_stride = x2_stride, a.res_stride = residual_stride, a.y_stride = y_stride;
+    a.eps = eps;
+    const cudaError_t e = launch_skinny_linear(a, epilogue, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? 0 : fail_cuda(e, "cape_skinny_linear launch");
+}
+
+int cape_tiny_linear(const float* x, int x_stride, const float* w, const float* bias, const float* refine_ref, float* y,
+                     int rows, int K, int N, void* stream) {
+    if (rows < 0 || K <= 0 || K % 4 != 0 || N <= 0 || N > 8 || x_stride % 4 != 0)
+        return fail(CAPE_ERR_BAD_DIMS, "bad tiny-linear dimensions (rows=%d K=%d N=%d stride=%d; N <= 8, K %% 4 == 0)", rows, K, N,
+                    x_stride);
+    int rc;
+    const bool empty = rows == 0;
+    if ((rc = check_ptr(x, "x", empty)) || (rc = check_ptr(w, "w", false)) || (rc = check_ptr(bias, "bias", true, 4)) ||
+        (rc = check_ptr(refine_ref, "refine_ref", true, 4)) || (rc = check_ptr(y, "y", empty, 4)))
+        return rc;
+    const cudaError_t e = launch_tiny_linear(x, x_stride, w, bias, refine_ref, y, rows, K, N, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? 0 : fail_cuda(e, "cape_tiny_linear launch");
+}
+
 // ---- host-buffer round trip ------------------------------------------------------------------------------------
 
 namespace {

@@ -73,6 +73,28 @@ cudaError_t launch_points_sample_forward(const float* x, const float* pos, float
                                          cudaStream_t stream);
 cudaError_t launch_points_sample_backward(const float* gout, const float* x, const float* pos, float* gx, float* gpos,
                                           const PointsDims& p, cudaStream_t stream);
+// y = epilogue(x W^T + b) for a few rows (decode step).  wt is the weight TRANSPOSED, (K, N) row-major.
+struct SkinnyArgs {
+    const float* x;            // (rows, K) with row stride x_stride; in sine mode the (rows, 2) reference points
+    const float* x2;           // optional addend on the input, row stride x2_stride
+    const float* wt;
+    const float* bias;         // (N) or NULL
+    const float* res;          // epilogue 2: optional residual (rows, N), row stride res_stride
+    const float* gamma;        // epilogue 2: LayerNorm weight / bias (N)
+    const float* beta;
+    const float* sine_dim_t;   // non-NULL: input = sine embedding of x with these 128 divisors (K must be 256)
+    float* y;                  // (rows, N), row stride y_stride
+    int rows, K, N;
+    int x_stride, x2_stride, res_stride, y_stride;
+    float eps;
+};
+
+cudaError_t launch_decode_attention(const float* q, const float* k_new, const float* v_new, float* k_cache, float* v_cache,
+                                    const int64_t* pos_dev, const float* key_bias, float* out, int B, int T, int H,
+                                    int q_stride, int new_stride, cudaStream_t stream);
+cudaError_t launch_skinny_linear(const SkinnyArgs& a, int epilogue, cudaStream_t stream);
+cudaError_t launch_tiny_linear(const float* x, int x_stride, const float* w, const float* bias, const float* refine_ref,
+                               float* y, int rows, int K, int N, cudaStream_t stream);
 cudaError_t launch_seq_embed_forward(const SeqEmbedArgs& a, cudaStream_t stream);
 cudaError_t launch_seq_embed_backward(const SeqEmbedArgs& a, cudaStream_t stream);
 cudaError_t launch_token_step(const float* cls_logits, const float* reg, int64_t* step_dev, const cape_token_state& st,

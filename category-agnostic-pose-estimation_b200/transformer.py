@@ -324,7 +324,8 @@ class AutoregressiveGenerator(IncrementalDecoder):
     ``forward(..., decode_token_pos=i)`` path (:func:`generate_eager`).
     """
 
-    def __init__(self, transformer: DeformableTransformer, spec: TokenizerSpec, max_batch_size: int, device):
+    def __init__(self, transformer: DeformableTransformer, spec: TokenizerSpec, max_batch_size: int, device,
+                 fused: Optional[bool] = None):
         dec = transformer.decoder
         if not transformer.poly_refine or transformer.pre_decoder_pos_embed or transformer.dec_attn_concat_src \
                 or dec.query_pos_type not in ("sine", "none") or dec.class_embed is None or dec.coords_embed is None:
@@ -338,8 +339,103 @@ class AutoregressiveGenerator(IncrementalDecoder):
         self.pos = self.state.step                      # the K/V write position IS the generation step counter
         self.ref_table = torch.zeros(spec.seq_len, 2, device=self.device)
         self.valid_ratios = None
+        layer0 = dec.layers[0]
+        can_fuse = (transformer.d_model == 256 and transformer.d_model // transformer.nhead == 32
+                    and isinstance(layer0.attn_q, nn.Linear) and layer0.activation is F.relu
+                    and dec.query_pos_type == "sine" and spec.seq_len <= 1024)
+        if fused and not can_fuse:
+            raise NotImplementedError("the fused decode step needs d_model 256, head dim 32, q/k/v projections, ReLU and "
+                                      "sine query positions (the CAPE configuration)")
+        self.fused = can_fuse if fused is None else fused
+        self._fprep = None
+
+    def invalidate(self):
+        super().invalidate()
+        self._fprep = None
+
+    def _prepare_fused(self):
+        """Transposed / concatenated weights of the hand-written decode step (csrc/decode_step.cu), derived once from the
+        modules' own parameters (call ``invalidate()`` after changing them)."""
+        dec = self.transformer.decoder
+        t = lambda w: w.detach().t().contiguous()
+        layers = []
+        for lid, layer in enumerate(self.layers):
+            base = self._prep[lid]
+            sa, xa, ca = layer.self_attn, layer.support_attn, layer.cross_attn
+            head = dec.coords_embed[lid]
+            layers.append({
+                "wt_qkv": t(base["w_qkv"]), "b_qkv": base["b_qkv"], "wt_qin": t(base["wq_in"]), "b_qin": base["bq_in"],
+                "wt_o": t(sa.out_proj.weight), "b_o": sa.out_proj.bias, "n2": (layer.norm2.weight, layer.norm2.bias, layer.norm2.eps),
+                "wt_qs": t(base["wq_s"]), "b_qs": base["bq_s"], "wt_so": t(xa.out_proj.weight), "b_so": xa.out_proj.bias,
+                "ns": (layer.norm_support.weight, layer.norm_support.bias, layer.norm_support.eps),
+                "wt_off": t(ca.sampling_offsets.weight), "b_off": ca.sampling_offsets.bias,
+                "wt_log": t(ca.attention_weights.weight), "b_log": ca.attention_weights.bias,
+                "wt_out": t(ca.output_proj.weight), "b_out": ca.output_proj.bias,
+                "n1": (layer.norm1.weight, layer.norm1.bias, layer.norm1.eps),
+                "wt_f1": t(layer.linear1.weight), "b_f1": layer.linear1.bias, "wt_f2": t(layer.linear2.weight),
+                "b_f2": layer.linear2.bias, "n3": (layer.norm3.weight, layer.norm3.bias, layer.norm3.eps),
+                "wt_c1": t(head.layers[0].weight), "b_c1": head.layers[0].bias, "wt_c2": t(head.layers[1].weight),
+                "b_c2": head.layers[1].bias, "w_c3": head.layers[2].weight.detach().contiguous(), "b_c3": head.layers[2].bias,
+            })
+        dim_t = torch.arange(128, dtype=torch.float32, device=self.device)
+        dim_t = 10000 ** (2 * (dim_t // 2) / 128)                               # get_query_pos_embed, :1010-1011
+        return {"layers": layers, "dim_t": dim_t.contiguous(), "wt_pos": t(dec.pos_trans.weight), "b_pos": dec.pos_trans.bias,
+                "npos": (dec.pos_trans_norm.weight, dec.pos_trans_norm.bias, dec.pos_trans_norm.eps),
+                "w_cls": dec.class_embed[-1].weight.detach().contiguous(), "b_cls": dec.class_embed[-1].bias}
+
+    def _run_fused(self):
+        """One token through every decoder layer with the hand-written step kernels: 18 launches per layer, no library
+        GEMM / attention call.  Same arithmetic as :meth:`_run` (fp32 FMA; only the summation order differs)."""
+        from . import decode_ops as K
+        dec, st = self.transformer.decoder, self.state
+        n = self.batch
+        fp = self._fprep
+        shapes, starts, sup, _ = self._ctx
+        heads = self.layers[0].self_attn.num_heads
+        x = dec._seq_embed(*st.seq, *st.delta).view(n, -1)                                     # (B, C)
+        ref = self.ref_table.index_select(0, self.pos).expand(n, -1).contiguous()              # (B, 2), :1049-1050
+        for lid, layer in enumerate(self.layers):
+            w = fp["layers"][lid]
+            ca = layer.cross_attn
+            g, b_, eps = fp["npos"]
+            qpos = K.skinny_linear(ref, fp["wt_pos"], fp["b_pos"], gamma=g, beta=b_, eps=eps, sine_dim_t=fp["dim_t"])
+            # causal self-attention on the K/V cache (:322-341)
+            qkv = K.skinny_linear(x, w["wt_qkv"], w["b_qkv"])                                  # [attn_q(x) | k_in | v_in]
+            q_in = K.skinny_linear(qkv[:, :256], w["wt_qin"], w["b_qin"], x2=qpos)
+            attn = K.decode_attention(q_in, self.k_cache[lid], self.v_cache[lid], qkv[:, 256:512], qkv[:, 512:], self.pos,
+                                      n_heads=heads)
+            g, b_, eps = w["n2"]
+            x = K.skinny_linear(attn, w["wt_o"], w["b_o"], residual=x, gamma=g, beta=b_, eps=eps)
+            if sup is not None:                                                                # support cross-attention (:350-357)
+                q_s = K.skinny_linear(x, w["wt_qs"], w["b_qs"])
+                xs = K.decode_attention(q_s, self._sup_k_rows[lid], self._sup_v_rows[lid], key_bias=self._sup_bias_rows,
+                                        n_heads=heads)
+                g, b_, eps = w["ns"]
+                x = K.skinny_linear(xs, w["wt_so"], w["b_so"], residual=x, gamma=g, beta=b_, eps=eps)
+            # MSDeformAttn on the cached projected value (:360-363)
+            offsets = K.skinny_linear(x, w["wt_off"], w["b_off"], x2=qpos)
+            logits = K.skinny_linear(x, w["wt_log"], w["b_log"], x2=qpos)
+            ref_input = (ref[:, None, None, :] * self.valid_ratios[:, None]).contiguous()      # (B, 1, L, 2), :1072
+            sampled = torch.ops.cape.ms_deform_attn_decode(
+                self.values[lid], shapes, starts, ref_input,
+                offsets.view(n, 1, ca.n_heads, ca.n_levels, ca.n_points, 2),
+                logits.view(n, 1, ca.n_heads, ca.n_levels * ca.n_points)).view(n, -1)
+            g, b_, eps = w["n1"]
+            x = K.skinny_linear(sampled, w["wt_out"], w["b_out"], residual=x, gamma=g, beta=b_, eps=eps)
+            hidden = K.skinny_linear(x, w["wt_f1"], w["b_f1"], relu=True)                      # FFN (:366-368)
+            g, b_, eps = w["n3"]
+            x = K.skinny_linear(hidden, w["wt_f2"], w["b_f2"], residual=x, gamma=g, beta=b_, eps=eps)
+            # iterative refinement of the reference point by this layer's coordinate head (:1096-1102)
+            c = K.skinny_linear(x, w["wt_c1"], w["b_c1"], relu=True)
+            c = K.skinny_linear(c, w["wt_c2"], w["b_c2"], relu=True)
+            ref = K.tiny_linear(c, w["w_c3"], w["b_c3"], refine_ref=ref)
+        cls = K.tiny_linear(x, fp["w_cls"], fp["b_cls"])                                       # :1117-1121
+        st.advance(cls, ref)
+        return x
 
     def _run(self):
+        if self.fused:
+            return self._run_fused()
         dec, st = self.transformer.decoder, self.state
         n = self.batch
         mask = torch.zeros(1, 1, 1, self.max_len, device=self.device).masked_fill_(
@@ -379,6 +475,22 @@ class AutoregressiveGenerator(IncrementalDecoder):
             self.graph = None
         self.valid_ratios.copy_(enc_cache["valid_ratios"])
         self.ref_table.copy_(query_embed.sigmoid())                                          # :227
+        if self.fused:
+            if self._fprep is None:
+                self._fprep = self._prepare_fused()
+                self.graph = None
+            if self._sup is not None:   # support K / V as (B, T, C) rows for the attention kernel
+                to_rows = lambda t: t.transpose(1, 2).reshape(t.shape[0], t.shape[2], -1)
+                rows_shape = to_rows(self._sup_k[0]).shape
+                if getattr(self, "_sup_k_rows", None) is None or self._sup_k_rows[0].shape != rows_shape:
+                    # buffers the captured graph reads: allocated once per shape, refilled per batch
+                    self._sup_k_rows = [torch.empty(rows_shape, device=self.device) for _ in self.layers]
+                    self._sup_v_rows = [torch.empty(rows_shape, device=self.device) for _ in self.layers]
+                    self._sup_bias_rows = torch.empty(rows_shape[0], rows_shape[1], device=self.device)
+                    self.graph = None
+                for dst, src in zip(self._sup_k_rows + self._sup_v_rows, self._sup_k + self._sup_v):
+                    dst.copy_(to_rows(src))
+                self._sup_bias_rows.copy_(self._sup_bias.view(rows_shape[0], rows_shape[1]))
         self.state.reset()
         max_len = self.spec.seq_len
         if use_graph and self.graph is None:

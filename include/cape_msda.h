@@ -218,6 +218,38 @@ CAPE_API int cape_token_step(const float* cls_logits, const float* reg, int64_t*
                              const cape_tokenizer* tokenizer, int B, int n_classes, void* stream);
 
 /*
+ * Kernels of the incremental-decode step around cape_msda_decode (one new token per sequence; fp32).
+ *
+ * cape_decode_attention — attention of the new token over a K/V cache, head dimension 32
+ *   (TransformerDecoderLayer.forward, models/deformable_transformer_v2.py:322-341 with models/kv_cache.py:3-36, and the
+ *   support cross-attention :350-357).  q (B, H*32) is the in-projected query; q_stride / new_stride are the row strides
+ *   (elements, multiples of 4) of q and of k_new / v_new, so slices of one fused projection output can be passed.
+ *   Self-attention form: pos_dev != NULL, k_new / v_new (B, H*32) are the token's in-projected key / value; they are
+ *   written to k_cache / v_cache (B, T, H*32) at row *pos_dev and positions 0..*pos_dev are attended.  A position
+ *   outside [0, T) makes the call a no-op.
+ *   Cross-attention form: pos_dev = k_new = v_new = NULL, all T cached keys are attended; key_bias (B, T) or NULL is
+ *   added to the scores (-inf at padded keys).  T <= 1024.  out (B, H*32), before the output projection.
+ *
+ * cape_skinny_linear — y = epilogue(x W^T + b) for `rows` rows: wt (K, N) is the weight TRANSPOSED; K % 16 == 0, N % 4 == 0.
+ *   epilogue 0: bias; 1: bias + ReLU; 2: LayerNorm_N(residual + x W^T + b) * gamma + beta (N <= 256, residual may be NULL).
+ *   x2 (optional) is added to x first (tgt + query_pos).  With sine_dim_t != NULL (128 divisors, K = 256) the input is
+ *   the sine embedding of the (rows, 2) reference points in x (TransformerDecoder.get_query_pos_embed, :1005-1018).
+ *   Strides are row strides in elements.
+ *
+ * cape_tiny_linear — y (rows, N) = x W^T + b with w (N, K) as a Linear stores it, N <= 8, K % 4 == 0; with refine_ref
+ *   (rows, N) != NULL the result is sigmoid(y + inverse_sigmoid(refine_ref)) (iterative refinement, :1096-1102).
+ */
+CAPE_API int cape_decode_attention(const float* q, int q_stride, const float* k_new, const float* v_new, int new_stride,
+                                   float* k_cache, float* v_cache, const int64_t* pos_dev, const float* key_bias,
+                                   float* out, int B, int T, int H, int D, void* stream);
+CAPE_API int cape_skinny_linear(const float* x, int x_stride, const float* x2, int x2_stride, const float* wt,
+                                const float* bias, const float* residual, int residual_stride, const float* gamma,
+                                const float* beta, float eps, const float* sine_dim_t, float* y, int y_stride, int rows,
+                                int K, int N, int epilogue, void* stream);
+CAPE_API int cape_tiny_linear(const float* x, int x_stride, const float* w, const float* bias, const float* refine_ref,
+                              float* y, int rows, int K, int N, void* stream);
+
+/*
  * Host-buffer round trip used for end-to-end measurement and for callers without device buffers:
  * copies the inputs from (ideally pinned) HOST memory into the caller-provided device workspace, runs forward and,
  * when grad_out_host != NULL, backward, and copies the results back to HOST memory — all enqueued on `stream`.

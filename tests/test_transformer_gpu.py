@@ -191,3 +191,111 @@ def test_token_step_follows_the_reference_bookkeeping_rules():
     state.advance(torch.zeros(b, 1, 3).cuda(), torch.zeros(b, 1, 2).cuda())        # past max_len: a no-op
     torch.cuda.synchronize()
     assert int(state.step.item()) == spec.seq_len + 1
+
+
+# ---- hand-written decode-step kernels (csrc/decode_step.cu) vs plain PyTorch fp32 ----------------------------------
+def test_generation_with_library_kernels_and_with_step_kernels_agree_with_the_reference(fx):
+    g, tr, spec = fx["g"], fx["tr"], fx["spec"]
+    for fused in (False, True):
+        gen = cape_b200.AutoregressiveGenerator(tr, spec, max_batch_size=2, device="cuda", fused=fused)
+        assert gen.fused is fused
+        out = gen.generate(fx["feats"], fx["masks"], fx["pos"], fx["query_embed"], fx["sup"], fx["sup_mask"])
+        _check_generation(out, g, "gen")
+
+
+@pytest.mark.parametrize("rows,k,n", [(128, 256, 256), (5, 256, 768), (2, 1024, 256), (7, 256, 1024), (3, 256, 128), (1, 64, 36)])
+def test_skinny_linear_epilogues_vs_torch(rows, k, n):
+    from cape_b200 import decode_ops as K
+    gen = torch.Generator().manual_seed(rows * 1000 + n)
+    lin = torch.nn.Linear(k, n)
+    x, x2, res = torch.randn(rows, k, generator=gen), torch.randn(rows, k, generator=gen), torch.randn(rows, n, generator=gen)
+    ln = torch.nn.LayerNorm(n)
+    with torch.no_grad():
+        ln.weight.add_(torch.randn(n, generator=gen) * 0.1)
+        ln.bias.add_(torch.randn(n, generator=gen) * 0.1)
+    lin, ln = lin.cuda(), ln.cuda()
+    wt = lin.weight.detach().t().contiguous()
+    xc, x2c, resc = x.cuda(), x2.cuda(), res.cuda()
+    with torch.no_grad():
+        assert rel_err(K.skinny_linear(xc, wt, lin.bias).cpu(), lin(xc).cpu()) < FWD_TOL_F32
+        assert rel_err(K.skinny_linear(xc, wt, None, x2=x2c).cpu(), torch.nn.functional.linear(xc + x2c, lin.weight).cpu()) < FWD_TOL_F32
+        assert rel_err(K.skinny_linear(xc, wt, lin.bias, relu=True).cpu(), lin(xc).relu().cpu()) < FWD_TOL_F32
+        # strided input rows (a slice of a wider projection output)
+        wide = torch.randn(rows, k + 64, generator=gen).cuda()
+        assert rel_err(K.skinny_linear(wide[:, 32:32 + k], wt, lin.bias).cpu(), lin(wide[:, 32:32 + k]).cpu()) < FWD_TOL_F32
+        if n <= 256:
+            got = K.skinny_linear(xc, wt, lin.bias, residual=resc, gamma=ln.weight, beta=ln.bias, eps=ln.eps)
+            assert rel_err(got.cpu(), ln(resc + lin(xc)).cpu()) < FWD_TOL_F32
+            got = K.skinny_linear(xc, wt, lin.bias, gamma=ln.weight, beta=ln.bias, eps=ln.eps)
+            assert rel_err(got.cpu(), ln(lin(xc)).cpu()) < FWD_TOL_F32
+
+
+def test_skinny_linear_sine_input_matches_query_pos_embedding():
+    from cape_b200 import decode_ops as K
+    torch.manual_seed(0)
+    lin, ln = torch.nn.Linear(256, 256).cuda(), torch.nn.LayerNorm(256).cuda()
+    ref = torch.rand(9, 2, device="cuda")
+    dim_t = torch.arange(128, dtype=torch.float32, device="cuda")
+    dim_t = 10000 ** (2 * (dim_t // 2) / 128)
+    with torch.no_grad():
+        want = ln(lin(cape_b200.TransformerDecoder.get_query_pos_embed(ref[:, None])[:, 0]))
+        got = K.skinny_linear(ref, lin.weight.t().contiguous(), lin.bias, gamma=ln.weight, beta=ln.bias, eps=ln.eps,
+                              sine_dim_t=dim_t)
+    assert rel_err(got.cpu(), want.cpu()) < FWD_TOL_F32
+
+
+def test_tiny_linear_and_refinement_vs_torch():
+    from cape_b200 import decode_ops as K
+    from cape_b200.transformer import inverse_sigmoid
+    torch.manual_seed(1)
+    for n in (2, 3, 8):
+        lin = torch.nn.Linear(256, n).cuda()
+        x = torch.randn(11, 256, device="cuda")
+        ref = torch.rand(11, n, device="cuda")
+        ref[0, 0], ref[1, 0] = 0.0, 1.0                                   # the clamps of inverse_sigmoid
+        with torch.no_grad():
+            assert rel_err(K.tiny_linear(x, lin.weight, lin.bias).cpu(), lin(x).cpu()) < FWD_TOL_F32
+            got = K.tiny_linear(x, lin.weight, lin.bias, refine_ref=ref)
+            assert rel_err(got.cpu(), (lin(x) + inverse_sigmoid(ref)).sigmoid().cpu()) < FWD_TOL_F32
+
+
+def test_decode_attention_vs_multihead_attention_with_kv_cache():
+    """Self-attention form against nn.MultiheadAttention over the growing prefix (what the reference layer does with its
+    KVCache, deformable_transformer_v2.py:322-341), and the cross-attention form with a key-padding mask (:350-357)."""
+    from cape_b200 import decode_ops as K
+    torch.manual_seed(5)
+    b, t_max, c, heads = 3, 40, 256, 8
+    mha = torch.nn.MultiheadAttention(c, heads, batch_first=True).cuda().eval()
+    wq, wk, wv = mha.in_proj_weight.chunk(3)
+    bq, bk, bv = mha.in_proj_bias.chunk(3)
+    xs = torch.randn(b, t_max, c, device="cuda")
+    k_cache = torch.zeros(b, t_max, c, device="cuda")
+    v_cache = torch.zeros(b, t_max, c, device="cuda")
+    pos = torch.zeros(1, dtype=torch.int64, device="cuda")
+    lin = torch.nn.functional.linear
+    with torch.no_grad():
+        for i in (0, 1, 2, 31, 32, 33, 39):                               # crosses the 32-key lane blocks
+            # fill the cache up to i-1 exactly, then decode token i
+            k_cache[:, :i] = lin(xs[:, :i], wk, bk)
+            v_cache[:, :i] = lin(xs[:, :i], wv, bv)
+            k_cache[:, i:], v_cache[:, i:] = 7.0, 7.0                      # stale rows beyond the position must not matter
+            pos.fill_(i)
+            x = xs[:, i]
+            proj = torch.cat([lin(x, wq, bq), lin(x, wk, bk), lin(x, wv, bv)], 1)          # strided slices, as the generator passes
+            got = K.decode_attention(proj[:, :c], k_cache, v_cache, proj[:, c:2 * c], proj[:, 2 * c:], pos, n_heads=heads)
+            want = mha(xs[:, i:i + 1], xs[:, :i + 1], xs[:, :i + 1], need_weights=False)[0][:, 0]
+            assert rel_err(mha.out_proj(got).cpu(), want.cpu()) < FWD_TOL_F32, i
+            assert torch.equal(k_cache[:, i], proj[:, c:2 * c]) and torch.equal(v_cache[:, i], proj[:, 2 * c:])
+        # cross-attention over 17 support keys, two of them padded for one sample
+        sup = torch.randn(b, 17, c, device="cuda")
+        pad = torch.zeros(b, 17, dtype=torch.bool, device="cuda")
+        pad[1, -2:] = True
+        bias = torch.zeros(b, 17, device="cuda").masked_fill_(pad, float("-inf"))
+        q = torch.randn(b, c, device="cuda")
+        got = K.decode_attention(lin(q, wq, bq), lin(sup, wk, bk).contiguous(), lin(sup, wv, bv).contiguous(), key_bias=bias,
+                                 n_heads=heads)
+        want = mha(q[:, None], sup, sup, key_padding_mask=pad, need_weights=False)[0][:, 0]
+        assert rel_err(mha.out_proj(got).cpu(), want.cpu()) < FWD_TOL_F32
+        pos.fill_(t_max)                                                   # out-of-range position: a no-op, not a fault
+        K.decode_attention(proj[:, :c], k_cache, v_cache, proj[:, c:2 * c], proj[:, 2 * c:], pos, n_heads=heads)
+        torch.cuda.synchronize()
