@@ -16,8 +16,12 @@
 // All fp32, FMA accumulation; weights are read from L2 (the whole 6-layer decoder is 32 MB).
 #include <cfloat>
 
+#include <cooperative_groups.h>
+
 #include "msda_common.cuh"
 #include "msda_launch.h"
+
+namespace cg = cooperative_groups;
 
 namespace cape {
 
@@ -109,20 +113,46 @@ decode_attn_kernel(const float* __restrict__ q, const float* __restrict__ k_new,
 }
 
 // ---- skinny linear ---------------------------------------------------------------------------------------------------
+// Latency-oriented: a decode-step GEMM is 128 rows x 256 x 256 (17 MFLOP) — what matters is how many bytes one SM has to
+// pull from L2 and how many dependent round trips the kernel makes.  Tile = 4 rows x 64 columns, so a 256 x 256 layer
+// spreads over 32 x 4 = 128 CTAs and each SM reads a 64 KB weight slab instead of the whole 256 KB matrix.
+// 256 threads = 16 k-groups x 16 column threads (4 columns each): a thread's share of the reduction dimension is K / 16
+// rows of the transposed weight, fetched as up to 16 independent LDG.128 issued BEFORE the input rows are staged, so the
+// weight round trip overlaps the input round trip.  The k-groups are summed through shared memory.  The LayerNorm
+// epilogue needs whole rows: the (up to 4) CTAs that share a row tile form a thread-block cluster and exchange their
+// per-row sums through distributed shared memory (two-pass mean / variance, like ATen).
 constexpr int kSkRows = 4;        // rows per CTA
-constexpr int kSkCols = 256;      // output columns per CTA (64 column threads x 4 columns)
-constexpr int kSkGroups = 4;      // k-groups: the reduction dimension is split over 4 x 64 threads
+constexpr int kSkCols = 64;       // output columns per CTA
+constexpr int kSkGroups = 16;     // k-groups
+constexpr int kSkBatch = 16;      // weight rows a thread keeps in flight
 
-template <int EPI>   // 0 bias, 1 bias + ReLU, 2 bias (+ residual) + LayerNorm over the N (= 256) outputs
+template <int EPI>   // 0 bias, 1 bias + ReLU, 2 bias (+ residual) + LayerNorm over the N (<= 256) outputs
 __global__ void __launch_bounds__(256)
 skinny_linear_kernel(SkinnyArgs a) {
     extern __shared__ __align__(16) float smem[];
     float* xs = smem;                                       // [kSkRows][K]
     float* part = smem + kSkRows * a.K;                     // [kSkGroups][kSkRows][kSkCols]
+    __shared__ float stat[2][kSkRows];                      // this CTA's per-row partial sums (read by cluster peers)
     const int tid = threadIdx.x;
     const int r0 = blockIdx.x * kSkRows;
     const int c0 = blockIdx.y * kSkCols;
     const int rows = min(kSkRows, a.rows - r0);
+    const int kg = tid >> 4, ct = tid & 15;
+    const int col = c0 + ct * 4;
+    const int kper = a.K / kSkGroups;                       // K % 16 == 0
+    const bool col_live = col < a.N;
+    const float* wp = a.wt + static_cast<int64_t>(kg * kper) * a.N + col;
+    float acc[kSkRows][4];
+#pragma unroll
+    for (int r = 0; r < kSkRows; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+    // first batch of weight rows: in flight while the inputs are staged
+    float4 w[kSkBatch];
+#pragma unroll
+    for (int j = 0; j < kSkBatch; ++j)
+        w[j] = (col_live && j < kper) ? __ldg(reinterpret_cast<const float4*>(wp + static_cast<int64_t>(j) * a.N))
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
     // stage the input rows (optionally x + x2, or the sine embedding of the reference points)
     for (int i = tid; i < kSkRows * a.K; i += 256) {
         const int r = i / a.K, k = i - r * a.K;
@@ -141,34 +171,27 @@ skinny_linear_kernel(SkinnyArgs a) {
         xs[i] = v;
     }
     __syncthreads();
-    const int kg = tid >> 6, ct = tid & 63;
-    const int col = c0 + ct * 4;
-    float acc[kSkRows][4];
+    const float* xp = xs + kg * kper;
+    for (int k0 = 0; k0 < kper; k0 += kSkBatch) {
 #pragma unroll
-    for (int r = 0; r < kSkRows; ++r)
+        for (int j = 0; j < kSkBatch; ++j) {
+            if (k0 + j < kper) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
-    const int kper = a.K / kSkGroups;
-    if (col < a.N) {
-        const float* wp = a.wt + static_cast<int64_t>(kg * kper) * a.N + col;
-        const float* xp = xs + kg * kper;
-#pragma unroll 4
-        for (int k = 0; k < kper; k += 4) {
-            float4 w[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) w[j] = __ldg(reinterpret_cast<const float4*>(wp + static_cast<int64_t>(k + j) * a.N));
-#pragma unroll
-            for (int r = 0; r < kSkRows; ++r) {
-                const float4 xv = *reinterpret_cast<const float4*>(xp + r * a.K + k);
-                const float xk[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    acc[r][0] = fmaf(xk[j], w[j].x, acc[r][0]);
-                    acc[r][1] = fmaf(xk[j], w[j].y, acc[r][1]);
-                    acc[r][2] = fmaf(xk[j], w[j].z, acc[r][2]);
-                    acc[r][3] = fmaf(xk[j], w[j].w, acc[r][3]);
+                for (int r = 0; r < kSkRows; ++r) {
+                    const float xk = xp[r * a.K + k0 + j];
+                    acc[r][0] = fmaf(xk, w[j].x, acc[r][0]);
+                    acc[r][1] = fmaf(xk, w[j].y, acc[r][1]);
+                    acc[r][2] = fmaf(xk, w[j].z, acc[r][2]);
+                    acc[r][3] = fmaf(xk, w[j].w, acc[r][3]);
                 }
             }
+        }
+        if (k0 + kSkBatch < kper) {
+#pragma unroll
+            for (int j = 0; j < kSkBatch; ++j)
+                w[j] = (col_live && k0 + kSkBatch + j < kper)
+                           ? __ldg(reinterpret_cast<const float4*>(wp + static_cast<int64_t>(k0 + kSkBatch + j) * a.N))
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
 #pragma unroll
@@ -176,54 +199,41 @@ skinny_linear_kernel(SkinnyArgs a) {
         *reinterpret_cast<float4*>(part + (kg * kSkRows + r) * kSkCols + ct * 4) =
             make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
     __syncthreads();
-    // thread t finishes column c0 + t of every row
-    const int c = c0 + tid;
-    const bool live = c < a.N;
-    float y[kSkRows];
+    // thread t finishes (row t / 64, column c0 + t % 64)
+    const int r = tid >> 6, cc = tid & 63;
+    const int c = c0 + cc;
+    const bool live = c < a.N && r < rows;
+    float v = 0.f;
 #pragma unroll
-    for (int r = 0; r < kSkRows; ++r) {
-        float v = 0.f;
-#pragma unroll
-        for (int g = 0; g < kSkGroups; ++g) v += part[(g * kSkRows + r) * kSkCols + tid];
-        if (live && a.bias) v += __ldg(a.bias + c);
-        if (EPI == 1) v = fmaxf(v, 0.f);
-        if (EPI == 2 && live && a.res && r < rows) v += a.res[static_cast<int64_t>(r0 + r) * a.res_stride + c];
-        y[r] = live ? v : 0.f;
-    }
-    if (EPI == 2) {   // LayerNorm over the N outputs of each row (N <= 256: one CTA holds the row); two-pass variance
-        __shared__ float red[kSkRows][8];
-        const int lane = tid & 31, warp = tid >> 5;
-        float mean[kSkRows], rstd[kSkRows];
+    for (int g = 0; g < kSkGroups; ++g) v += part[(g * kSkRows + r) * kSkCols + cc];
+    if (live && a.bias) v += __ldg(a.bias + c);
+    if (EPI == 1) v = fmaxf(v, 0.f);
+    if (EPI == 2) {
+        if (live && a.res) v += a.res[static_cast<int64_t>(r0 + r) * a.res_stride + c];
+        if (!live) v = 0.f;
+        cg::cluster_group cluster = cg::this_cluster();
+        const unsigned peers = cluster.num_blocks();
+        const int lane = tid & 31, half = (tid >> 5) & 1;            // a row is two warps
+        __shared__ float warp_part[kSkRows][2];
+        float mean = 0.f, rstd = 0.f;
 #pragma unroll
         for (int pass = 0; pass < 2; ++pass) {
+            float s = pass == 0 ? v : ((c < a.N) ? (v - mean) * (v - mean) : 0.f);
 #pragma unroll
-            for (int r = 0; r < kSkRows; ++r) {
-                float v = pass == 0 ? y[r] : (live ? (y[r] - mean[r]) * (y[r] - mean[r]) : 0.f);
-#pragma unroll
-                for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
-                if (lane == 0) red[r][warp] = v;
-            }
+            for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(kFullMask, s, o);
+            if (lane == 0) warp_part[r][half] = s;
             __syncthreads();
-#pragma unroll
-            for (int r = 0; r < kSkRows; ++r) {
-                float v = 0.f;
-#pragma unroll
-                for (int w = 0; w < 8; ++w) v += red[r][w];
-                if (pass == 0) mean[r] = v / static_cast<float>(a.N);
-                else rstd[r] = rsqrtf(v / static_cast<float>(a.N) + a.eps);
-            }
-            __syncthreads();
+            if (tid < kSkRows) stat[pass][tid] = warp_part[tid][0] + warp_part[tid][1];
+            cluster.sync();                                          // every CTA of the row tile has published its partial
+            float total = 0.f;
+            for (unsigned p = 0; p < peers; ++p) total += cluster.map_shared_rank(&stat[pass][0], p)[r];
+            if (pass == 0) mean = total / static_cast<float>(a.N);
+            else rstd = rsqrtf(total / static_cast<float>(a.N) + a.eps);
         }
-        if (live) {
-            const float gmm = __ldg(a.gamma + c), bta = __ldg(a.beta + c);
-#pragma unroll
-            for (int r = 0; r < kSkRows; ++r) y[r] = (y[r] - mean[r]) * rstd[r] * gmm + bta;
-        }
+        if (live) v = (v - mean) * rstd * __ldg(a.gamma + c) + __ldg(a.beta + c);
+        cluster.sync();                                              // nobody leaves while a peer may still read its stats
     }
-    if (live)
-#pragma unroll
-        for (int r = 0; r < kSkRows; ++r)
-            if (r < rows) a.y[static_cast<int64_t>(r0 + r) * a.y_stride + c] = y[r];
+    if (live) a.y[static_cast<int64_t>(r0 + r) * a.y_stride + c] = v;
 }
 
 // One warp per row; N <= 8 outputs; w is (N, K) row-major (a Linear's own layout).
@@ -281,16 +291,28 @@ size_t skinny_smem_bytes(int K) { return (static_cast<size_t>(kSkRows) * K + kSk
 
 cudaError_t launch_skinny_linear(const SkinnyArgs& a, int epilogue, cudaStream_t stream) {
     if (a.rows == 0) return cudaSuccess;
-    const dim3 grid((a.rows + kSkRows - 1) / kSkRows, (a.N + kSkCols - 1) / kSkCols);
-    const size_t smem = skinny_smem_bytes(a.K);
+    const unsigned col_tiles = (a.N + kSkCols - 1) / kSkCols;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((a.rows + kSkRows - 1) / kSkRows, col_tiles);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = skinny_smem_bytes(a.K);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = epilogue == 2 ? col_tiles : 1;    // LayerNorm: the CTAs of a row tile share statistics
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e;
     switch (epilogue) {
-        case 0: skinny_linear_kernel<0><<<grid, 256, smem, stream>>>(a); break;
-        case 1: skinny_linear_kernel<1><<<grid, 256, smem, stream>>>(a); break;
-        case 2: skinny_linear_kernel<2><<<grid, 256, smem, stream>>>(a); break;
+        case 0: e = cudaLaunchKernelEx(&cfg, skinny_linear_kernel<0>, a); break;
+        case 1: e = cudaLaunchKernelEx(&cfg, skinny_linear_kernel<1>, a); break;
+        case 2: e = cudaLaunchKernelEx(&cfg, skinny_linear_kernel<2>, a); break;
         default: return cudaErrorInvalidValue;
     }
     count_launch();
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 cudaError_t launch_tiny_linear(const float* x, int x_stride, const float* w, const float* bias, const float* refine_ref,

@@ -32,11 +32,34 @@ enc_cache = {"memory": memory, "spatial_shapes": shapes,
 query_embed = torch.randn(spec.seq_len, 2, device=dev)
 sup = torch.randn(n, 17, 256, device=dev)
 sup_mask = torch.zeros(n, 17, dtype=torch.bool, device=dev)
-gen = cape_b200.AutoregressiveGenerator(tr, spec, n, dev)
+gen = cape_b200.AutoregressiveGenerator(tr, spec, n, dev, fused=os.environ.get("GEN_FUSED", "1") == "1")
 with torch.no_grad():
-    gen.reset(memory, shapes, enc_cache["level_start_index"], sup, sup_mask, padding_mask=enc_cache["mask_flatten"])
-    gen.valid_ratios = enc_cache["valid_ratios"]
-    gen.ref_table.copy_(query_embed.sigmoid())
+    import time
+    out = gen.generate(None, None, None, query_embed, sup, sup_mask, enc_cache=enc_cache)      # captures the graph
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = gen.generate(None, None, None, query_embed, sup, sup_mask, enc_cache=enc_cache)
+    torch.cuda.synchronize()
+    t_all = time.perf_counter() - t0
+    gen.state.reset()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(100):
+        gen.graph.replay()
+    torch.cuda.synchronize()
+    t_rep = (time.perf_counter() - t0) / 100
+    print(f"generate() {t_all * 1e3:.1f} ms for {out['steps']} steps; graph replay {t_rep * 1e6:.0f} us per step")
+
+    def timed(fn):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        r = fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) * 1e3, r
+    t_reset, _ = timed(lambda: gen.reset(memory, shapes, enc_cache["level_start_index"], sup, sup_mask,
+                                         padding_mask=enc_cache["mask_flatten"]))
+    t_collect, _ = timed(gen._collect)
+    print(f"reset {t_reset:.1f} ms, collect {t_collect:.1f} ms")
     gen.state.reset()
     for _ in range(3):
         gen._run()
@@ -46,6 +69,8 @@ with torch.no_grad():
     torch.cuda.synchronize()
     torch.cuda.nvtx.range_pop()
     # timing of the same step, eager and as a graph
+    if gen.fused and gen._fprep is None:
+        pass
     import time
     t0 = time.perf_counter()
     for _ in range(20):
