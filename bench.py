@@ -209,7 +209,7 @@ def run_reference(args, rank, world):
 
 
 # ---- data-parallel training step of the deformable transformer (all N; BASELINE.json configs[2] and [4]) ---------
-def train_step(dev, rank, world, accumulation=4, steps=2):
+def train_step(dev, rank, world, accumulation=4, steps=2, amp=False):
     """One optimizer step of the CAPE transformer body on every rank: 6 deformable encoder layers (Lq = S = 5440) +
     6 decoder layers v1 (teacher-forced, 200 tokens, 17 support keypoints), micro-batch of 10 episodes x 2 queries
     (N = 20), gradient accumulation 4, ONE flat-bucket gradient all-reduce over NCCL (dist.FlatGradAllreduce), clip 0.1,
@@ -242,14 +242,21 @@ def train_step(dev, rank, world, accumulation=4, steps=2):
         x = tgt
         for layer in dec:
             x, _ = layer(x, qpos, ref, memory, shapes, starts, None, causal, support_features=sup, support_mask=sup_mask)
-        return x.square().mean() / accumulation
+        return x.float().square().mean() / accumulation
+
+    # amp=True is the reference's --use_amp path: fp16 autocast + GradScaler (engine_cape.py:163-165, 234-252)
+    scaler = torch.amp.GradScaler("cuda", enabled=amp)
 
     def optimizer_step():
         for _ in range(accumulation):
-            micro_batch().backward()
+            with torch.autocast("cuda", dtype=torch.float16, enabled=amp):
+                loss = micro_batch()
+            scaler.scale(loss).backward()
+        scaler.unscale_(opt)
         allreduce()                                # the only collective of the step
         torch.nn.utils.clip_grad_norm_(params, 0.1)
-        opt.step()
+        scaler.step(opt)
+        scaler.update()
         opt.zero_grad(set_to_none=True)
 
     launches0 = cape_b200.launch_count()
@@ -270,7 +277,9 @@ def train_step(dev, rank, world, accumulation=4, steps=2):
     torch.cuda.empty_cache()
     return {"episodes_per_s": round(episodes / (ms * 1e-3), 2), "ms_per_optimizer_step": round(ms, 2),
             "episodes_per_step": episodes, "accumulation": accumulation, "allreduce_mb": round(n_params * 4 / 2 ** 20, 1),
-            "msda_launches_per_step": int(per_step_launches), "dtype": "f32 (TF32 off)",
+            "msda_launches_per_step": int(per_step_launches),
+            "dtype": "fp16 autocast + GradScaler (the reference's --use_amp); MSDeformAttn value fp16, accumulation fp32"
+            if amp else "f32 (TF32 off)",
             "scope": "6 encoder + 6 decoder (v1) layers of the deformable transformer, fwd + bwd + NCCL all-reduce + "
                      "AdamW; synthetic features; no backbone / support encoder / heads"}
 
@@ -655,6 +664,12 @@ def run_b200(args, rank, world, local_rank):
             train = train_step(dev, rank, world)
         except Exception as exc:                                   # noqa: BLE001 - every rank must keep going
             train = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+    train_amp = None
+    if not args.no_extras:
+        try:
+            train_amp = train_step(dev, rank, world, amp=True)
+        except Exception as exc:                                   # noqa: BLE001 - every rank must keep going
+            train_amp = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     if rank != 0:
         return
     peak, peak_src = measured_peak()
@@ -683,6 +698,8 @@ def run_b200(args, rank, world, local_rank):
     }
     if train is not None:
         line["train_step"] = train
+    if train_amp is not None:
+        line["train_step_amp"] = train_amp
     if world == 1 and not args.no_extras:
         line["sweep"] = guarded(op_sweep, lib, dev)
         line["module"] = guarded(module_step, dev)
