@@ -27,6 +27,40 @@ __global__ void gather_f32_v4(const float4* __restrict__ table, const int* __res
     if (acc.x == 123.456f) out[threadIdx.x] = acc;
 }
 
+// same gather through the texture path (tex1Dfetch<float4> on a linear texture object): does TEX add gather throughput
+// next to the LSU?
+__global__ void gather_f32_tex(cudaTextureObject_t tex, const int* __restrict__ idx, float4* __restrict__ out, int rows_per_cta_window, int window_stride) {
+    const int lane = threadIdx.x & 31, slot = lane >> 3, k = lane & 7;
+    const int warp = threadIdx.x >> 5;
+    const int* my = idx + ((size_t)blockIdx.x * (kThreads / 32) + warp) * kIters * 4;
+    const int base = (blockIdx.x % window_stride) * rows_per_cta_window * 8;
+    float4 acc = make_float4(0, 0, 0, 0);
+#pragma unroll 8
+    for (int i = 0; i < kIters; ++i) {
+        const int r = __ldg(my + i * 4 + slot);
+        const float4 v = tex1Dfetch<float4>(tex, base + r * 8 + k);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    if (acc.x == 123.456f) out[threadIdx.x] = acc;
+}
+
+// alternate: even iterations through LDG.128, odd iterations through the texture path
+__global__ void gather_f32_mixed(const float4* __restrict__ table, cudaTextureObject_t tex, const int* __restrict__ idx, float4* __restrict__ out, int rows_per_cta_window, int window_stride) {
+    const int lane = threadIdx.x & 31, slot = lane >> 3, k = lane & 7;
+    const int warp = threadIdx.x >> 5;
+    const int* my = idx + ((size_t)blockIdx.x * (kThreads / 32) + warp) * kIters * 4;
+    const int base = (blockIdx.x % window_stride) * rows_per_cta_window * 8;
+    float4 acc = make_float4(0, 0, 0, 0);
+#pragma unroll 4
+    for (int i = 0; i < kIters; i += 2) {
+        const int r0 = __ldg(my + i * 4 + slot), r1 = __ldg(my + i * 4 + 4 + slot);
+        const float4 v = __ldg(table + base + (size_t)r0 * 8 + k);
+        const float4 u = tex1Dfetch<float4>(tex, base + r1 * 8 + k);
+        acc.x += v.x + u.x; acc.y += v.y + u.y; acc.z += v.z + u.z; acc.w += v.w + u.w;
+    }
+    if (acc.x == 123.456f) out[threadIdx.x] = acc;
+}
+
 // lane = channel: one row (128 B) per LDG.32 warp instruction
 __global__ void gather_f32_scalar(const float* __restrict__ table, const int* __restrict__ idx, float* __restrict__ out, int rows_per_cta_window, int window_stride) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -184,6 +218,17 @@ int main() {
     int* idx; CK(cudaMalloc(&idx, n_idx * sizeof(int)));
     float4* out; CK(cudaMalloc(&out, 1 << 20));
     std::vector<int> h(n_idx);
+    cudaTextureObject_t tex = 0;
+    {
+        cudaResourceDesc rd = {};
+        rd.resType = cudaResourceTypeLinear;
+        rd.res.linear.devPtr = table;
+        rd.res.linear.desc = cudaCreateChannelDesc<float4>();
+        rd.res.linear.sizeInBytes = (size_t)870400 * 128 + (size_t)148 * 512 * 128;
+        cudaTextureDesc td = {};
+        td.readMode = cudaReadModeElementType;
+        CK(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
+    }
     for (const Case& c : cases) {
         srand(1);
         for (size_t i = 0; i < n_idx; ++i) h[i] = rand() % c.rows;
@@ -195,6 +240,8 @@ int main() {
                    rows_per_s * bytes_per_row / 1e12, (clk_khz * 1e3) / (rows_per_s / sms), clk_khz / 1000.0);
         };
         report("gather fp32 LDG.128 (4 rows/instr)", time_ms([&] { gather_f32_v4<<<grid, kThreads>>>((const float4*)table, idx, out, c.rows, c.windows); }), 128);
+        report("gather fp32 TEX float4 (4 rows/instr)", time_ms([&] { gather_f32_tex<<<grid, kThreads>>>(tex, idx, out, c.rows, c.windows); }), 128);
+        report("gather fp32 LDG.128 + TEX alternating", time_ms([&] { gather_f32_mixed<<<grid, kThreads>>>((const float4*)table, tex, idx, out, c.rows, c.windows); }), 128);
         report("gather fp32 LDG.32 (1 row/instr)", time_ms([&] { gather_f32_scalar<<<grid, kThreads>>>(table, idx, (float*)out, c.rows, c.windows); }), 128);
         report("gather bf16 LDG.64 (4 rows/instr)", time_ms([&] { gather_bf16_v2<<<grid, kThreads>>>((const uint2*)table, idx, (uint2*)out, c.rows, c.windows); }), 64);
         report("red.global.add.v4.f32 (4 rows/instr)", time_ms([&] { red_global_v4<<<grid, kThreads>>>(table, idx, c.rows, c.windows); }), 128);
