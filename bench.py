@@ -514,6 +514,10 @@ def generation(dev, episodes=64, keypoints=100):
     run()                                                    # captures the graph
     t_dec, out = timed(run)
     steps = out["steps"]
+    gen.state.reset()                                        # the token step alone: replays of the captured graph
+    t_rep, _ = timed(lambda: [gen.graph.replay() for _ in range(50)])
+    t_reset, _ = timed(lambda: gen.reset(enc_cache["memory"], enc_cache["spatial_shapes"], enc_cache["level_start_index"],
+                                         sup, sup_mask, padding_mask=enc_cache["mask_flatten"]))
     few = 6
     short = cape_b200.TokenizerSpec(num_bins=44, seq_len=few)
     cape_b200.generate_eager(tr, short, feats, masks, pos, query_embed[:few], sup, sup_mask)
@@ -521,7 +525,8 @@ def generation(dev, episodes=64, keypoints=100):
     t_eager_tok = (t_eager - t_enc) / few
     total = t_enc + t_dec
     return {"episodes": episodes, "queries_per_episode": 2, "tokens": steps, "encoder_layers": 6, "decoder_layers": 6,
-            "encoder_s": round(t_enc, 4), "decode_s": round(t_dec, 4), "us_per_token_step": round(t_dec / steps * 1e6, 1),
+            "encoder_s": round(t_enc, 4), "decode_s": round(t_dec, 4), "value_projection_s": round(t_reset, 4),
+            "us_per_token_step": round(t_rep / 50 * 1e6, 1), "launches_per_token_step": 6 * 16 + 6,
             "episodes_per_s": round(episodes / total, 2), "tokens_per_s": round(n * steps / t_dec, 1),
             "eager_loop": {"us_per_token_step": round(t_eager_tok * 1e6, 1),
                            "episodes_per_s": round(episodes / (t_enc + t_eager_tok * steps), 2),

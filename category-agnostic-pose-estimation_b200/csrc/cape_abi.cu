@@ -457,15 +457,17 @@ int cape_decode_attention(const float* q, int q_stride, const float* k_new, cons
 int cape_skinny_linear(const float* x, int x_stride, const float* x2, int x2_stride, const float* wt, const float* bias,
                        const float* residual, int residual_stride, const float* gamma, const float* beta, float eps,
                        const float* sine_dim_t, float* y, int y_stride, int rows, int K, int N, int epilogue, void* stream) {
-    if (rows < 0 || K <= 0 || N <= 0 || K % 16 != 0 || N % 4 != 0 || K > 4096)
-        return fail(CAPE_ERR_BAD_DIMS, "bad linear dimensions (rows=%d K=%d N=%d; K %% 16 == 0, K <= 4096, N %% 4 == 0)", rows, K, N);
+    if (rows < 0 || K <= 0 || N <= 0 || K % 16 != 0 || N % 4 != 0 || K > 2048)
+        return fail(CAPE_ERR_BAD_DIMS, "bad linear dimensions (rows=%d K=%d N=%d; K %% 16 == 0, K <= 2048, N %% 4 == 0)", rows, K, N);
     if (epilogue < 0 || epilogue > 2) return fail(CAPE_ERR_BAD_DIMS, "unknown epilogue %d", epilogue);
     if (epilogue == 2 && (N > 256 || !gamma || !beta))
         return fail(CAPE_ERR_BAD_DIMS, "the LayerNorm epilogue needs N <= 256 (got %d) and gamma / beta", N);
     if (sine_dim_t && K != 256) return fail(CAPE_ERR_BAD_DIMS, "the sine-embedding input has K = 256, got %d", K);
     int rc;
     const bool empty = rows == 0;
-    if ((rc = check_ptr(x, "x", empty, sine_dim_t ? 4 : 16)) || (rc = check_ptr(x2, "x2", true, 4)) ||
+    if (!sine_dim_t && (x_stride % 4 != 0 || (x2 && x2_stride % 4 != 0)))
+        return fail(CAPE_ERR_MISALIGNED, "row strides of x / x2 must be multiples of 4 elements (got %d, %d)", x_stride, x2_stride);
+    if ((rc = check_ptr(x, "x", empty, sine_dim_t ? 4 : 16)) || (rc = check_ptr(x2, "x2", true, 16)) ||
         (rc = check_ptr(wt, "wt", false)) || (rc = check_ptr(bias, "bias", true, 4)) ||
         (rc = check_ptr(residual, "residual", true, 4)) || (rc = check_ptr(gamma, "gamma", true, 4)) ||
         (rc = check_ptr(beta, "beta", true, 4)) || (rc = check_ptr(sine_dim_t, "sine_dim_t", true, 4)) ||
@@ -479,6 +481,49 @@ int cape_skinny_linear(const float* x, int x_stride, const float* x2, int x2_str
     a.eps = eps;
     const cudaError_t e = launch_skinny_linear(a, epilogue, static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? 0 : fail_cuda(e, "cape_skinny_linear launch");
+}
+
+int cape_skinny_linear_split(const float* x, int x_stride, const float* x2, int x2_stride, const float* wt,
+                             const float* bias, float* y, int y_stride, float* y2, int y2_stride, int split, int rows, int K,
+                             int N, void* stream) {
+    if (rows < 0 || K <= 0 || N <= 0 || K % 16 != 0 || N % 4 != 0 || K > 2048 || split <= 0 || split >= N)
+        return fail(CAPE_ERR_BAD_DIMS, "bad split-linear dimensions (rows=%d K=%d N=%d split=%d)", rows, K, N, split);
+    int rc;
+    const bool empty = rows == 0;
+    if (x_stride % 4 != 0 || (x2 && x2_stride % 4 != 0))
+        return fail(CAPE_ERR_MISALIGNED, "row strides of x / x2 must be multiples of 4 elements (got %d, %d)", x_stride, x2_stride);
+    if ((rc = check_ptr(x, "x", empty)) || (rc = check_ptr(x2, "x2", true, 16)) || (rc = check_ptr(wt, "wt", false)) ||
+        (rc = check_ptr(bias, "bias", true, 4)) || (rc = check_ptr(y, "y", empty, 4)) || (rc = check_ptr(y2, "y2", empty, 4)))
+        return rc;
+    SkinnyArgs a{};
+    a.x = x, a.x2 = x2, a.wt = wt, a.bias = bias, a.y = y, a.y2 = y2;
+    a.rows = rows, a.K = K, a.N = N;
+    a.x_stride = x_stride, a.x2_stride = x2_stride, a.y_stride = y_stride, a.y2_stride = y2_stride, a.split = split;
+    const cudaError_t e = launch_skinny_linear(a, 0, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? 0 : fail_cuda(e, "cape_skinny_linear_split launch");
+}
+
+int cape_coord_head_refine(const float* x, int x_stride, const float* wt, const float* bias, const float* w3, const float* b3,
+                           const float* ref_in, const float* valid_ratios, float* ref_out, float* ref_levels, int rows,
+                           int K, int N, int n_levels, void* stream) {
+    if (rows < 0 || K <= 0 || N <= 0 || K % 16 != 0 || N % 4 != 0 || K > 2048 || N > 256 || n_levels <= 0 || n_levels > 8)
+        return fail(CAPE_ERR_BAD_DIMS, "bad coordinate-head dimensions (rows=%d K=%d N=%d levels=%d; N <= 256)", rows, K, N,
+                    n_levels);
+    int rc;
+    const bool empty = rows == 0;
+    if (x_stride % 4 != 0) return fail(CAPE_ERR_MISALIGNED, "row stride of x must be a multiple of 4 elements (got %d)", x_stride);
+    if ((rc = check_ptr(x, "x", empty)) || (rc = check_ptr(wt, "wt", false)) || (rc = check_ptr(bias, "bias", true, 4)) ||
+        (rc = check_ptr(w3, "w3", false, 4)) || (rc = check_ptr(b3, "b3", false, 4)) ||
+        (rc = check_ptr(ref_in, "ref_in", empty, 4)) || (rc = check_ptr(valid_ratios, "valid_ratios", empty, 4)) ||
+        (rc = check_ptr(ref_out, "ref_out", empty, 4)) || (rc = check_ptr(ref_levels, "ref_levels", empty, 4)))
+        return rc;
+    SkinnyArgs a{};
+    a.x = x, a.wt = wt, a.bias = bias;
+    a.rows = rows, a.K = K, a.N = N, a.x_stride = x_stride;
+    a.w3 = w3, a.b3 = b3, a.ref_in = ref_in, a.valid_ratios = valid_ratios, a.ref_out = ref_out, a.ref_levels = ref_levels;
+    a.n_levels = n_levels;
+    const cudaError_t e = launch_skinny_linear(a, 3, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? 0 : fail_cuda(e, "cape_coord_head_refine launch");
 }
 
 int cape_tiny_linear(const float* x, int x_stride, const float* w, const float* bias, const float* refine_ref, float* y,

@@ -84,9 +84,18 @@ struct SkinnyArgs {
     const float* beta;
     const float* sine_dim_t;   // non-NULL: input = sine embedding of x with these 128 divisors (K must be 256)
     float* y;                  // (rows, N), row stride y_stride
+    float* y2;                 // optional second output: columns >= split go to y2[:, c - split] (row stride y2_stride)
     int rows, K, N;
-    int x_stride, x2_stride, res_stride, y_stride;
+    int x_stride, x2_stride, res_stride, y_stride, y2_stride, split;
     float eps;
+    // epilogue 3 (coordinate head + refinement)
+    const float* w3;           // (2, N)
+    const float* b3;           // (2)
+    const float* ref_in;       // (rows, 2)
+    const float* valid_ratios; // (rows, n_levels, 2)
+    float* ref_out;            // (rows, 2)
+    float* ref_levels;         // (rows, n_levels, 2)
+    int n_levels;
 };
 
 cudaError_t launch_decode_attention(const float* q, const float* k_new, const float* v_new, float* k_cache, float* v_cache,

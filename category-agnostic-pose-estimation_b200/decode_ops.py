@@ -76,6 +76,46 @@ def skinny_linear(x, wt, bias=None, *, x2=None, residual=None, gamma=None, beta=
     return y
 
 
+def skinny_linear_split(x, wt, bias, split: int, *, x2=None):
+    """(x [+ x2]) @ wt + bias with the output columns split over two tensors: returns (y[:, :split], y[:, split:]) as two
+    contiguous tensors (MSDeformAttn's offsets | logits projections in one launch)."""
+    lib = _lib.load()
+    x = _rows2d(x, "x")
+    rows = x.shape[0]
+    k, n = wt.shape
+    if x2 is not None:
+        x2 = _rows2d(x2, "x2")
+    y = torch.empty(rows, split, dtype=torch.float32, device=x.device)
+    y2 = torch.empty(rows, n - split, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = lib.cape_skinny_linear_split(_ptr(x), x.stride(0), _p(x2), 0 if x2 is None else x2.stride(0), _ptr(wt),
+                                          _p(bias), _ptr(y), split, _ptr(y2), n - split, split, rows, k, n,
+                                          _stream(x.device))
+    _lib.check(rc, "cape_skinny_linear_split")
+    return y, y2
+
+
+def coord_head_refine(x, wt, bias, w3, b3, ref, valid_ratios):
+    """Last two layers of the coordinate MLP + refinement: returns (ref' (rows, 2), ref' * valid_ratios (rows, L, 2)) for
+    h = relu(x @ wt + bias), ref' = sigmoid(h @ w3.T + b3 + inverse_sigmoid(ref))."""
+    lib = _lib.load()
+    x = _rows2d(x, "x")
+    rows = x.shape[0]
+    k, n = wt.shape
+    levels = valid_ratios.shape[1]
+    if tuple(ref.shape) != (rows, 2) or not ref.is_contiguous() or tuple(valid_ratios.shape) != (rows, levels, 2) \
+            or not valid_ratios.is_contiguous() or tuple(w3.shape) != (2, n) or not w3.is_contiguous():
+        raise ValueError("coord_head_refine: ref (rows, 2), valid_ratios (rows, L, 2), w3 (2, N), all contiguous")
+    ref_out = torch.empty(rows, 2, dtype=torch.float32, device=x.device)
+    ref_levels = torch.empty(rows, levels, 2, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = lib.cape_coord_head_refine(_ptr(x), x.stride(0), _ptr(wt), _p(bias), _ptr(w3), _ptr(b3), _ptr(ref),
+                                        _ptr(valid_ratios), _ptr(ref_out), _ptr(ref_levels), rows, k, n, levels,
+                                        _stream(x.device))
+    _lib.check(rc, "cape_coord_head_refine")
+    return ref_out, ref_levels
+
+
 def tiny_linear(x, w, bias=None, refine_ref=None):
     """y (rows, N <= 8) = x @ w.T + bias with ``w`` (N, K) as nn.Linear stores it; ``refine_ref`` (rows, N) turns the result
     into sigmoid(y + inverse_sigmoid(refine_ref))."""

@@ -368,8 +368,7 @@ class AutoregressiveGenerator(IncrementalDecoder):
                 "wt_o": t(sa.out_proj.weight), "b_o": sa.out_proj.bias, "n2": (layer.norm2.weight, layer.norm2.bias, layer.norm2.eps),
                 "wt_qs": t(base["wq_s"]), "b_qs": base["bq_s"], "wt_so": t(xa.out_proj.weight), "b_so": xa.out_proj.bias,
                 "ns": (layer.norm_support.weight, layer.norm_support.bias, layer.norm_support.eps),
-                "wt_off": t(ca.sampling_offsets.weight), "b_off": ca.sampling_offsets.bias,
-                "wt_log": t(ca.attention_weights.weight), "b_log": ca.attention_weights.bias,
+                "wt_ol": t(base["w_ol"]), "b_ol": base["b_ol"], "n_off": base["n_off"],
                 "wt_out": t(ca.output_proj.weight), "b_out": ca.output_proj.bias,
                 "n1": (layer.norm1.weight, layer.norm1.bias, layer.norm1.eps),
                 "wt_f1": t(layer.linear1.weight), "b_f1": layer.linear1.bias, "wt_f2": t(layer.linear2.weight),
@@ -384,7 +383,7 @@ class AutoregressiveGenerator(IncrementalDecoder):
                 "w_cls": dec.class_embed[-1].weight.detach().contiguous(), "b_cls": dec.class_embed[-1].bias}
 
     def _run_fused(self):
-        """One token through every decoder layer with the hand-written step kernels: 18 launches per layer, no library
+        """One token through every decoder layer with the hand-written step kernels: 16 launches per layer, no library
         GEMM / attention call.  Same arithmetic as :meth:`_run` (fp32 FMA; only the summation order differs)."""
         from . import decode_ops as K
         dec, st = self.transformer.decoder, self.state
@@ -394,6 +393,7 @@ class AutoregressiveGenerator(IncrementalDecoder):
         heads = self.layers[0].self_attn.num_heads
         x = dec._seq_embed(*st.seq, *st.delta).view(n, -1)                                     # (B, C)
         ref = self.ref_table.index_select(0, self.pos).expand(n, -1).contiguous()              # (B, 2), :1049-1050
+        ref_levels = (ref[:, None, :] * self.valid_ratios).contiguous()                        # (B, L, 2), :1072
         for lid, layer in enumerate(self.layers):
             w = fp["layers"][lid]
             ca = layer.cross_attn
@@ -413,11 +413,9 @@ class AutoregressiveGenerator(IncrementalDecoder):
                 g, b_, eps = w["ns"]
                 x = K.skinny_linear(xs, w["wt_so"], w["b_so"], residual=x, gamma=g, beta=b_, eps=eps)
             # MSDeformAttn on the cached projected value (:360-363)
-            offsets = K.skinny_linear(x, w["wt_off"], w["b_off"], x2=qpos)
-            logits = K.skinny_linear(x, w["wt_log"], w["b_log"], x2=qpos)
-            ref_input = (ref[:, None, None, :] * self.valid_ratios[:, None]).contiguous()      # (B, 1, L, 2), :1072
+            offsets, logits = K.skinny_linear_split(x, w["wt_ol"], w["b_ol"], w["n_off"], x2=qpos)   # :99-100
             sampled = torch.ops.cape.ms_deform_attn_decode(
-                self.values[lid], shapes, starts, ref_input,
+                self.values[lid], shapes, starts, ref_levels.view(n, 1, ca.n_levels, 2),
                 offsets.view(n, 1, ca.n_heads, ca.n_levels, ca.n_points, 2),
                 logits.view(n, 1, ca.n_heads, ca.n_levels * ca.n_points)).view(n, -1)
             g, b_, eps = w["n1"]
@@ -427,8 +425,7 @@ class AutoregressiveGenerator(IncrementalDecoder):
             x = K.skinny_linear(hidden, w["wt_f2"], w["b_f2"], residual=x, gamma=g, beta=b_, eps=eps)
             # iterative refinement of the reference point by this layer's coordinate head (:1096-1102)
             c = K.skinny_linear(x, w["wt_c1"], w["b_c1"], relu=True)
-            c = K.skinny_linear(c, w["wt_c2"], w["b_c2"], relu=True)
-            ref = K.tiny_linear(c, w["w_c3"], w["b_c3"], refine_ref=ref)
+            ref, ref_levels = K.coord_head_refine(c, w["wt_c2"], w["b_c2"], w["w_c3"], w["b_c3"], ref, self.valid_ratios)
         cls = K.tiny_linear(x, fp["w_cls"], fp["b_cls"])                                       # :1117-1121
         st.advance(cls, ref)
         return x

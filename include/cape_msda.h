@@ -230,7 +230,7 @@ CAPE_API int cape_token_step(const float* cls_logits, const float* reg, int64_t*
  *   Cross-attention form: pos_dev = k_new = v_new = NULL, all T cached keys are attended; key_bias (B, T) or NULL is
  *   added to the scores (-inf at padded keys).  T <= 1024.  out (B, H*32), before the output projection.
  *
- * cape_skinny_linear — y = epilogue(x W^T + b) for `rows` rows: wt (K, N) is the weight TRANSPOSED; K % 16 == 0, N % 4 == 0.
+ * cape_skinny_linear — y = epilogue(x W^T + b) for `rows` rows: wt (K, N) is the weight TRANSPOSED; K % 16 == 0, K <= 2048, N % 4 == 0.
  *   epilogue 0: bias; 1: bias + ReLU; 2: LayerNorm_N(residual + x W^T + b) * gamma + beta (N <= 256, residual may be NULL).
  *   x2 (optional) is added to x first (tgt + query_pos).  With sine_dim_t != NULL (128 divisors, K = 256) the input is
  *   the sine embedding of the (rows, 2) reference points in x (TransformerDecoder.get_query_pos_embed, :1005-1018).
@@ -246,6 +246,20 @@ CAPE_API int cape_skinny_linear(const float* x, int x_stride, const float* x2, i
                                 const float* bias, const float* residual, int residual_stride, const float* gamma,
                                 const float* beta, float eps, const float* sine_dim_t, float* y, int y_stride, int rows,
                                 int K, int N, int epilogue, void* stream);
+/*
+ * Two fusions of the decode step on top of cape_skinny_linear (same constraints on x / wt / K / N):
+ *   cape_skinny_linear_split — epilogue 0 with the output columns split over two tensors: columns < split go to y,
+ *     the rest to y2 (MSDeformAttn's sampling_offsets | attention_weights projections of one query, :99-100).
+ *   cape_coord_head_refine — the last two layers of the coordinate MLP and the iterative refinement in one launch:
+ *     h = relu(x wt + bias) (N <= 256), ref_out = sigmoid(h w3^T + b3 + inverse_sigmoid(ref_in)) with w3 (2, N), and
+ *     ref_levels[r, l, :] = ref_out[r, :] * valid_ratios[r, l, :] (deformable_transformer_v2.py:1072, 1096-1102).
+ */
+CAPE_API int cape_skinny_linear_split(const float* x, int x_stride, const float* x2, int x2_stride, const float* wt,
+                                      const float* bias, float* y, int y_stride, float* y2, int y2_stride, int split,
+                                      int rows, int K, int N, void* stream);
+CAPE_API int cape_coord_head_refine(const float* x, int x_stride, const float* wt, const float* bias, const float* w3,
+                                    const float* b3, const float* ref_in, const float* valid_ratios, float* ref_out,
+                                    float* ref_levels, int rows, int K, int N, int n_levels, void* stream);
 CAPE_API int cape_tiny_linear(const float* x, int x_stride, const float* w, const float* bias, const float* refine_ref,
                               float* y, int rows, int K, int N, void* stream);
 

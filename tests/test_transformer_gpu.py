@@ -299,3 +299,29 @@ def test_decode_attention_vs_multihead_attention_with_kv_cache():
         pos.fill_(t_max)                                                   # out-of-range position: a no-op, not a fault
         K.decode_attention(proj[:, :c], k_cache, v_cache, proj[:, c:2 * c], proj[:, 2 * c:], pos, n_heads=heads)
         torch.cuda.synchronize()
+
+
+def test_split_linear_and_coordinate_head_fusions_vs_torch():
+    from cape_b200 import decode_ops as K
+    from cape_b200.transformer import MLP, inverse_sigmoid
+    torch.manual_seed(3)
+    for rows in (1, 6, 128):
+        lin = torch.nn.Linear(256, 384).cuda()
+        x, x2 = torch.randn(rows, 256, device="cuda"), torch.randn(rows, 256, device="cuda")
+        with torch.no_grad():
+            want = lin(x + x2)
+            y, y2 = K.skinny_linear_split(x, lin.weight.t().contiguous(), lin.bias, 256, x2=x2)
+        assert y.shape == (rows, 256) and y2.shape == (rows, 128) and y.is_contiguous() and y2.is_contiguous()
+        assert rel_err(torch.cat([y, y2], 1).cpu(), want.cpu()) < FWD_TOL_F32
+        # coordinate MLP (roomformer_v2.py:956-968) layers 2 + 3, refinement (:1096-1102), per-level centres (:1072)
+        mlp = MLP(256, 256, 2, 3).cuda()
+        ref = torch.rand(rows, 2, device="cuda")
+        ref[0, 0] = 1.0
+        valid = torch.rand(rows, 4, 2, device="cuda") * 0.5 + 0.5
+        with torch.no_grad():
+            h1 = mlp.layers[0](x).relu()
+            want_ref = (mlp.layers[2](mlp.layers[1](h1).relu()) + inverse_sigmoid(ref)).sigmoid()
+            got_ref, got_levels = K.coord_head_refine(h1, mlp.layers[1].weight.t().contiguous(), mlp.layers[1].bias,
+                                                      mlp.layers[2].weight.contiguous(), mlp.layers[2].bias, ref, valid)
+        assert rel_err(got_ref.cpu(), want_ref.cpu()) < FWD_TOL_F32
+        assert rel_err(got_levels.cpu(), (want_ref[:, None, :] * valid).cpu()) < FWD_TOL_F32
