@@ -509,6 +509,20 @@ def generation(dev, episodes=64, keypoints=100):
     with torch.no_grad():
         t_enc, enc_cache = timed(lambda: tr.encode(feats, masks, pos))
         t_enc, enc_cache = timed(lambda: tr.encode(feats, masks, pos))
+    # opt-in 3xTF32 tensor-core linears for the encoder / value projections (fp32-level accuracy, cape_b200.gemm)
+    cape_b200.set_linear_mode("tf32x3")
+    try:
+        with torch.no_grad():
+            tr.encode(feats, masks, pos)
+            t_enc_tc, enc_tc = timed(lambda: tr.encode(feats, masks, pos))
+            enc_err = float((enc_tc["memory"] - enc_cache["memory"]).abs().max() / enc_cache["memory"].abs().max())
+            gen_tc = cape_b200.AutoregressiveGenerator(tr, spec, n, dev)
+            run_tc = lambda: gen_tc.generate(feats, masks, pos, query_embed, sup, sup_mask, enc_cache=enc_tc)
+            run_tc()
+            t_dec_tc, _ = timed(run_tc)
+        del gen_tc, enc_tc
+    finally:
+        cape_b200.set_linear_mode("fp32")
     gen = cape_b200.AutoregressiveGenerator(tr, spec, n, dev)
     run = lambda: gen.generate(feats, masks, pos, query_embed, sup, sup_mask, enc_cache=enc_cache)
     run()                                                    # captures the graph
@@ -528,6 +542,11 @@ def generation(dev, episodes=64, keypoints=100):
             "encoder_s": round(t_enc, 4), "decode_s": round(t_dec, 4), "value_projection_s": round(t_reset, 4),
             "us_per_token_step": round(t_rep / 50 * 1e6, 1), "launches_per_token_step": 6 * 16 + 6,
             "episodes_per_s": round(episodes / total, 2), "tokens_per_s": round(n * steps / t_dec, 1),
+            "tensor_core_linears": {"encoder_s": round(t_enc_tc, 4), "decode_s": round(t_dec_tc, 4),
+                                    "episodes_per_s": round(episodes / (t_enc_tc + t_dec_tc), 2),
+                                    "encoder_memory_rel_err_vs_fp32": float(f"{enc_err:.2e}"),
+                                    "note": "opt-in cape_b200.set_linear_mode('tf32x3'): tcgen05 3xTF32 GEMM for the encoder's "
+                                            "projections / FFN and the per-batch value projection"},
             "eager_loop": {"us_per_token_step": round(t_eager_tok * 1e6, 1),
                            "episodes_per_s": round(episodes / (t_enc + t_eager_tok * steps), 2),
                            "note": f"mirror transformer.forward per token with KV + value caches, extrapolated from {few} tokens"},

@@ -540,6 +540,29 @@ int cape_tiny_linear(const float* x, int x_stride, const float* w, const float* 
     return e == cudaSuccess ? 0 : fail_cuda(e, "cape_tiny_linear launch");
 }
 
+// ---- fp32-accurate tensor-core linear ----------------------------------------------------------------------------
+
+int cape_tf32_split_lo(const float* x, float* lo, int64_t n, void* stream) {
+    if (n < 0) return fail(CAPE_ERR_BAD_DIMS, "negative element count");
+    int rc;
+    if ((rc = check_ptr(x, "x", n == 0, 4)) || (rc = check_ptr(lo, "lo", n == 0, 4))) return rc;
+    const cudaError_t e = launch_tf32_split_lo(x, lo, n, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? 0 : fail_cuda(e, "cape_tf32_split_lo launch");
+}
+
+int cape_linear_tf32x3(const float* x, const float* w, const float* w_lo, const float* bias, float* y, int M, int N, int K,
+                       int act, void* stream) {
+    if (M < 0 || N <= 0 || K <= 0 || K % 32 != 0 || N % 128 != 0 || act < 0 || act > 1)
+        return fail(CAPE_ERR_BAD_DIMS, "bad linear dimensions (M=%d N=%d K=%d act=%d; K %% 32 == 0, N %% 128 == 0)", M, N, K, act);
+    int rc;
+    const bool empty = M == 0;
+    if ((rc = check_ptr(x, "x", empty)) || (rc = check_ptr(w, "w", false)) || (rc = check_ptr(w_lo, "w_lo", false)) ||
+        (rc = check_ptr(bias, "bias", true)) || (rc = check_ptr(y, "y", empty)))
+        return rc;
+    const cudaError_t e = launch_linear_tf32x3(x, w, w_lo, bias, y, M, N, K, act, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? 0 : fail_cuda(e, "cape_linear_tf32x3 launch");
+}
+
 // ---- host-buffer round trip ------------------------------------------------------------------------------------
 
 namespace {

@@ -1,0 +1,88 @@
+"""fp32-accurate linear layers on the tensor cores (``csrc/linear_tf32x3.cu``: tcgen05.mma.kind::tf32 fed by TMA, every
+operand used as hi + lo, three products accumulated in fp32 in tensor memory).
+
+The reference runs the projections around the sampling op (``value_proj`` / ``output_proj`` / ``sampling_offsets`` /
+``attention_weights`` of MSDeformAttn, the encoder FFN; ``/root/reference/models/deformable_transformer.py:95-113,219-224``)
+as strict-fp32 ``nn.Linear``, which cuBLAS serves with SIMT kernels on B200.  ``linear()`` is what the mirrors call
+instead of ``module(x)``: by default it IS ``module(x)`` (bit-for-bit the reference's arithmetic); after
+``set_linear_mode("tf32x3")`` inference calls (no autograd) with supported shapes (K % 32 == 0, N % 128 == 0, fp32, CUDA)
+go through the 3xTF32 kernel — max error about 2e-6 of the output scale at K = 256 (cuBLAS fp32: 5e-7), 3.3x faster.
+Training keeps cuBLAS (the kernel has no backward).
+"""
+from __future__ import annotations
+
+import ctypes
+import weakref
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from .ops import _ptr, _stream
+
+_MODE = "fp32"
+_LO_CACHE: dict = {}
+
+
+def set_linear_mode(mode: str) -> str:
+    """"fp32" (default: plain nn.Linear) or "tf32x3" (3xTF32 tensor-core kernel for inference).  Returns the old mode."""
+    global _MODE
+    if mode not in ("fp32", "tf32x3"):
+        raise ValueError(f"unknown linear mode {mode!r}")
+    old, _MODE = _MODE, mode
+    return old
+
+
+def linear_mode() -> str:
+    return _MODE
+
+
+def _weight_lo(weight: torch.Tensor) -> torch.Tensor:
+    """lo part of a weight (cached per tensor object and version; recomputed after an in-place update)."""
+    key = id(weight)
+    hit = _LO_CACHE.get(key)
+    if hit is not None and hit[0]() is weight and hit[1] == weight._version and hit[2] == weight.data_ptr():
+        return hit[3]
+    lib = _lib.load()
+    w = weight.detach()
+    lo = torch.empty_like(w)
+    with torch.cuda.device(w.device):
+        _lib.check(lib.cape_tf32_split_lo(_ptr(w), _ptr(lo), w.numel(), _stream(w.device)), "cape_tf32_split_lo")
+    if len(_LO_CACHE) > 512:
+        _LO_CACHE.clear()
+    _LO_CACHE[key] = (weakref.ref(weight), weight._version, weight.data_ptr(), lo)
+    return lo
+
+
+def supported(x: torch.Tensor, weight: torch.Tensor) -> bool:
+    n, k = weight.shape
+    return (x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32 and weight.is_contiguous()
+            and k % 32 == 0 and n % 128 == 0 and x.shape[-1] == k and x.numel() > 0)
+
+
+def linear_tf32x3(x: torch.Tensor, weight: torch.Tensor, bias=None, relu: bool = False) -> torch.Tensor:
+    """act(x @ weight.T + bias) through the 3xTF32 kernel.  x (..., K) fp32 CUDA; weight (N, K) contiguous."""
+    if not supported(x, weight):
+        raise ValueError(f"linear_tf32x3: unsupported operands x {tuple(x.shape)} {x.dtype}, weight {tuple(weight.shape)}")
+    lib = _lib.load()
+    n, k = weight.shape
+    x2 = x.detach().reshape(-1, k)
+    if not x2.is_contiguous() or x2.data_ptr() % 16 != 0:
+        x2 = x2.contiguous()
+    w = weight.detach()
+    y = torch.empty(x2.shape[0], n, dtype=torch.float32, device=x.device)
+    b = None if bias is None else bias.detach().contiguous()
+    with torch.cuda.device(x.device):
+        rc = lib.cape_linear_tf32x3(_ptr(x2), _ptr(w), _ptr(_weight_lo(weight)), None if b is None else _ptr(b), _ptr(y),
+                                    x2.shape[0], n, k, 1 if relu else 0, _stream(x.device))
+    _lib.check(rc, "cape_linear_tf32x3")
+    return y.view(*x.shape[:-1], n)
+
+
+def linear(module: torch.nn.Linear, x: torch.Tensor, relu: bool = False) -> torch.Tensor:
+    """``module(x)`` (optionally followed by ReLU), routed to the tensor-core kernel when the mode allows it."""
+    if _MODE == "tf32x3" and not torch.is_grad_enabled() and supported(x, module.weight) \
+            and x.numel() // x.shape[-1] >= 128:
+        return linear_tf32x3(x, module.weight, module.bias, relu)
+    y = module(x)
+    return F.relu(y) if relu else y

@@ -20,6 +20,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from .gemm import linear as _linear
 from .modules import MSDeformAttn, ValueCache
 
 
@@ -77,8 +78,11 @@ class DeformableTransformerEncoderLayer(nn.Module):
         return tensor if pos is None else tensor + pos
 
     def forward_ffn(self, src):
-        hidden = self.dropout2(self.activation(self.linear1(src)))
-        return self.norm2(src + self.dropout3(self.linear2(hidden)))
+        if self.activation is F.relu:
+            hidden = self.dropout2(_linear(self.linear1, src, relu=True))     # ReLU in the GEMM epilogue when routed
+        else:
+            hidden = self.dropout2(self.activation(self.linear1(src)))
+        return self.norm2(src + self.dropout3(_linear(self.linear2, hidden)))
 
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None):
         attn = self.self_attn(self.with_pos_embed(src, pos), reference_points, src, spatial_shapes, level_start_index,
@@ -267,7 +271,7 @@ class IncrementalDecoder:
             self.graph = None
         for layer, dst in zip(self.layers, self.values):
             ca = layer.cross_attn
-            v = ca.value_proj(memory)
+            v = _linear(ca.value_proj, memory)
             if padding_mask is not None:
                 v = v.masked_fill(padding_mask[..., None], 0.0)
             dst.copy_(v.view(dst.shape))

@@ -25,6 +25,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import functional as CF
+from .gemm import linear as _linear
 
 
 def _is_power_of_2(n) -> bool:
@@ -123,15 +124,15 @@ class MSDeformAttn(nn.Module):
         if bool(use_cache) and not torch.is_grad_enabled():
             value = self._cache_load(N, Len_in)
         if value is None:
-            value = self.value_proj(input_flatten)                                          # :95
+            value = _linear(self.value_proj, input_flatten)                                 # :95
             if input_padding_mask is not None:
                 value = value.masked_fill(input_padding_mask[..., None], float(0))          # :96-97
             value = value.view(N, Len_in, self.n_heads, self.d_model // self.n_heads)       # :98
             if not torch.is_grad_enabled():
                 self._cache_store(value)
-        sampling_offsets = self.sampling_offsets(query).view(
+        sampling_offsets = _linear(self.sampling_offsets, query).view(
             N, Len_q, self.n_heads, self.n_levels, self.n_points, 2)                        # :99
-        attention_logits = self.attention_weights(query).view(
+        attention_logits = _linear(self.attention_weights, query).view(
             N, Len_q, self.n_heads, self.n_levels * self.n_points)                          # :100
         if reference_points.shape[-1] not in (2, 4):                                        # :109-111
             raise ValueError("Last dim of reference_points must be 2 or 4, but get {} instead.".format(
@@ -140,7 +141,7 @@ class MSDeformAttn(nn.Module):
             # softmax (:100-101) and ref + off / (W_l, H_l) (:102-105) run inside the sampling kernel, forward and backward
             output = CF.ms_deform_attn_fused(value, input_spatial_shapes, input_level_start_index, reference_points,
                                              sampling_offsets, attention_logits)
-            return self.output_proj(output)
+            return _linear(self.output_proj, output)
         attention_weights = F.softmax(attention_logits, -1).view(
             N, Len_q, self.n_heads, self.n_levels, self.n_points)                           # :101
         if reference_points.shape[-1] == 2:                                                 # :102-105
@@ -152,4 +153,4 @@ class MSDeformAttn(nn.Module):
                 + sampling_offsets / self.n_points * reference_points[:, :, None, :, None, 2:] * 0.5
         output = CF.ms_deform_attn(value, input_spatial_shapes, input_level_start_index, sampling_locations,
                                    attention_weights)                                       # :112
-        return self.output_proj(output)                                                     # :113
+        return _linear(self.output_proj, output)                                                     # :113

@@ -264,6 +264,18 @@ CAPE_API int cape_tiny_linear(const float* x, int x_stride, const float* w, cons
                               float* y, int rows, int K, int N, void* stream);
 
 /*
+ * fp32-accurate linear layer on the tensor cores ("3xTF32", tcgen05.mma.kind::tf32 with TMA-fed operands) for the
+ * projections around the sampling op (value_proj / output_proj / FFN, models/deformable_transformer.py:95,113,219-224):
+ *     y (M, N) = act(x (M, K) . w (N, K)^T + bias)        act: 0 none, 1 ReLU
+ * with every operand used as hi + lo (hi = the 19 bits kind::tf32 reads, lo = the exact remainder) and
+ * x_lo w_hi + x_hi w_lo + x_hi w_hi accumulated in fp32.  w_lo (N, K) comes from cape_tf32_split_lo(w) once per weight;
+ * x_lo is produced inside the kernel.  x, w, w_lo, y row-major fp32, 16-byte aligned; K % 32 == 0, N % 128 == 0.
+ */
+CAPE_API int cape_tf32_split_lo(const float* x, float* lo, int64_t n, void* stream);
+CAPE_API int cape_linear_tf32x3(const float* x, const float* w, const float* w_lo, const float* bias, float* y, int M, int N,
+                                int K, int act, void* stream);
+
+/*
  * Host-buffer round trip used for end-to-end measurement and for callers without device buffers:
  * copies the inputs from (ideally pinned) HOST memory into the caller-provided device workspace, runs forward and,
  * when grad_out_host != NULL, backward, and copies the results back to HOST memory — all enqueued on `stream`.

@@ -576,6 +576,34 @@ def test_encoder_stack_mirror_matches_reference():
     assert rel_err(gx.cpu().numpy(), g["grad_src"]) < GRAD_TOL_F32
 
 
+def test_encoder_stack_with_tensor_core_linears_stays_at_fp32_level():
+    """CAPE-width encoder (d_model 256, FFN 1024, 2 layers) at inference through the opt-in 3xTF32 linears vs the same
+    stack on nn.Linear: the sampling op is unchanged, the 12 projections each carry ~2e-6 instead of ~5e-7."""
+    enc = cape_b200.DeformableTransformerEncoder(
+        cape_b200.DeformableTransformerEncoderLayer(256, 1024, 0.0, "relu", 4, 8, 4), 2)
+    synthetic.fill_parameters_(enc, seed=5)
+    enc = enc.cuda().eval()
+    shapes = ((16, 12), (8, 6), (4, 3), (2, 2))
+    s = sum(h * w for h, w in shapes)
+    n = 3
+    src = torch.from_numpy(synthetic.seeded_array("src", (n, s, 256), 5)).cuda()
+    pos = torch.from_numpy(synthetic.seeded_array("pos", (n, s, 256), 5)).cuda() * 0.5
+    args = (src, torch.tensor(shapes, device="cuda"), torch.tensor(synthetic.level_start_index(shapes), device="cuda"),
+            torch.ones(n, 4, 2, device="cuda"), pos)
+    with torch.no_grad():
+        want = enc(*args)
+        old = cape_b200.set_linear_mode("tf32x3")
+        try:
+            enc(*args)                                  # first call also splits the 12 weights (cached afterwards)
+            before = cape_b200.launch_count()
+            out = enc(*args)
+            launches = cape_b200.launch_count() - before
+        finally:
+            cape_b200.set_linear_mode(old)
+    assert launches == 2 * (1 + 6)                      # per layer: the sampling kernel + 6 tensor-core linears
+    assert rel_err(out.cpu().numpy(), want.cpu().numpy()) < 2e-5
+
+
 def test_decoder_layer_mirror_teacher_forced_and_incremental():
     """TransformerDecoderLayer v1 (deformable_transformer_v2.py:262-370): teacher-forced forward/backward, then the same
     sequence token by token with KV cache + projected-value cache, then one decode step replayed from a CUDA graph."""

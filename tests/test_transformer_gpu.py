@@ -325,3 +325,58 @@ def test_split_linear_and_coordinate_head_fusions_vs_torch():
                                                       mlp.layers[2].weight.contiguous(), mlp.layers[2].bias, ref, valid)
         assert rel_err(got_ref.cpu(), want_ref.cpu()) < FWD_TOL_F32
         assert rel_err(got_levels.cpu(), (want_ref[:, None, :] * valid).cpu()) < FWD_TOL_F32
+
+
+# ---- 3xTF32 tensor-core linear (csrc/linear_tf32x3.cu) ---------------------------------------------------------------
+@pytest.mark.parametrize("m,n,k", [(128, 128, 32), (1, 128, 64), (300, 256, 256), (4099, 1024, 256), (1000, 256, 1024),
+                                    (129, 384, 96)])
+def test_linear_tf32x3_matches_fp64_at_fp32_level(m, n, k):
+    """The hi/lo split keeps the tensor-core GEMM at fp32-level accuracy: both it and cuBLAS' fp32 kernel are compared
+    with an fp64 product; plain TF32 (one pass) would be off by ~1e-3."""
+    gen = torch.Generator().manual_seed(m + n + k)
+    x = torch.randn(m, k, generator=gen).cuda()
+    w = (torch.randn(n, k, generator=gen) / k ** 0.5).cuda()
+    b = torch.randn(n, generator=gen).cuda()
+    ref = x.double() @ w.double().t() + b.double()
+    got = cape_b200.linear_tf32x3(x, w, b)
+    assert got.shape == (m, n) and not torch.isnan(got).any()
+    err = rel_err(got.cpu(), ref.cpu())
+    err_fp32 = rel_err(torch.nn.functional.linear(x, w, b).cpu(), ref.cpu())
+    assert err < 1e-5 and err < 12 * max(err_fp32, 1e-7), (err, err_fp32)
+    relu = cape_b200.linear_tf32x3(x.view(1, m, k), w, None, relu=True)            # leading dims, no bias, fused ReLU
+    assert relu.shape == (1, m, n)
+    assert rel_err(relu.cpu(), (x.double() @ w.double().t()).clamp_min(0).cpu()[None]) < 1e-5
+
+
+def test_linear_mode_routes_inference_only_and_tracks_weight_updates():
+    lin = torch.nn.Linear(256, 256).cuda()
+    x = torch.randn(4, 200, 256, device="cuda")
+    old = cape_b200.set_linear_mode("tf32x3")
+    try:
+        from cape_b200 import gemm
+        before = cape_b200.launch_count()
+        y_train = gemm.linear(lin, x)                                    # autograd on: stays nn.Linear
+        assert y_train.requires_grad and cape_b200.launch_count() == before
+        with torch.no_grad():
+            y = gemm.linear(lin, x)
+            assert cape_b200.launch_count() > before
+            assert rel_err(y.cpu(), y_train.detach().cpu()) < 1e-5
+            lin.weight.mul_(2.0)                                         # in-place update: the cached lo part must follow
+            y2 = gemm.linear(lin, x)
+            assert rel_err(y2.cpu(), lin(x).cpu()) < 1e-5
+            small = gemm.linear(lin, x[:1, :3])                          # tiny inputs stay on nn.Linear
+            assert torch.equal(small, lin(x[:1, :3]))
+    finally:
+        cape_b200.set_linear_mode(old)
+    assert cape_b200.linear_mode() == old
+
+
+def test_generation_with_tensor_core_linears_produces_the_reference_tokens(fx):
+    g, tr, spec = fx["g"], fx["tr"], fx["spec"]
+    old = cape_b200.set_linear_mode("tf32x3")
+    try:
+        gen = cape_b200.AutoregressiveGenerator(tr, spec, max_batch_size=2, device="cuda")
+        out = gen.generate(fx["feats"], fx["masks"], fx["pos"], fx["query_embed"], fx["sup"], fx["sup_mask"])
+    finally:
+        cape_b200.set_linear_mode(old)
+    _check_generation(out, g, "gen")
