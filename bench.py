@@ -506,15 +506,16 @@ def generation(dev, episodes=64, keypoints=100):
         torch.cuda.synchronize(dev)
         return time.perf_counter() - t0, out
 
+    torch.cuda.empty_cache()
     with torch.no_grad():
-        t_enc, enc_cache = timed(lambda: tr.encode(feats, masks, pos))
-        t_enc, enc_cache = timed(lambda: tr.encode(feats, masks, pos))
+        tr.encode(feats, masks, pos)
+        t_enc, enc_cache = min((timed(lambda: tr.encode(feats, masks, pos)) for _ in range(3)), key=lambda r: r[0])
     # opt-in 3xTF32 tensor-core linears for the encoder / value projections (fp32-level accuracy, cape_b200.gemm)
     cape_b200.set_linear_mode("tf32x3")
     try:
         with torch.no_grad():
             tr.encode(feats, masks, pos)
-            t_enc_tc, enc_tc = timed(lambda: tr.encode(feats, masks, pos))
+            t_enc_tc, enc_tc = min((timed(lambda: tr.encode(feats, masks, pos)) for _ in range(3)), key=lambda r: r[0])
             enc_err = float((enc_tc["memory"] - enc_cache["memory"]).abs().max() / enc_cache["memory"].abs().max())
             gen_tc = cape_b200.AutoregressiveGenerator(tr, spec, n, dev)
             run_tc = lambda: gen_tc.generate(feats, masks, pos, query_embed, sup, sup_mask, enc_cache=enc_tc)

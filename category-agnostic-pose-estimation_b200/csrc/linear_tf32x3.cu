@@ -7,13 +7,14 @@
 //
 //   * operands: x (M, K) and W (N, K), both K-major, row-major fp32, K % 32 == 0, N % 128 == 0; W_lo is prepared once per
 //     weight (cape_tf32_split_lo); x_lo is produced inside the kernel from the x tile the TMA already brought in;
-//   * CTA tile 128 x 128, K step 32 (one 128-byte swizzle atom per row), 3-stage TMA -> smem pipeline;
-//   * 6 warps: warp 0 = TMA producer (one elected lane), warp 1 = tensor-memory allocator + MMA issuer (one elected lane),
-//     warps 2..5 = x_lo converters during the main loop (element-wise on the swizzled tile: same offsets in, same offsets
-//     out, so the swizzle never has to be undone), then the epilogue (tcgen05.ld of their 32-lane quarter, bias,
-//     activation, 128-byte row segments to global);
+//   * persistent: one CTA per SM walks 128 x 128 output tiles; K step 32 (one 128-byte swizzle atom per row), 3-stage
+//     TMA -> smem pipeline; two accumulators in tensor memory so a tile's epilogue overlaps the next tile's main loop;
+//   * 10 warps: warp 0 = TMA producer (one elected lane), warp 1 = tensor-memory allocator + MMA issuer (one elected
+//     lane), warps 2..5 = x_lo converters (element-wise on the swizzled tile: same offsets in, same offsets out, so the
+//     swizzle never has to be undone), warps 6..9 = epilogue (tcgen05.ld of their 32-lane quarter, bias, activation,
+//     swizzled staging in shared memory, TMA tensor store — per-thread row stores would cost 32 LSU wavefronts each);
 //   * mbarriers: full (TMA bytes landed), conv (x_lo written and fenced for the async proxy), empty (tcgen05.commit: the
-//     MMAs that read the stage are done), tmem_full (accumulator complete).
+//     MMAs that read the stage are done), tmem_full / tmem_empty (accumulator complete / drained).
 #include <cuda.h>
 
 #include <mutex>
@@ -28,13 +29,16 @@ namespace {
 constexpr int kBM = 128, kBN = 128, kBK = 32, kStages = 3;
 constexpr int kTileBytes = kBM * kBK * 4;                 // 16 KB: one operand tile (128 rows x 128 B)
 constexpr int kStageBytes = 4 * kTileBytes;               // x, x_lo, W_hi, W_lo
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;          // TMA warp, MMA warp, 4 converter warps, 4 epilogue warps
 #ifndef CAPE_TF32_LOLO
 #define CAPE_TF32_LOLO 0
 #endif
 constexpr bool kLoLo = CAPE_TF32_LOLO != 0;    // also accumulate x_lo w_lo (a 4th MMA per k-step)
 constexpr int kConvThreads = 128;
-constexpr size_t kGemmSmem = static_cast<size_t>(kStages) * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
+constexpr int kEpiThreads = 128;
+constexpr int kStoreTile = 32 * 32 * 4;                   // epilogue staging: 32 rows x 32 columns per warp and step
+constexpr size_t kGemmSmem = static_cast<size_t>(kStages) * kStageBytes + 1024 /* alignment slack */ + 1024 /* barriers */ +
+                             4 * 2 * kStoreTile /* 4 epilogue warps x 2 buffers */;
 
 // lo part of an fp32 number for the hi/lo split: the exact remainder x - trunc19(x) (<= 13 significant bits), rounded
 // to nearest tf32 — the tensor core would otherwise truncate it, and a truncation bias adds up coherently over K.
@@ -104,20 +108,23 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 template <int ACT>   // 0 none, 1 ReLU
 __global__ void __launch_bounds__(kGemmThreads, 1)
 linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_wh,
-                     const __grid_constant__ CUtensorMap map_wl, const float* __restrict__ bias, float* __restrict__ y,
-                     int M, int N, int K) {
+                     const __grid_constant__ CUtensorMap map_wl, const __grid_constant__ CUtensorMap map_y,
+                     const float* __restrict__ bias, int M, int N, int K) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // swizzle atoms need 1024-byte alignment
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
-    const uint32_t bars = base + kStages * kStageBytes;                    // full[3], conv[3], empty[3], tmem_full, tmem ptr
+    // barriers: full[S], conv[S], empty[S], tmem_full[2], tmem_empty[2]; then the tensor-memory base address
+    const uint32_t bars = base + kStages * kStageBytes;
     const auto full = [&](int s) { return bars + 8u * s; };
     const auto conv = [&](int s) { return bars + 8u * (kStages + s); };
     const auto empty = [&](int s) { return bars + 8u * (2 * kStages + s); };
-    const uint32_t tmem_full = bars + 8u * (3 * kStages);
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + kStages * kStageBytes + 8 * (3 * kStages + 1));
+    const auto tmem_full = [&](int b) { return bars + 8u * (3 * kStages + b); };
+    const auto tmem_empty = [&](int b) { return bars + 8u * (3 * kStages + 2 + b); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + kStages * kStageBytes + 8 * (3 * kStages + 4));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * kBN;
     const int k_blocks = K / kBK;
+    const int n_tiles = N / kBN;
+    const int tiles = n_tiles * ((M + kBM - 1) / kBM);                     // persistent: tile t = blockIdx.x, += gridDim.x
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -125,116 +132,149 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             mbar_init(conv(s), kConvThreads);
             mbar_init(empty(s), 1);
         }
-        mbar_init(tmem_full, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(tmem_full(b), 1);
+            mbar_init(tmem_empty(b), kEpiThreads);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {   // 128 columns of tensor memory: the 128 x 128 fp32 accumulator
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(const_cast<uint32_t*>(tmem_slot))), "n"(kBN) : "memory");
+    if (warp == 1) {   // 2 x 128 columns of tensor memory: two 128 x 128 fp32 accumulators (mainloop / epilogue overlap)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(const_cast<uint32_t*>(tmem_slot))), "n"(2 * kBN) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_acc = *tmem_slot;
+    const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         if (lane == 0) {   // ===== TMA producer =====
-            for (int kb = 0; kb < k_blocks; ++kb) {
-                const int s = kb % kStages;
-                mbar_wait(empty(s), ((kb / kStages) & 1) ^ 1);
-                const uint32_t st = base + s * kStageBytes;
-                mbar_arrive_expect_tx(full(s), 3 * kTileBytes);
-                tma_load_2d(st, &map_x, full(s), kb * kBK, m0);
-                tma_load_2d(st + 2 * kTileBytes, &map_wh, full(s), kb * kBK, n0);
-                tma_load_2d(st + 3 * kTileBytes, &map_wl, full(s), kb * kBK, n0);
+            int it = 0;
+            for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+                const int m0 = (t / n_tiles) * kBM, n0 = (t % n_tiles) * kBN;
+                for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+                    const int s = it % kStages;
+                    mbar_wait(empty(s), ((it / kStages) & 1) ^ 1);
+                    const uint32_t st = base + s * kStageBytes;
+                    mbar_arrive_expect_tx(full(s), 3 * kTileBytes);
+                    tma_load_2d(st, &map_x, full(s), kb * kBK, m0);
+                    tma_load_2d(st + 2 * kTileBytes, &map_wh, full(s), kb * kBK, n0);
+                    tma_load_2d(st + 3 * kTileBytes, &map_wl, full(s), kb * kBK, n0);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {   // ===== MMA issuer =====
-            for (int kb = 0; kb < k_blocks; ++kb) {
-                const int s = kb % kStages;
-                const uint32_t parity = (kb / kStages) & 1;
-                mbar_wait(full(s), parity);
-                mbar_wait(conv(s), parity);
+            int it = 0, j = 0;
+            for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++j) {
+                const int ab = j & 1;
+                mbar_wait(tmem_empty(ab), ((j >> 1) & 1) ^ 1);            // the epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t st = base + s * kStageBytes;
-                const uint64_t d_x = umma_desc(st), d_xlo = umma_desc(st + kTileBytes);
-                const uint64_t d_wh = umma_desc(st + 2 * kTileBytes), d_wl = umma_desc(st + 3 * kTileBytes);
+                const uint32_t tmem_acc = tmem_base + ab * kBN;
+                for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+                    const int s = it % kStages;
+                    const uint32_t parity = (it / kStages) & 1;
+                    mbar_wait(full(s), parity);
+                    mbar_wait(conv(s), parity);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t st = base + s * kStageBytes;
+                    const uint64_t d_x = umma_desc(st), d_xlo = umma_desc(st + kTileBytes);
+                    const uint64_t d_wh = umma_desc(st + 2 * kTileBytes), d_wl = umma_desc(st + 3 * kTileBytes);
 #pragma unroll
-                for (int k = 0; k < kBK / 8; ++k) {   // UMMA_K = 8 for tf32: 32 bytes along K -> +2 in the address field
-                    const uint64_t adv = static_cast<uint64_t>(k * 2);
-                    if (kLoLo) {
-                        umma_tf32(tmem_acc, d_xlo + adv, d_wl + adv, (kb | k) != 0);
-                        umma_tf32(tmem_acc, d_xlo + adv, d_wh + adv, 1);
-                    } else {
+                    for (int k = 0; k < kBK / 8; ++k) {   // UMMA_K = 8 for tf32: 32 bytes along K -> +2 in the address field
+                        const uint64_t adv = static_cast<uint64_t>(k * 2);
                         umma_tf32(tmem_acc, d_xlo + adv, d_wh + adv, (kb | k) != 0);
+                        umma_tf32(tmem_acc, d_x + adv, d_wl + adv, 1);
+                        umma_tf32(tmem_acc, d_x + adv, d_wh + adv, 1);
                     }
-                    umma_tf32(tmem_acc, d_x + adv, d_wl + adv, 1);
-                    umma_tf32(tmem_acc, d_x + adv, d_wh + adv, 1);
+                    umma_commit(empty(s));                  // the stage may be refilled once these MMAs have read it
                 }
-                umma_commit(empty(s));                  // the stage may be refilled once these MMAs have read it
+                umma_commit(tmem_full(ab));
             }
-            umma_commit(tmem_full);
+        }
+    } else if (warp < 2 + kConvThreads / 32) {
+        // ===== x_lo converters: element-wise on the swizzled tile (same offsets in and out) =====
+        const int ct = threadIdx.x - 64;               // 0..127
+        int it = 0;
+        for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+            for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+                const int s = it % kStages;
+                mbar_wait(full(s), (it / kStages) & 1);
+                const float4* src = reinterpret_cast<const float4*>(base_ptr + s * kStageBytes);
+                float4* dst = reinterpret_cast<float4*>(base_ptr + s * kStageBytes + kTileBytes);
+#pragma unroll
+                for (int i = 0; i < kTileBytes / 16 / kConvThreads; ++i) {
+                    const float4 v = src[i * kConvThreads + ct];
+                    float4 r;
+                    r.x = tf32_lo(v.x);
+                    r.y = tf32_lo(v.y);
+                    r.z = tf32_lo(v.z);
+                    r.w = tf32_lo(v.w);
+                    dst[i * kConvThreads + ct] = r;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
+                mbar_arrive(conv(s));
+            }
         }
     } else {
-        // ===== x_lo converters (main loop) =====
-        const int ct = threadIdx.x - 64;               // 0..127
-        for (int kb = 0; kb < k_blocks; ++kb) {
-            const int s = kb % kStages;
-            mbar_wait(full(s), (kb / kStages) & 1);
-            const float4* src = reinterpret_cast<const float4*>(base_ptr + s * kStageBytes);
-            float4* dst = reinterpret_cast<float4*>(base_ptr + s * kStageBytes + kTileBytes);
-#pragma unroll
-            for (int i = 0; i < kTileBytes / 16 / kConvThreads; ++i) {
-                const float4 v = src[i * kConvThreads + ct];
-                float4 r;
-                r.x = tf32_lo(v.x);
-                r.y = tf32_lo(v.y);
-                r.z = tf32_lo(v.z);
-                r.w = tf32_lo(v.w);
-                dst[i * kConvThreads + ct] = r;
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
-            mbar_arrive(conv(s));
-        }
         // ===== epilogue: warp w owns tensor-memory lanes 32 (w % 4) .. +31 =====
-        mbar_wait(tmem_full, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int quarter = warp & 3;
-        const int row = m0 + quarter * 32 + lane;
+        int j = 0;
+        for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++j) {
+            const int m0 = (t / n_tiles) * kBM, n0 = (t % n_tiles) * kBN;
+            const int ab = j & 1;
+            mbar_wait(tmem_full(ab), (j >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            // staging buffers of this warp (1024-aligned, 128-byte swizzle like the TMA store expects)
+            uint8_t* stage_ptr = base_ptr + kStages * kStageBytes + 1024 + (warp - 6) * 2 * kStoreTile;
 #pragma unroll 1
-        for (int c = 0; c < kBN / 32; ++c) {
-            uint32_t r[32];
-            const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16) + c * 32;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-                  "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-                  "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (row < M) {
-                float* dst = y + static_cast<int64_t>(row) * N + n0 + c * 32;
+            for (int c = 0; c < kBN / 32; ++c) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + ab * kBN + (static_cast<uint32_t>(quarter * 32) << 16) + c * 32;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                      "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                      "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                      "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                // the buffer used two steps ago must have been read by its TMA store
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                __syncwarp();
+                uint8_t* buf = stage_ptr + (c & 1) * kStoreTile;
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
+                for (int jj = 0; jj < 32; jj += 4) {
                     float4 o;
-                    o.x = __uint_as_float(r[j]), o.y = __uint_as_float(r[j + 1]);
-                    o.z = __uint_as_float(r[j + 2]), o.w = __uint_as_float(r[j + 3]);
+                    o.x = __uint_as_float(r[jj]), o.y = __uint_as_float(r[jj + 1]);
+                    o.z = __uint_as_float(r[jj + 2]), o.w = __uint_as_float(r[jj + 3]);
                     if (bias) {
-                        const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + n0 + c * 32 + j));
+                        const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + n0 + c * 32 + jj));
                         o.x += bv.x, o.y += bv.y, o.z += bv.z, o.w += bv.w;
                     }
                     if (ACT == 1) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
-                    *reinterpret_cast<float4*>(dst + j) = o;
+                    // row = lane (128 B), 16-byte chunk jj / 4, swizzled with the row's low 3 bits: conflict-free STS.128
+                    *reinterpret_cast<float4*>(buf + lane * 128 + (((jj >> 2) ^ (lane & 7)) << 4)) = o;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {   // rows past M are clipped by the tensor map
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                 ::"l"(reinterpret_cast<uint64_t>(&map_y)), "r"(smem_u32(buf)), "r"(n0 + c * 32),
+                                   "r"(m0 + quarter * 32)
+                                 : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(tmem_empty(ab));                   // this accumulator may be overwritten by the next-but-one tile
         }
     }
+    if (warp >= 6 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before exit
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "n"(kBN) : "memory");
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * kBN) : "memory");
 }
 
 // lo part of an fp32 tensor for the kernel above: x - (x with the 13 low mantissa bits cleared), exact in fp32.
@@ -261,13 +301,14 @@ EncodeTiledFn encode_tiled() {
     return fn;
 }
 
-// (rows, K) row-major fp32 -> boxes of 128 rows x 32 columns, 128-byte swizzle; out-of-range rows read as zeros.
-bool make_map(CUtensorMap* map, const float* ptr, int rows, int K) {
+// (rows, K) row-major fp32 -> boxes of box_rows rows x 32 columns, 128-byte swizzle; out-of-range rows read as zeros /
+// are not written.
+bool make_map(CUtensorMap* map, const float* ptr, int rows, int K, int box_rows = kBM) {
     EncodeTiledFn fn = encode_tiled();
     if (!fn) return false;
     const cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
     const cuuint64_t strides[1] = {static_cast<cuuint64_t>(K) * sizeof(float)};
-    const cuuint32_t box[2] = {kBK, kBM};
+    const cuuint32_t box[2] = {kBK, static_cast<cuuint32_t>(box_rows)};
     const cuuint32_t elem[2] = {1, 1};
     return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, elem,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -288,19 +329,23 @@ cudaError_t launch_tf32_split_lo(const float* x, float* lo, int64_t n, cudaStrea
 cudaError_t launch_linear_tf32x3(const float* x, const float* w, const float* w_lo, const float* bias, float* y, int M, int N,
                                  int K, int act, cudaStream_t stream) {
     if (M == 0) return cudaSuccess;
-    CUtensorMap map_x, map_wh, map_wl;
-    if (!make_map(&map_x, x, M, K) || !make_map(&map_wh, w, N, K) || !make_map(&map_wl, w_lo, N, K))
+    CUtensorMap map_x, map_wh, map_wl, map_y;
+    if (!make_map(&map_x, x, M, K) || !make_map(&map_wh, w, N, K) || !make_map(&map_wl, w_lo, N, K) ||
+        !make_map(&map_y, y, M, N, 32))
         return cudaErrorNotSupported;
     static std::once_flag once;
     std::call_once(once, [] {
         cudaFuncSetAttribute(linear_tf32x3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmem));
         cudaFuncSetAttribute(linear_tf32x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmem));
     });
-    const dim3 grid(N / kBN, (M + kBM - 1) / kBM);
+    const int tiles = (N / kBN) * ((M + kBM - 1) / kBM);
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const dim3 grid(tiles < sms ? tiles : sms);          // persistent: one CTA per SM walks the tiles
     if (act == 1)
-        linear_tf32x3_kernel<1><<<grid, kGemmThreads, kGemmSmem, stream>>>(map_x, map_wh, map_wl, bias, y, M, N, K);
+        linear_tf32x3_kernel<1><<<grid, kGemmThreads, kGemmSmem, stream>>>(map_x, map_wh, map_wl, map_y, bias, M, N, K);
     else
-        linear_tf32x3_kernel<0><<<grid, kGemmThreads, kGemmSmem, stream>>>(map_x, map_wh, map_wl, bias, y, M, N, K);
+        linear_tf32x3_kernel<0><<<grid, kGemmThreads, kGemmSmem, stream>>>(map_x, map_wh, map_wl, map_y, bias, M, N, K);
     count_launch();
     return cudaGetLastError();
 }
