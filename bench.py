@@ -209,7 +209,7 @@ def run_reference(args, rank, world):
 
 
 # ---- data-parallel training step of the deformable transformer (all N; BASELINE.json configs[2] and [4]) ---------
-def train_step(dev, rank, world, accumulation=4, steps=2, amp=False):
+def train_step(dev, rank, world, accumulation=4, steps=2, amp=False, linear_mode="fp32"):
     """One optimizer step of the CAPE transformer body on every rank: 6 deformable encoder layers (Lq = S = 5440) +
     6 decoder layers v1 (teacher-forced, 200 tokens, 17 support keypoints), micro-batch of 10 episodes x 2 queries
     (N = 20), gradient accumulation 4, ONE flat-bucket gradient all-reduce over NCCL (dist.FlatGradAllreduce), clip 0.1,
@@ -218,6 +218,7 @@ def train_step(dev, rank, world, accumulation=4, steps=2, amp=False):
     import torch
     import cape_b200
     from cape_b200 import dist as cdist
+    cape_b200.set_linear_mode(linear_mode)
     torch.manual_seed(1234)                       # same weights on every rank
     kw = dict(d_model=256, d_ffn=1024, dropout=0.1, activation="relu", n_levels=4, n_heads=8, n_points=4)
     enc = cape_b200.DeformableTransformerEncoder(cape_b200.DeformableTransformerEncoderLayer(**kw), 6).to(dev)
@@ -259,8 +260,9 @@ def train_step(dev, rank, world, accumulation=4, steps=2, amp=False):
         scaler.update()
         opt.zero_grad(set_to_none=True)
 
+    optimizer_step()                               # warm-up (cuBLAS heuristics, allocator, cached weight splits)
     launches0 = cape_b200.launch_count()
-    optimizer_step()                               # warm-up (cuBLAS heuristics, allocator)
+    optimizer_step()
     per_step_launches = cape_b200.launch_count() - launches0
     cdist.barrier(dev)
     torch.cuda.synchronize(dev)
@@ -274,12 +276,14 @@ def train_step(dev, rank, world, accumulation=4, steps=2, amp=False):
     episodes = world * accumulation * (n // 2)
     n_params = sum(p.numel() for p in params)
     del enc, dec, opt, allreduce
+    cape_b200.set_linear_mode("fp32")
     torch.cuda.empty_cache()
     return {"episodes_per_s": round(episodes / (ms * 1e-3), 2), "ms_per_optimizer_step": round(ms, 2),
             "episodes_per_step": episodes, "accumulation": accumulation, "allreduce_mb": round(n_params * 4 / 2 ** 20, 1),
             "msda_launches_per_step": int(per_step_launches),
             "dtype": "fp16 autocast + GradScaler (the reference's --use_amp); MSDeformAttn value fp16, accumulation fp32"
-            if amp else "f32 (TF32 off)",
+            if amp else ("f32; opt-in tcgen05 3xTF32 linears for the MSDeformAttn projections and FFNs (forward + input "
+                         "gradient; weight gradient cuBLAS fp32)" if linear_mode == "tf32x3" else "f32 (TF32 off)"),
             "scope": "6 encoder + 6 decoder (v1) layers of the deformable transformer, fwd + bwd + NCCL all-reduce + "
                      "AdamW; synthetic features; no backbone / support encoder / heads"}
 
@@ -695,6 +699,14 @@ def run_b200(args, rank, world, local_rank):
             train_amp = train_step(dev, rank, world, amp=True)
         except Exception as exc:                                   # noqa: BLE001 - every rank must keep going
             train_amp = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+    train_tc = None
+    if not args.no_extras:
+        try:   # two invocations: the first one after a mode switch has measured 310-430 ms, repeats are steady at ~310
+            first = train_step(dev, rank, world, linear_mode="tf32x3")
+            train_tc = train_step(dev, rank, world, linear_mode="tf32x3")
+            train_tc["ms_per_optimizer_step_runs"] = [first["ms_per_optimizer_step"], train_tc["ms_per_optimizer_step"]]
+        except Exception as exc:                                   # noqa: BLE001 - every rank must keep going
+            train_tc = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     if rank != 0:
         return
     peak, peak_src = measured_peak()
@@ -725,6 +737,8 @@ def run_b200(args, rank, world, local_rank):
         line["train_step"] = train
     if train_amp is not None:
         line["train_step_amp"] = train_amp
+    if train_tc is not None:
+        line["train_step_tensor_core_linears"] = train_tc
     if world == 1 and not args.no_extras:
         line["sweep"] = guarded(op_sweep, lib, dev)
         line["module"] = guarded(module_step, dev)

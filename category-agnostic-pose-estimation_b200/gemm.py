@@ -6,8 +6,8 @@ The reference runs the projections around the sampling op (``value_proj`` / ``ou
 as strict-fp32 ``nn.Linear``, which cuBLAS serves with SIMT kernels on B200.  ``linear()`` is what the mirrors call
 instead of ``module(x)``: by default it IS ``module(x)`` (bit-for-bit the reference's arithmetic); after
 ``set_linear_mode("tf32x3")`` inference calls (no autograd) with supported shapes (K % 32 == 0, N % 128 == 0, fp32, CUDA)
-go through the 3xTF32 kernel — max error about 2e-6 of the output scale at K = 256 (cuBLAS fp32: 5e-7), 3.3x faster.
-Training keeps cuBLAS (the kernel has no backward).
+go through the 3xTF32 kernel — max error about 2e-6 of the output scale at K = 256 (cuBLAS fp32: 5e-7), ~5x faster.
+With autograd on, forward and the input gradient use the kernel and the weight gradient stays cuBLAS.
 """
 from __future__ import annotations
 
@@ -79,10 +79,56 @@ def linear_tf32x3(x: torch.Tensor, weight: torch.Tensor, bias=None, relu: bool =
     return y.view(*x.shape[:-1], n)
 
 
+_WT_CACHE: dict = {}
+
+
+def _weight_t(weight: torch.Tensor) -> torch.Tensor:
+    """W^T (K, N) contiguous, cached per tensor version: the operand of the input-gradient GEMM g . W."""
+    key = id(weight)
+    hit = _WT_CACHE.get(key)
+    if hit is not None and hit[0]() is weight and hit[1] == weight._version and hit[2] == weight.data_ptr():
+        return hit[3]
+    wt = weight.detach().t().contiguous()
+    if len(_WT_CACHE) > 512:
+        _WT_CACHE.clear()
+    _WT_CACHE[key] = (weakref.ref(weight), weight._version, weight.data_ptr(), wt)
+    return wt
+
+
+class _LinearTF32x3(torch.autograd.Function):
+    """Training form: forward and the input gradient (g . W, the same K-major GEMM with W^T as the weight) run on the
+    3xTF32 kernel; the weight gradient g^T . x reduces over the rows, which the kernel does not split — it stays cuBLAS."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return linear_tf32x3(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, weight = ctx.saved_tensors
+        g = grad_out.contiguous()
+        grad_x = grad_w = grad_b = None
+        if ctx.needs_input_grad[0]:
+            wt = _weight_t(weight)
+            if supported(g, wt):
+                grad_x = linear_tf32x3(g, wt, None)
+            else:
+                grad_x = g.matmul(weight)
+        if ctx.needs_input_grad[1]:
+            grad_w = g.reshape(-1, g.shape[-1]).t().matmul(x.reshape(-1, x.shape[-1]))
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            grad_b = g.reshape(-1, g.shape[-1]).sum(0)
+        return grad_x, grad_w, grad_b
+
+
 def linear(module: torch.nn.Linear, x: torch.Tensor, relu: bool = False) -> torch.Tensor:
     """``module(x)`` (optionally followed by ReLU), routed to the tensor-core kernel when the mode allows it."""
-    if _MODE == "tf32x3" and not torch.is_grad_enabled() and supported(x, module.weight) \
-            and x.numel() // x.shape[-1] >= 128:
-        return linear_tf32x3(x, module.weight, module.bias, relu)
+    if _MODE == "tf32x3" and supported(x, module.weight) and x.numel() // x.shape[-1] >= 128:
+        if not torch.is_grad_enabled():
+            return linear_tf32x3(x, module.weight, module.bias, relu)
+        y = _LinearTF32x3.apply(x, module.weight, module.bias)
+        return F.relu(y) if relu else y
     y = module(x)
     return F.relu(y) if relu else y

@@ -183,8 +183,11 @@ class TransformerDecoderLayer(nn.Module):
         return tensor if pos is None else tensor + pos[:, :tensor.size(1)]
 
     def forward_ffn(self, tgt):
-        hidden = self.dropout3(self.activation(self.linear1(tgt)))
-        return self.norm3(tgt + self.dropout4(self.linear2(hidden)))
+        if self.activation is F.relu:
+            hidden = self.dropout3(_linear(self.linear1, tgt, relu=True))
+        else:
+            hidden = self.dropout3(self.activation(self.linear1(tgt)))
+        return self.norm3(tgt + self.dropout4(_linear(self.linear2, hidden)))
 
     def forward(self, tgt, query_pos, reference_points, src, src_spatial_shapes, level_start_index,
                 src_padding_mask=None, tgt_masks=None, attn_concat_src=False, input_pos=None, support_features=None,

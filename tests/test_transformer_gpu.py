@@ -355,8 +355,15 @@ def test_linear_mode_routes_inference_only_and_tracks_weight_updates():
     try:
         from cape_b200 import gemm
         before = cape_b200.launch_count()
-        y_train = gemm.linear(lin, x)                                    # autograd on: stays nn.Linear
-        assert y_train.requires_grad and cape_b200.launch_count() == before
+        xg = x.clone().requires_grad_(True)
+        y_train = gemm.linear(lin, xg)                                   # autograd on: kernel forward + input gradient
+        assert y_train.requires_grad and cape_b200.launch_count() > before
+        gout = torch.randn_like(y_train)
+        gx, gw, gb = torch.autograd.grad(y_train, (xg, lin.weight, lin.bias), gout)
+        xr = x.clone().requires_grad_(True)
+        rx, rw, rb = torch.autograd.grad(lin(xr), (xr, lin.weight, lin.bias), gout)
+        assert rel_err(gx.cpu(), rx.cpu()) < 1e-5 and rel_err(gw.cpu(), rw.cpu()) < 1e-5 and rel_err(gb.cpu(), rb.cpu()) < 1e-5
+        before = cape_b200.launch_count()
         with torch.no_grad():
             y = gemm.linear(lin, x)
             assert cape_b200.launch_count() > before
