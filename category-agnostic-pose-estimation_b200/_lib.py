@@ -72,6 +72,7 @@ _SIGNATURES = {
     "cape_tiny_linear": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "cape_tf32_split_lo": (_i, [_vp, _vp, ctypes.c_int64, _vp]),
     "cape_linear_tf32x3": (_i, [_vp] * 5 + [_i] * 4 + [_vp]),
+    "cape_linear_tf32x3_wgrad": (_i, [_vp] * 4 + [_i] * 3 + [_vp]),
     "cape_msda_host_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(Dims), _i]),
     "cape_msda_forward_backward_host": (_i, [_vp] * 10 + [ctypes.POINTER(Dims), _vp, ctypes.c_size_t, _vp]),
 }

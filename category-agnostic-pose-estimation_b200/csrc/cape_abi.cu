@@ -559,8 +559,29 @@ int cape_linear_tf32x3(const float* x, const float* w, const float* w_lo, const 
     if ((rc = check_ptr(x, "x", empty)) || (rc = check_ptr(w, "w", false)) || (rc = check_ptr(w_lo, "w_lo", false)) ||
         (rc = check_ptr(bias, "bias", true)) || (rc = check_ptr(y, "y", empty)))
         return rc;
-    const cudaError_t e = launch_linear_tf32x3(x, w, w_lo, bias, y, M, N, K, act, static_cast<cudaStream_t>(stream));
+    const cudaError_t e = launch_linear_tf32x3(x, w, w_lo, bias, y, M, N, K, act, 0, static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? 0 : fail_cuda(e, "cape_linear_tf32x3 launch");
+}
+
+int cape_linear_tf32x3_wgrad(const float* grad_out, const float* x, float* grad_w, float* workspace, int rows, int N, int K,
+                             void* stream) {
+    if (rows <= 0 || N <= 0 || K <= 0 || rows % 32 != 0 || N % 32 != 0 || K % 128 != 0)
+        return fail(CAPE_ERR_BAD_DIMS, "bad weight-gradient dimensions (rows=%d N=%d K=%d; rows %% 32 == 0, K %% 128 == 0)", rows, N, K);
+    int rc;
+    if ((rc = check_ptr(grad_out, "grad_out", false)) || (rc = check_ptr(x, "x", false)) || (rc = check_ptr(grad_w, "grad_w", false)) ||
+        (rc = check_ptr(workspace, "workspace", false)))
+        return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // workspace: g^T (N, rows) | x^T (K, rows) | lo(x^T) (K, rows)
+    float* gt = workspace;
+    float* xt = gt + static_cast<size_t>(N) * rows;
+    float* xt_lo = xt + static_cast<size_t>(K) * rows;
+    cudaError_t e;
+    if ((e = launch_transpose_lo(grad_out, gt, nullptr, rows, N, s)) != cudaSuccess) return fail_cuda(e, "transpose(grad_out)");
+    if ((e = launch_transpose_lo(x, xt, xt_lo, rows, K, s)) != cudaSuccess) return fail_cuda(e, "transpose(x)");
+    // grad_w (N, K) = g^T (N, rows) . (x^T (K, rows))^T : the same K-major GEMM with the row index as the reduction dimension
+    e = launch_linear_tf32x3(gt, xt, xt_lo, nullptr, grad_w, N, K, rows, 0, 1, s);
+    return e == cudaSuccess ? 0 : fail_cuda(e, "cape_linear_tf32x3_wgrad launch");
 }
 
 // ---- host-buffer round trip ------------------------------------------------------------------------------------

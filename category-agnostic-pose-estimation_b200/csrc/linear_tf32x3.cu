@@ -109,7 +109,7 @@ template <int ACT>   // 0 none, 1 ReLU
 __global__ void __launch_bounds__(kGemmThreads, 1)
 linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_wh,
                      const __grid_constant__ CUtensorMap map_wl, const __grid_constant__ CUtensorMap map_y,
-                     const float* __restrict__ bias, int M, int N, int K) {
+                     const float* __restrict__ bias, int M, int N, int K, int splits) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // swizzle atoms need 1024-byte alignment
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -122,9 +122,19 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     const auto tmem_empty = [&](int b) { return bars + 8u * (3 * kStages + 2 + b); };
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + kStages * kStageBytes + 8 * (3 * kStages + 4));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int k_blocks = K / kBK;
+    // Work item t = (output tile, K split): with splits > 1 (weight gradients: tiny output, reduction over all rows)
+    // every item covers a slice of the reduction dimension and the epilogue ADDS its partial tile to y (TMA reduce).
+    const int k_blocks_all = K / kBK;
+    const int kb_per = (k_blocks_all + splits - 1) / splits;
     const int n_tiles = N / kBN;
-    const int tiles = n_tiles * ((M + kBM - 1) / kBM);                     // persistent: tile t = blockIdx.x, += gridDim.x
+    const int tiles = n_tiles * ((M + kBM - 1) / kBM) * splits;            // persistent: item t = blockIdx.x, += gridDim.x
+    const auto item = [&](int t, int& m0, int& n0, int& kb0, int& kb1) {
+        const int sp = t % splits, tile = t / splits;
+        m0 = (tile / n_tiles) * kBM;
+        n0 = (tile % n_tiles) * kBN;
+        kb0 = sp * kb_per;
+        kb1 = min(k_blocks_all, kb0 + kb_per);
+    };
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -151,8 +161,9 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         if (lane == 0) {   // ===== TMA producer =====
             int it = 0;
             for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
-                const int m0 = (t / n_tiles) * kBM, n0 = (t % n_tiles) * kBN;
-                for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+                int m0, n0, kb0, kb1;
+                item(t, m0, n0, kb0, kb1);
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const int s = it % kStages;
                     mbar_wait(empty(s), ((it / kStages) & 1) ^ 1);
                     const uint32_t st = base + s * kStageBytes;
@@ -171,7 +182,9 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 mbar_wait(tmem_empty(ab), ((j >> 1) & 1) ^ 1);            // the epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t tmem_acc = tmem_base + ab * kBN;
-                for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+                int m0, n0, kb0, kb1;
+                item(t, m0, n0, kb0, kb1);
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const int s = it % kStages;
                     const uint32_t parity = (it / kStages) & 1;
                     mbar_wait(full(s), parity);
@@ -183,7 +196,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
 #pragma unroll
                     for (int k = 0; k < kBK / 8; ++k) {   // UMMA_K = 8 for tf32: 32 bytes along K -> +2 in the address field
                         const uint64_t adv = static_cast<uint64_t>(k * 2);
-                        umma_tf32(tmem_acc, d_xlo + adv, d_wh + adv, (kb | k) != 0);
+                        umma_tf32(tmem_acc, d_xlo + adv, d_wh + adv, (kb != kb0) | (k != 0));
                         umma_tf32(tmem_acc, d_x + adv, d_wl + adv, 1);
                         umma_tf32(tmem_acc, d_x + adv, d_wh + adv, 1);
                     }
@@ -197,7 +210,9 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         const int ct = threadIdx.x - 64;               // 0..127
         int it = 0;
         for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
-            for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+            int m0, n0, kb0, kb1;
+            item(t, m0, n0, kb0, kb1);
+            for (int kb = kb0; kb < kb1; ++kb, ++it) {
                 const int s = it % kStages;
                 mbar_wait(full(s), (it / kStages) & 1);
                 const float4* src = reinterpret_cast<const float4*>(base_ptr + s * kStageBytes);
@@ -221,7 +236,8 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         const int quarter = warp & 3;
         int j = 0;
         for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++j) {
-            const int m0 = (t / n_tiles) * kBM, n0 = (t % n_tiles) * kBN;
+            int m0, n0, kb0, kb1;
+            item(t, m0, n0, kb0, kb1);
             const int ab = j & 1;
             mbar_wait(tmem_full(ab), (j >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -260,10 +276,16 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) {   // rows past M are clipped by the tensor map
-                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                                 ::"l"(reinterpret_cast<uint64_t>(&map_y)), "r"(smem_u32(buf)), "r"(n0 + c * 32),
-                                   "r"(m0 + quarter * 32)
-                                 : "memory");
+                    if (splits > 1)
+                        asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                                     ::"l"(reinterpret_cast<uint64_t>(&map_y)), "r"(smem_u32(buf)), "r"(n0 + c * 32),
+                                       "r"(m0 + quarter * 32)
+                                     : "memory");
+                    else
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                     ::"l"(reinterpret_cast<uint64_t>(&map_y)), "r"(smem_u32(buf)), "r"(n0 + c * 32),
+                                       "r"(m0 + quarter * 32)
+                                     : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
@@ -282,6 +304,30 @@ __global__ void tf32_split_lo_kernel(const float* __restrict__ x, float* __restr
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i < n) {
         lo[i] = tf32_lo(x[i]);
+    }
+}
+
+// out[c][r] = in[r][c] for a row-major (R, C) matrix, optionally also the tf32 lo part of the transposed matrix: the
+// operands of the weight-gradient GEMM g^T . x are the activations with the ROW index as the contiguous (reduction) one.
+__global__ void __launch_bounds__(256)
+transpose_lo_kernel(const float* __restrict__ in, float* __restrict__ out, float* __restrict__ out_lo, int R, int C) {
+    __shared__ float tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+        const int r = r0 + ty + i, c = c0 + tx;
+        tile[ty + i][tx] = (r < R && c < C) ? in[static_cast<int64_t>(r) * C + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+        const int c = c0 + ty + i, r = r0 + tx;
+        if (c < C && r < R) {
+            const float v = tile[tx][ty + i];
+            out[static_cast<int64_t>(c) * R + r] = v;
+            if (out_lo) out_lo[static_cast<int64_t>(c) * R + r] = tf32_lo(v);
+        }
     }
 }
 
@@ -326,8 +372,17 @@ cudaError_t launch_tf32_split_lo(const float* x, float* lo, int64_t n, cudaStrea
     return cudaGetLastError();
 }
 
+cudaError_t launch_transpose_lo(const float* in, float* out, float* out_lo, int R, int C, cudaStream_t stream) {
+    if (R == 0 || C == 0) return cudaSuccess;
+    const dim3 grid((C + 31) / 32, (R + 31) / 32);
+    if (grid.y > 65535) return cudaErrorInvalidConfiguration;
+    transpose_lo_kernel<<<grid, 256, 0, stream>>>(in, out, out_lo, R, C);
+    count_launch();
+    return cudaGetLastError();
+}
+
 cudaError_t launch_linear_tf32x3(const float* x, const float* w, const float* w_lo, const float* bias, float* y, int M, int N,
-                                 int K, int act, cudaStream_t stream) {
+                                 int K, int act, int split_k, cudaStream_t stream) {
     if (M == 0) return cudaSuccess;
     CUtensorMap map_x, map_wh, map_wl, map_y;
     if (!make_map(&map_x, x, M, K) || !make_map(&map_wh, w, N, K) || !make_map(&map_wl, w_lo, N, K) ||
@@ -338,14 +393,36 @@ cudaError_t launch_linear_tf32x3(const float* x, const float* w, const float* w_
         cudaFuncSetAttribute(linear_tf32x3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmem));
         cudaFuncSetAttribute(linear_tf32x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmem));
     });
-    const int tiles = (N / kBN) * ((M + kBM - 1) / kBM);
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const dim3 grid(tiles < sms ? tiles : sms);          // persistent: one CTA per SM walks the tiles
+    const int out_tiles = (N / kBN) * ((M + kBM - 1) / kBM);
+    // split the reduction dimension when the output alone cannot fill the machine (split_k: 0 = never, 1 = automatic);
+    // partial tiles are added into y by the TMA, so y is zero-filled first and there is no bias / activation
+    // A slice is at most kMaxChain K-blocks long: the tensor core's fp32 accumulation is not round-to-nearest, and over a
+    // reduction of 10^5 rows (weight gradients) one accumulator chain drifts to ~8e-5; 1024-element chains whose partial
+    // tiles are added in L2 (round-to-nearest) stay at the forward's ~5e-6.
+    constexpr int kMaxChain = 32;
+    int splits = 1;
+    if (split_k) {
+        const int k_blocks = K / kBK;
+        splits = out_tiles < sms ? sms / out_tiles : 1;
+        if (splits * kMaxChain < k_blocks) splits = (k_blocks + kMaxChain - 1) / kMaxChain;
+        if (splits > k_blocks) splits = k_blocks;
+        if (splits < 1) splits = 1;
+        const int per = (k_blocks + splits - 1) / splits;
+        splits = (k_blocks + per - 1) / per;             // no empty slice
+    }
+    if (splits > 1) {
+        if (bias || act) return cudaErrorInvalidValue;
+        const cudaError_t e = cudaMemsetAsync(y, 0, static_cast<size_t>(M) * N * sizeof(float), stream);
+        if (e != cudaSuccess) return e;
+    }
+    const int tiles = out_tiles * splits;
+    const dim3 grid(tiles < sms ? tiles : sms);          // persistent: one CTA per SM walks the work items
     if (act == 1)
-        linear_tf32x3_kernel<1><<<grid, kGemmThreads, kGemmSmem, stream>>>(map_x, map_wh, map_wl, map_y, bias, M, N, K);
+        linear_tf32x3_kernel<1><<<grid, kGemmThreads, kGemmSmem, stream>>>(map_x, map_wh, map_wl, map_y, bias, M, N, K, splits);
     else
-        linear_tf32x3_kernel<0><<<grid, kGemmThreads, kGemmSmem, stream>>>(map_x, map_wh, map_wl, map_y, bias, M, N, K);
+        linear_tf32x3_kernel<0><<<grid, kGemmThreads, kGemmSmem, stream>>>(map_x, map_wh, map_wl, map_y, bias, M, N, K, splits);
     count_launch();
     return cudaGetLastError();
 }

@@ -106,7 +106,8 @@ cudaError_t launch_tiny_linear(const float* x, int x_stride, const float* w, con
                                float* y, int rows, int K, int N, cudaStream_t stream);
 cudaError_t launch_tf32_split_lo(const float* x, float* lo, int64_t n, cudaStream_t stream);
 cudaError_t launch_linear_tf32x3(const float* x, const float* w, const float* w_lo, const float* bias, float* y, int M, int N,
-                                 int K, int act, cudaStream_t stream);
+                                 int K, int act, int split_k, cudaStream_t stream);
+cudaError_t launch_transpose_lo(const float* in, float* out, float* out_lo, int R, int C, cudaStream_t stream);
 cudaError_t launch_seq_embed_forward(const SeqEmbedArgs& a, cudaStream_t stream);
 cudaError_t launch_seq_embed_backward(const SeqEmbedArgs& a, cudaStream_t stream);
 cudaError_t launch_token_step(const float* cls_logits, const float* reg, int64_t* step_dev, const cape_token_state& st,

@@ -95,9 +95,30 @@ def _weight_t(weight: torch.Tensor) -> torch.Tensor:
     return wt
 
 
+def wgrad_supported(g2: torch.Tensor, x2: torch.Tensor) -> bool:
+    rows, n = g2.shape
+    k = x2.shape[1]
+    return (g2.is_cuda and g2.dtype == torch.float32 and x2.dtype == torch.float32 and rows % 32 == 0 and rows >= 1024
+            and n % 128 == 0 and k % 128 == 0)
+
+
+def linear_tf32x3_wgrad(grad_out: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """grad_w (N, K) = grad_out (rows, N)^T @ x (rows, K) through the 3xTF32 kernel (split over the SMs along the rows)."""
+    lib = _lib.load()
+    g2, x2 = grad_out.detach().contiguous(), x.detach().contiguous()
+    rows, n = g2.shape
+    k = x2.shape[1]
+    grad_w = torch.empty(n, k, dtype=torch.float32, device=g2.device)
+    workspace = torch.empty((n + 2 * k) * rows, dtype=torch.float32, device=g2.device)
+    with torch.cuda.device(g2.device):
+        rc = lib.cape_linear_tf32x3_wgrad(_ptr(g2), _ptr(x2), _ptr(grad_w), _ptr(workspace), rows, n, k, _stream(g2.device))
+    _lib.check(rc, "cape_linear_tf32x3_wgrad")
+    return grad_w
+
+
 class _LinearTF32x3(torch.autograd.Function):
-    """Training form: forward and the input gradient (g . W, the same K-major GEMM with W^T as the weight) run on the
-    3xTF32 kernel; the weight gradient g^T . x reduces over the rows, which the kernel does not split — it stays cuBLAS."""
+    """Training form: forward, the input gradient (g . W, the same K-major GEMM with W^T as the weight) and the weight
+    gradient (g^T . x on transposed operands, reduction split over the SMs) all run on the 3xTF32 kernel."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):
@@ -117,7 +138,11 @@ class _LinearTF32x3(torch.autograd.Function):
             else:
                 grad_x = g.matmul(weight)
         if ctx.needs_input_grad[1]:
-            grad_w = g.reshape(-1, g.shape[-1]).t().matmul(x.reshape(-1, x.shape[-1]))
+            g2, x2 = g.reshape(-1, g.shape[-1]), x.reshape(-1, x.shape[-1])
+            if wgrad_supported(g2, x2):
+                grad_w = linear_tf32x3_wgrad(g2, x2)
+            else:
+                grad_w = g2.t().matmul(x2)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             grad_b = g.reshape(-1, g.shape[-1]).sum(0)
         return grad_x, grad_w, grad_b

@@ -274,6 +274,14 @@ CAPE_API int cape_tiny_linear(const float* x, int x_stride, const float* w, cons
 CAPE_API int cape_tf32_split_lo(const float* x, float* lo, int64_t n, void* stream);
 CAPE_API int cape_linear_tf32x3(const float* x, const float* w, const float* w_lo, const float* bias, float* y, int M, int N,
                                 int K, int act, void* stream);
+/*
+ * Weight gradient of that layer, grad_w (N, K) = grad_out (rows, N)^T . x (rows, K), on the same kernel: the operands are
+ * transposed into `workspace` ((N + 2 K) * rows floats: grad_out^T, x^T and the lo part of x^T) so that the row index is the
+ * contiguous reduction dimension, the reduction is split over the SMs and the partial tiles are added into grad_w by the
+ * TMA (cp.reduce.async.bulk.tensor ... add); grad_w is zero-filled by the call.  rows % 32 == 0, N % 32 == 0, K % 128 == 0.
+ */
+CAPE_API int cape_linear_tf32x3_wgrad(const float* grad_out, const float* x, float* grad_w, float* workspace, int rows, int N,
+                                      int K, void* stream);
 
 /*
  * Host-buffer round trip used for end-to-end measurement and for callers without device buffers:

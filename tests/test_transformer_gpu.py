@@ -387,3 +387,34 @@ def test_generation_with_tensor_core_linears_produces_the_reference_tokens(fx):
     finally:
         cape_b200.set_linear_mode(old)
     _check_generation(out, g, "gen")
+
+
+@pytest.mark.parametrize("rows,n,k", [(4096, 256, 256), (2048, 1024, 256), (20 * 5440, 256, 1024), (1024, 128, 256)])
+def test_linear_tf32x3_weight_gradient_split_over_the_rows(rows, n, k):
+    """grad_w = g^T x on the 3xTF32 kernel (transposed operands, reduction split over the SMs, partial tiles added by the
+    TMA) against an fp64 product; cuBLAS fp32 is measured on the same inputs for scale."""
+    from cape_b200 import gemm
+    gen = torch.Generator().manual_seed(rows + n + k)
+    g = torch.randn(rows, n, generator=gen).cuda()
+    x = torch.randn(rows, k, generator=gen).cuda()
+    assert gemm.wgrad_supported(g, x)
+    ref = g.double().t() @ x.double()
+    got = gemm.linear_tf32x3_wgrad(g, x)
+    again = gemm.linear_tf32x3_wgrad(g, x)
+    assert got.shape == (n, k)
+    err, err_fp32 = rel_err(got.cpu(), ref.cpu()), rel_err((g.t() @ x).cpu(), ref.cpu())
+    assert err < 1e-5 and err < 12 * max(err_fp32, 1e-7), (err, err_fp32)
+    rerun = rel_err(again.cpu(), got.cpu())
+    assert rerun < 5e-6, rerun                                         # order of the TMA adds may differ run to run
+    # end to end through autograd
+    lin = torch.nn.Linear(k, n).cuda()
+    old = cape_b200.set_linear_mode("tf32x3")
+    try:
+        xg = x.clone().requires_grad_(True)
+        gx, gw, gb = torch.autograd.grad(gemm.linear(lin, xg), (xg, lin.weight, lin.bias), g)
+    finally:
+        cape_b200.set_linear_mode(old)
+    xr = x.clone().requires_grad_(True)
+    rx, rw, rb = torch.autograd.grad(lin(xr), (xr, lin.weight, lin.bias), g)
+    errs = (rel_err(gx.cpu(), rx.cpu()), rel_err(gw.cpu(), rw.cpu()), rel_err(gb.cpu(), rb.cpu()))
+    assert max(errs) < 1e-5, errs
