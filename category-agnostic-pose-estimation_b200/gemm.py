@@ -95,6 +95,21 @@ def _weight_t(weight: torch.Tensor) -> torch.Tensor:
     return wt
 
 
+_WORKSPACE: dict = {}
+
+
+def _workspace(numel: int, device) -> torch.Tensor:
+    """Grow-only scratch for the transposed operands of the weight gradient (up to 0.7 GB at the FFN shapes): one buffer
+    per device and stream instead of an allocation per call.  Safe to share: every use is enqueued on the stream it is
+    keyed by, and the kernels that read it are enqueued before the next use overwrites it."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _WORKSPACE.get(key)
+    if buf is None or buf.numel() < numel:
+        buf = torch.empty(numel, dtype=torch.float32, device=device)
+        _WORKSPACE[key] = buf
+    return buf
+
+
 def wgrad_supported(g2: torch.Tensor, x2: torch.Tensor) -> bool:
     rows, n = g2.shape
     k = x2.shape[1]
@@ -109,7 +124,7 @@ def linear_tf32x3_wgrad(grad_out: torch.Tensor, x: torch.Tensor) -> torch.Tensor
     rows, n = g2.shape
     k = x2.shape[1]
     grad_w = torch.empty(n, k, dtype=torch.float32, device=g2.device)
-    workspace = torch.empty((n + 2 * k) * rows, dtype=torch.float32, device=g2.device)
+    workspace = _workspace((n + 2 * k) * rows, g2.device)
     with torch.cuda.device(g2.device):
         rc = lib.cape_linear_tf32x3_wgrad(_ptr(g2), _ptr(x2), _ptr(grad_w), _ptr(workspace), rows, n, k, _stream(g2.device))
     _lib.check(rc, "cape_linear_tf32x3_wgrad")

@@ -1,6 +1,9 @@
-"""bench.train_step in both linear modes, fresh process, with allocator statistics.  Development tool."""
+"""bench.train_step in both linear modes, fresh process, with allocator statistics and NVML clock / power samples.
+Development tool."""
 import os
 import sys
+import threading
+import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -9,10 +12,35 @@ import bench
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(dev)
 steps = int(os.environ.get("STEPS", "2"))
+import pynvml
+pynvml.nvmlInit()
+h = pynvml.nvmlDeviceGetHandleByIndex(0)
+
+
+class Sampler(threading.Thread):
+    def __init__(self):
+        super().__init__(daemon=True)
+        self.stop = False
+        self.samples = []
+
+    def run(self):
+        while not self.stop:
+            self.samples.append((pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM), pynvml.nvmlDeviceGetPowerUsage(h) / 1000,
+                                 pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)))
+            time.sleep(0.02)
+
+
 for mode in sys.argv[1:] or ["fp32", "tf32x3", "fp32", "tf32x3"]:
-    s0 = torch.cuda.memory_stats(dev)
+    s = Sampler()
+    s.start()
     r = bench.train_step(dev, 0, 1, linear_mode=mode, steps=steps)
-    s1 = torch.cuda.memory_stats(dev)
-    d = {k: s1[k] - s0[k] for k in ("num_device_alloc", "num_device_free", "num_alloc_retries")}
-    print(mode, r["ms_per_optimizer_step"], "ms", r["episodes_per_s"], "episodes/s", d,
-          "peak GB", round(s1["allocated_bytes.all.peak"] / 2 ** 30, 1), "reserved GB", round(s1["reserved_bytes.all.peak"] / 2 ** 30, 1), flush=True)
+    s.stop = True
+    s.join()
+    clk = sorted(c for c, _, _ in s.samples)
+    pw = sorted(p for _, p, _ in s.samples)
+    reasons = 0
+    for _, _, rs in s.samples:
+        reasons |= rs
+    print(mode, r["ms_per_optimizer_step"], "ms", r["episodes_per_s"], "episodes/s",
+          f"sm MHz min/med/max {clk[0]}/{clk[len(clk) // 2]}/{clk[-1]}  power W med/max {pw[len(pw) // 2]:.0f}/{pw[-1]:.0f}  throttle reasons {reasons:#x}",
+          flush=True)
