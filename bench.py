@@ -370,12 +370,18 @@ def module_step(dev):
     mod.fuse_prologue = False
     unfused = run(lambda: mod(src + pos, ref, src, shapes, starts, None))
     mod.fuse_prologue = True
+    cape_b200.set_linear_mode("tf32x3")            # opt-in: the four projections on the tcgen05 3xTF32 kernel (fwd + bwd)
+    try:
+        fused_tc = run(lambda: mod(src + pos, ref, src, shapes, starts, None))
+    finally:
+        cape_b200.set_linear_mode("fp32")
     wreq = {k: v.clone().requires_grad_(True) for k, v in weights.items()}
     eager = run(lambda: msda_torch.msda_module_forward(wreq, src + pos, ref, src, shapes_l, None))
     return {"N": w["N"], "Lq": w["Lq"], "fwd_bwd_ms": {"mirror_fused_prologue": round(fused, 3),
+                                                         "mirror_fused_prologue_tensor_core_linears": round(fused_tc, 3),
                                                          "mirror_materialised_prologue": round(unfused, 3),
                                                          "reference_formulation_eager_gpu": round(eager, 3)},
-            "note": "includes the four nn.Linear projections (cuBLAS fp32) and their backward"}
+            "note": "includes the four nn.Linear projections and their backward (cuBLAS fp32, or the opt-in 3xTF32 kernel)"}
 
 
 def decode_step(dev):
