@@ -258,3 +258,25 @@ def test_seeded_array_is_a_pure_function_of_name_shape_seed():
     assert -2.0 <= big.min() < -1.99 and 1.99 < big.max() < 2.0 and abs(float(big.mean())) < 0.02
     # a fixed known answer so a change of the recipe cannot go unnoticed
     assert synthetic.seeded_array("x.weight", (3, 4), 1)[0, 0] == np.float32(0.62825286)
+
+
+def test_linear_mode_switch_and_cpu_fallthrough():
+    """gemm.linear is nn.Linear unless the tensor-core mode is on AND the operands are CUDA fp32 with supported shapes."""
+    from cape_b200 import gemm
+    assert cape_b200.linear_mode() == "fp32"
+    with pytest.raises(ValueError):
+        cape_b200.set_linear_mode("bf16")
+    lin = torch.nn.Linear(256, 256)
+    x = torch.randn(130, 256)
+    want = lin(x)
+    old = cape_b200.set_linear_mode("tf32x3")
+    try:
+        assert old == "fp32" and cape_b200.linear_mode() == "tf32x3"
+        assert not gemm.supported(x, lin.weight)                          # CPU tensors never reach the kernel
+        assert torch.equal(gemm.linear(lin, x), want)
+        assert torch.equal(gemm.linear(lin, x, relu=True), want.relu())
+        with pytest.raises(ValueError):
+            cape_b200.linear_tf32x3(x, lin.weight, lin.bias)              # the explicit entry point does not fall back
+    finally:
+        cape_b200.set_linear_mode(old)
+    assert not gemm.wgrad_supported(torch.zeros(1000, 256, device="meta"), torch.zeros(1000, 256, device="meta"))
