@@ -6,15 +6,23 @@
 // tensor memory as   x_lo W_hi + x_hi W_lo + x_hi W_hi   (the lo*lo term, 2^-22 relative, is dropped).
 //
 //   * operands: x (M, K) and W (N, K), both K-major, row-major fp32, K % 32 == 0, N % 128 == 0; W_lo is prepared once per
-//     weight (cape_tf32_split_lo); x_lo is produced inside the kernel from the x tile the TMA already brought in;
-//   * persistent: one CTA per SM walks 128 x 128 output tiles; K step 32 (one 128-byte swizzle atom per row), 3-stage
-//     TMA -> smem pipeline; two accumulators in tensor memory so a tile's epilogue overlaps the next tile's main loop;
+//     weight (cape_tf32_split_lo); x_lo is produced inside the kernel from the x tile the TMA already brought in and is
+//     handed to the tensor core through TENSOR MEMORY (tcgen05.st; the MMA takes its A operand from there), so a
+//     pipeline stage holds three 16 KB tiles (x, W_hi, W_lo) and four stages fit;
+//   * persistent: one CTA per SM walks 128 x 128 output tiles; K step 32 (one 128-byte swizzle atom per row); two
+//     accumulators in tensor memory so a tile's epilogue overlaps the next tile's main loop (512 columns in all:
+//     2 x 128 accumulator columns + 4 x 32 columns of x_lo);
 //   * 10 warps: warp 0 = TMA producer (one elected lane), warp 1 = tensor-memory allocator + MMA issuer (one elected
-//     lane), warps 2..5 = x_lo converters (element-wise on the swizzled tile: same offsets in, same offsets out, so the
-//     swizzle never has to be undone), warps 6..9 = epilogue (tcgen05.ld of their 32-lane quarter, bias, activation,
-//     swizzled staging in shared memory, TMA tensor store — per-thread row stores would cost 32 LSU wavefronts each);
-//   * mbarriers: full (TMA bytes landed), conv (x_lo written and fenced for the async proxy), empty (tcgen05.commit: the
-//     MMAs that read the stage are done), tmem_full / tmem_empty (accumulator complete / drained).
+//     lane), warps 2..5 = x_lo converters (thread = row: 8 conflict-free LDS.128 of the swizzled row, 32 cvt.rna.tf32,
+//     one tcgen05.st.32x32b.x32), warps 6..9 = epilogue (tcgen05.ld of their 32-lane quarter, bias, activation, swizzled
+//     staging in shared memory, TMA tensor store — per-thread row stores would cost 32 LSU wavefronts each);
+//   * mbarriers: full (TMA bytes landed), conv (x_lo in tensor memory), empty (tcgen05.commit: the MMAs that read the
+//     stage are done), tmem_full / tmem_empty (accumulator complete / drained);
+//   * split-K mode for weight gradients (tiny output, reduction over ~10^5 rows): work item = (tile, K slice of <= 1024),
+//     partial tiles are ADDED into y by the TMA (cp.reduce.async.bulk.tensor ... add).
+// What bounds it (ncu): tensor pipe ~58 % active; per tile the SM takes in 384 KB of operand tiles (2/3 of it the W tiles
+// every CTA re-reads from L2), ~31 B/clk/SM — the L2 -> shared-memory ingress of one SM, not the stage count (3 -> 4
+// stages gained 3 %).  A 256-row tile per CTA (two MMAs per W tile) is the next step.
 #include <cuda.h>
 
 #include <mutex>
@@ -26,14 +34,12 @@ namespace cape {
 
 namespace {
 
-constexpr int kBM = 128, kBN = 128, kBK = 32, kStages = 3;
+constexpr int kBM = 128, kBN = 128, kBK = 32, kStages = 4;
 constexpr int kTileBytes = kBM * kBK * 4;                 // 16 KB: one operand tile (128 rows x 128 B)
-constexpr int kStageBytes = 4 * kTileBytes;               // x, x_lo, W_hi, W_lo
+constexpr int kStageBytes = 3 * kTileBytes;               // x, W_hi, W_lo (x_lo lives in tensor memory)
+constexpr int kTmemCols = 512;                            // 2 accumulators x 128 + kStages x 32 columns of x_lo
+constexpr int kALoCol = 2 * kBN;
 constexpr int kGemmThreads = 320;          // TMA warp, MMA warp, 4 converter warps, 4 epilogue warps
-#ifndef CAPE_TF32_LOLO
-#define CAPE_TF32_LOLO 0
-#endif
-constexpr bool kLoLo = CAPE_TF32_LOLO != 0;    // also accumulate x_lo w_lo (a 4th MMA per k-step)
 constexpr int kConvThreads = 128;
 constexpr int kEpiThreads = 128;
 constexpr int kStoreTile = 32 * 32 * 4;                   // epilogue staging: 32 rows x 32 columns per warp and step
@@ -101,6 +107,15 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(kInstrDesc), "r"(accumulate)
         : "memory");
 }
+// same MMA with the A operand read from tensor memory (128 lanes = rows, 8 columns = one K step of tf32 values)
+__device__ __forceinline__ void umma_tf32_ta(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(kInstrDesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -149,7 +164,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {   // 2 x 128 columns of tensor memory: two 128 x 128 fp32 accumulators (mainloop / epilogue overlap)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(const_cast<uint32_t*>(tmem_slot))), "n"(2 * kBN) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(const_cast<uint32_t*>(tmem_slot))), "n"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -169,8 +184,8 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                     const uint32_t st = base + s * kStageBytes;
                     mbar_arrive_expect_tx(full(s), 3 * kTileBytes);
                     tma_load_2d(st, &map_x, full(s), kb * kBK, m0);
-                    tma_load_2d(st + 2 * kTileBytes, &map_wh, full(s), kb * kBK, n0);
-                    tma_load_2d(st + 3 * kTileBytes, &map_wl, full(s), kb * kBK, n0);
+                    tma_load_2d(st + kTileBytes, &map_wh, full(s), kb * kBK, n0);
+                    tma_load_2d(st + 2 * kTileBytes, &map_wl, full(s), kb * kBK, n0);
                 }
             }
         }
@@ -191,12 +206,13 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                     mbar_wait(conv(s), parity);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t st = base + s * kStageBytes;
-                    const uint64_t d_x = umma_desc(st), d_xlo = umma_desc(st + kTileBytes);
-                    const uint64_t d_wh = umma_desc(st + 2 * kTileBytes), d_wl = umma_desc(st + 3 * kTileBytes);
+                    const uint64_t d_x = umma_desc(st);
+                    const uint64_t d_wh = umma_desc(st + kTileBytes), d_wl = umma_desc(st + 2 * kTileBytes);
+                    const uint32_t t_xlo = tmem_base + kALoCol + s * kBK;
 #pragma unroll
                     for (int k = 0; k < kBK / 8; ++k) {   // UMMA_K = 8 for tf32: 32 bytes along K -> +2 in the address field
                         const uint64_t adv = static_cast<uint64_t>(k * 2);
-                        umma_tf32(tmem_acc, d_xlo + adv, d_wh + adv, (kb != kb0) | (k != 0));
+                        umma_tf32_ta(tmem_acc, t_xlo + k * 8, d_wh + adv, (kb != kb0) | (k != 0));
                         umma_tf32(tmem_acc, d_x + adv, d_wl + adv, 1);
                         umma_tf32(tmem_acc, d_x + adv, d_wh + adv, 1);
                     }
@@ -206,8 +222,9 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             }
         }
     } else if (warp < 2 + kConvThreads / 32) {
-        // ===== x_lo converters: element-wise on the swizzled tile (same offsets in and out) =====
-        const int ct = threadIdx.x - 64;               // 0..127
+        // ===== x_lo converters: thread = row of the x tile; the lo parts go to tensor memory (lane = row, column = k) =====
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
         int it = 0;
         for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
             int m0, n0, kb0, kb1;
@@ -215,19 +232,27 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             for (int kb = kb0; kb < kb1; ++kb, ++it) {
                 const int s = it % kStages;
                 mbar_wait(full(s), (it / kStages) & 1);
-                const float4* src = reinterpret_cast<const float4*>(base_ptr + s * kStageBytes);
-                float4* dst = reinterpret_cast<float4*>(base_ptr + s * kStageBytes + kTileBytes);
+                const uint8_t* src = base_ptr + s * kStageBytes + row * 128;
+                uint32_t r[32];
 #pragma unroll
-                for (int i = 0; i < kTileBytes / 16 / kConvThreads; ++i) {
-                    const float4 v = src[i * kConvThreads + ct];
-                    float4 r;
-                    r.x = tf32_lo(v.x);
-                    r.y = tf32_lo(v.y);
-                    r.z = tf32_lo(v.z);
-                    r.w = tf32_lo(v.w);
-                    dst[i * kConvThreads + ct] = r;
+                for (int j = 0; j < 8; ++j) {   // 16-byte chunk j of the row sits at chunk position j ^ (row % 8) (128-byte swizzle)
+                    const float4 v = *reinterpret_cast<const float4*>(src + ((j ^ (row & 7)) << 4));
+                    r[4 * j] = __float_as_uint(tf32_lo(v.x));
+                    r[4 * j + 1] = __float_as_uint(tf32_lo(v.y));
+                    r[4 * j + 2] = __float_as_uint(tf32_lo(v.z));
+                    r[4 * j + 3] = __float_as_uint(tf32_lo(v.w));
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
+                const uint32_t taddr = tmem_base + kALoCol + s * kBK + (static_cast<uint32_t>(quarter * 32) << 16);
+                asm volatile(
+                    "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+                    "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+                    ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+                      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+                      "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+                      "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+                    : "memory");
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 mbar_arrive(conv(s));
             }
         }
@@ -296,7 +321,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     if (warp >= 6 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before exit
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * kBN) : "memory");
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
 }
 
 // lo part of an fp32 tensor for the kernel above: x - (x with the 13 low mantissa bits cleared), exact in fp32.
