@@ -604,6 +604,42 @@ def test_encoder_stack_with_tensor_core_linears_stays_at_fp32_level():
     assert rel_err(out.cpu().numpy(), want.cpu().numpy()) < 2e-5
 
 
+def test_encoder_layer_training_step_with_tensor_core_linears_matches_fp32_gradients():
+    """One CAPE-width encoder layer, forward + backward with autograd, opt-in 3xTF32 linears (forward, input gradient and
+    weight gradient on the tensor cores) vs nn.Linear: outputs and every parameter gradient at fp32 level."""
+    layer = cape_b200.DeformableTransformerEncoderLayer(256, 1024, 0.0, "relu", 4, 8, 4)
+    synthetic.fill_parameters_(layer, seed=9)
+    layer = layer.cuda()
+    shapes = ((32, 24), (16, 12), (8, 6), (4, 3))
+    s = sum(h * w for h, w in shapes)                       # 1020 tokens x 2 images = 2040 rows (>= 1024, % 32 != 0 -> pad check)
+    n = 2
+    src = torch.from_numpy(synthetic.seeded_array("src", (n, s, 256), 9)).cuda()
+    pos = torch.from_numpy(synthetic.seeded_array("pos", (n, s, 256), 9)).cuda() * 0.5
+    shapes_t = torch.tensor(shapes, device="cuda")
+    starts = torch.tensor(synthetic.level_start_index(shapes), device="cuda")
+    ref = cape_b200.DeformableTransformerEncoder.get_reference_points(shapes_t, torch.ones(n, 4, 2, device="cuda"), "cuda")
+    gout = torch.from_numpy(synthetic.seeded_array("gout", (n, s, 256), 9)).cuda()
+
+    def run():
+        x = src.clone().requires_grad_(True)
+        out = layer(x, pos, ref, shapes_t, starts, None)
+        grads = torch.autograd.grad(out, [x] + list(layer.parameters()), gout)
+        return out.detach(), grads
+
+    want_out, want = run()
+    old = cape_b200.set_linear_mode("tf32x3")
+    try:
+        before = cape_b200.launch_count()
+        got_out, got = run()
+        assert cape_b200.launch_count() - before >= 2 + 6 * 2          # the sampling pair + tensor-core forward / dgrad calls
+    finally:
+        cape_b200.set_linear_mode(old)
+    assert rel_err(got_out.cpu().numpy(), want_out.cpu().numpy()) < 2e-5
+    names = ["src"] + [k for k, _ in layer.named_parameters()]
+    errs = {k: rel_err(a.cpu().numpy(), b.cpu().numpy()) for k, a, b in zip(names, got, want)}
+    assert max(errs.values()) < 1e-4, errs
+
+
 def test_decoder_layer_mirror_teacher_forced_and_incremental():
     """TransformerDecoderLayer v1 (deformable_transformer_v2.py:262-370): teacher-forced forward/backward, then the same
     sequence token by token with KV cache + projected-value cache, then one decode step replayed from a CUDA graph."""
