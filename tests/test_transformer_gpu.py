@@ -418,3 +418,43 @@ def test_linear_tf32x3_weight_gradient_split_over_the_rows(rows, n, k):
     rx, rw, rb = torch.autograd.grad(lin(xr), (xr, lin.weight, lin.bias), g)
     errs = (rel_err(gx.cpu(), rx.cpu()), rel_err(gw.cpu(), rw.cpu()), rel_err(gb.cpu(), rb.cpu()))
     assert max(errs) < 1e-5, errs
+
+
+def test_empty_and_degenerate_inputs_of_the_sequence_and_step_kernels():
+    """Zero rows / tokens are no-ops (not launches with a zero grid), and the ABI rejects what the kernels cannot take."""
+    import ctypes
+    from cape_b200 import _lib, decode_ops as K
+    lib = _lib.load()
+    dev = "cuda"
+    table = torch.randn(10, 256, device=dev)
+    empty_idx = torch.zeros(2, 0, dtype=torch.int64, device=dev)
+    empty_d = torch.zeros(2, 0, device=dev)
+    out = cape_b200.seq_embed(table, empty_idx, empty_idx, empty_idx, empty_idx, empty_d, empty_d, empty_d, empty_d, -1)
+    assert out.shape == (2, 0, 256)
+    bad = torch.full((1, 1), 99, dtype=torch.int64, device=dev)                    # token id outside the table -> NaN row
+    one = torch.ones(1, 1, device=dev)
+    assert torch.isnan(cape_b200.seq_embed(table, bad, bad, bad, bad, one, one, one, one, -1)).all()
+    w = torch.randn(256, 256, device=dev)
+    assert K.skinny_linear(torch.zeros(0, 256, device=dev), w).shape == (0, 256)
+    assert K.tiny_linear(torch.zeros(0, 256, device=dev), torch.randn(3, 256, device=dev)).shape == (0, 3)
+    kc = torch.zeros(0, 8, 256, device=dev)
+    assert K.decode_attention(torch.zeros(0, 256, device=dev), kc, kc).shape == (0, 256)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    x = torch.randn(4, 256, device=dev)
+    y = torch.empty(4, 256, device=dev)
+    # K not a multiple of 16 / unknown epilogue / LayerNorm without gamma / misaligned rows
+    assert lib.cape_skinny_linear(p(x), 256, None, 0, p(w), None, None, 0, None, None, 1e-5, None, p(y), 256, 4, 250, 256, 0, None) == -1
+    assert lib.cape_skinny_linear(p(x), 256, None, 0, p(w), None, None, 0, None, None, 1e-5, None, p(y), 256, 4, 256, 256, 7, None) == -1
+    assert lib.cape_skinny_linear(p(x), 256, None, 0, p(w), None, None, 0, None, None, 1e-5, None, p(y), 256, 4, 256, 256, 2, None) == -1
+    assert lib.cape_skinny_linear(p(x), 255, None, 0, p(w), None, None, 0, None, None, 1e-5, None, p(y), 256, 4, 256, 256, 0, None) == -4
+    # head dim other than 32 / more than 1024 keys
+    assert lib.cape_decode_attention(p(x), 256, None, None, 0, p(x), p(x), None, None, p(y), 1, 4, 4, 64, None) == -1
+    assert lib.cape_decode_attention(p(x), 256, None, None, 0, p(x), p(x), None, None, p(y), 1, 2048, 8, 32, None) == -1
+    # 3xTF32 linear: N not a multiple of 128, K not a multiple of 32; host pointers are rejected
+    assert lib.cape_linear_tf32x3(p(x), p(w), p(w), None, p(y), 4, 200, 256, 0, None) == -1
+    assert lib.cape_linear_tf32x3(p(x), p(w), p(w), None, p(y), 4, 256, 250, 0, None) == -1
+    host = torch.randn(4, 256)
+    assert lib.cape_linear_tf32x3(p(host), p(w), p(w), None, p(y), 4, 256, 256, 0, None) == -5
+    assert b"host memory" in lib.cape_last_error()
+    with pytest.raises(ValueError):
+        cape_b200.linear_tf32x3(torch.zeros(0, 256, device=dev), w)
