@@ -24,7 +24,7 @@ from .layers import (DeformableTransformerEncoder, DeformableTransformerEncoderL
 from .variants import MSDeformablePoints, ms_deform_attn_query_pool, points_sample, sample_reference_points
 from .sequence import TokenState, TokenizerSpec, seq_embed
 from .transformer import (MLP, AutoregressiveGenerator, DeformableTransformer, TransformerDecoder, build_prediction_heads,
-                          generate_eager)
+                          generate_eager, load_reference_checkpoint, to_cape_predictions)
 from .gemm import linear_mode, linear_tf32x3, set_linear_mode
 from . import synthetic
 
@@ -34,4 +34,4 @@ __all__ = ["MSDeformAttn", "ValueCache", "MSDeformAttnFunction", "ms_deform_attn
            "DeformableTransformerEncoderLayer", "TransformerDecoderLayer", "KVCache", "IncrementalDecoder", "MSDeformablePoints",
            "ms_deform_attn_query_pool", "points_sample", "sample_reference_points", "seq_embed", "TokenizerSpec", "TokenState",
            "TransformerDecoder", "DeformableTransformer", "MLP", "build_prediction_heads", "AutoregressiveGenerator",
-           "generate_eager", "set_linear_mode", "linear_mode", "linear_tf32x3"]
+           "generate_eager", "load_reference_checkpoint", "to_cape_predictions", "set_linear_mode", "linear_mode", "linear_tf32x3"]

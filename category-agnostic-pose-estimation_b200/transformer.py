@@ -568,3 +568,45 @@ def generate_eager(transformer: DeformableTransformer, spec: TokenizerSpec, srcs
             layer.cross_attn.cache = None
     return {"pred_logits": state.pred_logits[:, :steps].clone(), "pred_coords": state.pred_coords[:, :steps].clone(),
             "sequences": state.pred_logits[:, :steps].argmax(-1), "steps": steps}
+
+
+def to_cape_predictions(generated: dict) -> dict:
+    """The dict ``CAPEModel.forward_inference`` returns (cape_model.py:200-209) from :meth:`AutoregressiveGenerator.generate`
+    / :func:`generate_eager` output: ``sequences`` = argmax token types, ``coordinates``, ``logits``."""
+    logits = generated["pred_logits"]
+    return {"sequences": logits.argmax(dim=-1), "coordinates": generated["pred_coords"], "logits": logits}
+
+
+def load_reference_checkpoint(transformer: DeformableTransformer, model_state: dict, prefix: Optional[str] = None):
+    """Load the transformer part of a reference checkpoint (``checkpoint['model']`` of train_cape_episodic.py:863-888, i.e. a
+    ``CAPEModel.state_dict()``) into the mirror.
+
+    Reference keys look like ``base_model.transformer.encoder.layers.0...`` (CAPEModel wraps RoomFormerV2 as
+    ``base_model``, cape_model.py:40-60); the prediction heads the decoder uses live at ``base_model.class_embed.*`` /
+    ``base_model.coords_embed.*`` as well as under ``...transformer.decoder.*`` (same modules, roomformer_v2.py:245-246).
+    Cache buffers that the reference leaks into its state dict (``kv_cache.*``, ``cross_attn.cache.*``; SURVEY.md
+    Appendix A.2) are dropped.  Returns ``(query_embed_weight or None, missing_keys, unexpected_keys)``."""
+    if prefix is None:
+        for cand in ("base_model.transformer.", "transformer.", ""):
+            if any(k.startswith(cand + "encoder.layers.") for k in model_state):
+                prefix = cand
+                break
+        else:
+            raise KeyError("no '...encoder.layers.*' keys found: not a RoomFormerV2 / CAPEModel state dict")
+    state = {}
+    for k, v in model_state.items():
+        if not k.startswith(prefix):
+            continue
+        name = k[len(prefix):]
+        if ".kv_cache." in name or ".cross_attn.cache." in name:
+            continue
+        state[name] = v
+    outer = prefix[:-len("transformer.")] if prefix.endswith("transformer.") else None
+    if outer is not None:   # heads saved on the owning model only (older checkpoints)
+        for head in ("class_embed", "coords_embed"):
+            for k, v in model_state.items():
+                if k.startswith(outer + head + ".") and ("decoder." + k[len(outer):]) not in state:
+                    state["decoder." + k[len(outer):]] = v
+    missing, unexpected = transformer.load_state_dict(state, strict=False)
+    query = model_state.get((outer or "") + "query_embed.weight")
+    return query, list(missing), list(unexpected)

@@ -280,3 +280,32 @@ def test_linear_mode_switch_and_cpu_fallthrough():
     finally:
         cape_b200.set_linear_mode(old)
     assert not gemm.wgrad_supported(torch.zeros(1000, 256, device="meta"), torch.zeros(1000, 256, device="meta"))
+
+
+def test_reference_checkpoint_keys_load_into_the_mirror():
+    """A CAPEModel-style state dict (prefix base_model.transformer., heads also on the owner, leaked cache buffers) loads
+    into the mirror with nothing missing."""
+    spec = cape_b200.TokenizerSpec(6, 20)
+    src = _small_transformer(spec).attach_heads(*cape_b200.build_prediction_heads(256, 3, 2, True))
+    synthetic.fill_parameters_(src, seed=3)
+    ckpt = {"base_model.transformer." + k: v.clone() for k, v in src.state_dict().items()}
+    for k, v in src.decoder.class_embed.state_dict().items():                      # the owner's copy (roomformer_v2.py:178)
+        ckpt["base_model.class_embed." + k] = v.clone()
+    ckpt["base_model.query_embed.weight"] = torch.randn(20, 2)
+    ckpt["base_model.transformer.decoder.layers.0.kv_cache.k_cache"] = torch.zeros(2, 20, 256)     # Appendix A.2 leak
+    ckpt["base_model.transformer.decoder.layers.0.cross_attn.cache.v_cache"] = torch.zeros(1)
+    ckpt["base_model.backbone.0.body.conv1.weight"] = torch.zeros(1)              # not ours: ignored
+    dst = _small_transformer(spec).attach_heads(*cape_b200.build_prediction_heads(256, 3, 2, True))
+    query, missing, unexpected = cape_b200.load_reference_checkpoint(dst, ckpt)
+    assert missing == [] and unexpected == [] and torch.equal(query, ckpt["base_model.query_embed.weight"])
+    assert all(torch.equal(a, b) for a, b in zip(src.state_dict().values(), dst.state_dict().values()))
+    # heads present only on the owner (decoder.* copies absent): still filled
+    ckpt2 = {k: v for k, v in ckpt.items() if ".decoder.class_embed." not in k}
+    dst2 = _small_transformer(spec).attach_heads(*cape_b200.build_prediction_heads(256, 3, 2, True))
+    _, missing, _ = cape_b200.load_reference_checkpoint(dst2, ckpt2)
+    assert missing == []
+    assert torch.equal(dst2.decoder.class_embed[1].weight, src.decoder.class_embed[1].weight)
+    with pytest.raises(KeyError):
+        cape_b200.load_reference_checkpoint(dst, {"foo.weight": torch.zeros(1)})
+    out = cape_b200.to_cape_predictions({"pred_logits": torch.tensor([[[0.1, 2.0, 0.3]]]), "pred_coords": torch.zeros(1, 1, 2)})
+    assert out["sequences"].tolist() == [[1]] and set(out) == {"sequences", "coordinates", "logits"}
