@@ -309,3 +309,25 @@ def test_reference_checkpoint_keys_load_into_the_mirror():
         cape_b200.load_reference_checkpoint(dst, {"foo.weight": torch.zeros(1)})
     out = cape_b200.to_cape_predictions({"pred_logits": torch.tensor([[[0.1, 2.0, 0.3]]]), "pred_coords": torch.zeros(1, 1, 2)})
     assert out["sequences"].tolist() == [[1]] and set(out) == {"sequences", "coordinates", "logits"}
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="needs the reference sources (build container only)")
+def test_real_reference_state_dict_loads_into_the_mirror():
+    """The reference's own RoomFormerV2 (stub backbone, oracle/make_golden.py) after `_setup_caches` — i.e. with the leaked
+    KV / V cache buffers of Appendix A.2 in its state dict — loads into the mirror with nothing missing or unexpected."""
+    from oracle import make_golden
+    syn = make_golden.load_synthetic()
+    shapes = ((8, 12), (4, 6), (2, 3), (1, 2))
+    feats = [torch.zeros(2, 256, h, w) for h, w in shapes]
+    model, tokenizer, _ = make_golden.build_reference_model(syn, 20, 6, feats, None, 31)
+    model._setup_caches(2, sum(h * w for h, w in shapes))
+    state = model.state_dict()
+    assert any(".kv_cache." in k for k in state)                                  # the leak is real
+    spec = cape_b200.TokenizerSpec.from_tokenizer(tokenizer)
+    tr = _small_transformer(spec).attach_heads(*cape_b200.build_prediction_heads(256, 3, 2, True))
+    query, missing, unexpected = cape_b200.load_reference_checkpoint(tr, state)
+    assert missing == [] and unexpected == []
+    assert torch.equal(query, model.query_embed.weight)
+    ref_tr = model.transformer.state_dict()
+    for k, v in tr.state_dict().items():
+        assert torch.equal(v, ref_tr[k]), k
