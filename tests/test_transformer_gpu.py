@@ -458,3 +458,70 @@ def test_empty_and_degenerate_inputs_of_the_sequence_and_step_kernels():
     assert b"host memory" in lib.cape_last_error()
     with pytest.raises(ValueError):
         cape_b200.linear_tf32x3(torch.zeros(0, 256, device=dev), w)
+
+
+def test_guard_zones_around_outputs_of_the_step_and_gemm_kernels():
+    """compute-sanitizer is closed on this pool: outputs (and inputs) of the new kernels are carved out of one NaN-filled
+    arena and called through the C ABI directly; afterwards every guard word must be untouched — ragged row counts
+    exercise the TMA store clipping, the split-K TMA reduce and the partial tiles of the skinny kernel."""
+    import ctypes
+    from cape_b200 import _lib
+    lib = _lib.load()
+    guard = 4096
+    sizes = {"x": 300 * 256, "w": 256 * 256, "w_lo": 256 * 256, "bias": 256, "y": 300 * 256,             # 3xTF32 forward, M = 300
+             "g": 1056 * 128, "xg": 1056 * 256, "gw": 128 * 256, "ws": (128 + 2 * 256) * 1056,             # weight gradient, 1056 rows
+             "sx": 5 * 256, "swt": 256 * 256, "sy": 5 * 256, "gamma": 256, "beta": 256,                    # skinny linear + LayerNorm, 5 rows
+             "q": 3 * 256, "knew": 3 * 256, "vnew": 3 * 256, "kc": 3 * 9 * 256, "vc": 3 * 9 * 256, "ao": 3 * 256}
+    total = sum(v + 2 * guard for v in sizes.values())
+    arena = torch.full((total,), float("nan"), device="cuda")
+    views, off = {}, 0
+    for k, numel in sizes.items():
+        off += guard
+        views[k] = arena[off:off + numel]
+        off += numel + guard
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    for k in ("x", "w", "bias", "g", "xg", "sx", "swt", "gamma", "beta", "q", "knew", "vnew", "kc", "vc"):
+        views[k].copy_(torch.randn(views[k].numel(), device="cuda", generator=gen) * 0.1)
+    for k in ("w_lo", "y", "gw", "ws", "sy", "ao"):
+        views[k].zero_()
+    snapshot = arena.clone()
+    outputs = ("w_lo", "y", "gw", "ws", "sy", "ao", "kc", "vc")
+    p = lambda k: ctypes.c_void_p(views[k].data_ptr())
+    sp = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    pos = torch.full((1,), 4, dtype=torch.int64, device="cuda")
+    _lib.check(lib.cape_tf32_split_lo(p("w"), p("w_lo"), 256 * 256, sp), "split")
+    _lib.check(lib.cape_linear_tf32x3(p("x"), p("w"), p("w_lo"), p("bias"), p("y"), 300, 256, 256, 1, sp), "gemm")
+    _lib.check(lib.cape_linear_tf32x3_wgrad(p("g"), p("xg"), p("gw"), p("ws"), 1056, 128, 256, sp), "wgrad")
+    _lib.check(lib.cape_skinny_linear(p("sx"), 256, None, 0, p("swt"), p("bias"), p("sx"), 256, p("gamma"), p("beta"), 1e-5, None,
+                                      p("sy"), 256, 5, 256, 256, 2, sp), "skinny")
+    _lib.check(lib.cape_decode_attention(p("q"), 256, p("knew"), p("vnew"), 256, p("kc"), p("vc"), ctypes.c_void_p(pos.data_ptr()),
+                                         None, p("ao"), 3, 9, 8, 32, sp), "attention")
+    torch.cuda.synchronize()
+    mask = torch.ones(total, dtype=torch.bool, device="cuda")           # everything except the output tensors must be unchanged
+    off = 0
+    for k, numel in sizes.items():
+        off += guard
+        if k in outputs:
+            mask[off:off + numel] = False
+        off += numel + guard
+    same = (arena == snapshot) | (torch.isnan(arena) & torch.isnan(snapshot))
+    assert bool(same[mask].all()), "a kernel wrote outside its output tensors"
+    for k in ("y", "gw", "sy", "ao"):
+        assert bool(torch.isfinite(views[k]).all()), k
+    # and the results are right
+    x, w, b = views["x"].view(300, 256), views["w"].view(256, 256), views["bias"]
+    assert rel_err(views["y"].view(300, 256).cpu(), (x.double() @ w.double().t() + b.double()).clamp_min(0).cpu()) < 1e-5
+    g, xg = views["g"].view(1056, 128), views["xg"].view(1056, 256)
+    assert rel_err(views["gw"].view(128, 256).cpu(), (g.double().t() @ xg.double()).cpu()) < 1e-5
+    kc = views["kc"].view(3, 9, 256)
+    assert torch.equal(kc[:, 4], views["knew"].view(3, 256)) and torch.equal(kc[:, 5:], snapshot_view(snapshot, sizes, guard, "kc").view(3, 9, 256)[:, 5:])
+
+
+def snapshot_view(snapshot, sizes, guard, name):
+    off = 0
+    for k, numel in sizes.items():
+        off += guard
+        if k == name:
+            return snapshot[off:off + numel]
+        off += numel + guard
+    raise KeyError(name)
