@@ -79,6 +79,17 @@ int check_ptr(const void* p, const char* name, bool empty_ok, unsigned align = 1
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+bool first_use_on_device(unsigned long long* flags) {
+    static std::mutex mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;   // unknown device: just redo the set-up
+    std::lock_guard<std::mutex> lock(mu);
+    const unsigned long long bit = 1ull << dev;
+    if (*flags & bit) return false;
+    *flags |= bit;
+    return true;
+}
+
 }  // namespace cape
 
 using namespace cape;

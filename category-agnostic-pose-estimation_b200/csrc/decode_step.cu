@@ -15,7 +15,6 @@
 //
 // All fp32, FMA accumulation; weights are read from L2 (the whole 6-layer decoder is 32 MB).
 #include <cfloat>
-#include <mutex>
 
 #include <cooperative_groups.h>
 
@@ -420,13 +419,13 @@ cudaError_t launch_skinny_groups(const SkinnyArgs& a, int epilogue, cudaStream_t
                  (static_cast<size_t>(kSkRows) * a.K + static_cast<size_t>(GROUPS) * kSkRows * kSkCols) * sizeof(float), stream,
                  epilogue >= 2 ? col_tiles : 1);
     cudaLaunchConfig_t& cfg = l.cfg;
-    static std::once_flag once;   // per GROUPS instantiation: opt in to > 48 KB of shared memory (long reductions)
-    std::call_once(once, [] {
+    static unsigned long long configured = 0;   // per GROUPS instantiation and device: opt in to > 48 KB of shared memory
+    if (first_use_on_device(&configured)) {
         cudaFuncSetAttribute(skinny_linear_kernel<0, GROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
         cudaFuncSetAttribute(skinny_linear_kernel<1, GROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
         cudaFuncSetAttribute(skinny_linear_kernel<2, GROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
         cudaFuncSetAttribute(skinny_linear_kernel<3, GROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    });
+    }
     switch (epilogue) {
         case 0: return cudaLaunchKernelEx(&cfg, skinny_linear_kernel<0, GROUPS>, a);
         case 1: return cudaLaunchKernelEx(&cfg, skinny_linear_kernel<1, GROUPS>, a);

@@ -25,8 +25,6 @@
 // stages gained 3 %).  A 256-row tile per CTA (two MMAs per W tile) is the next step.
 #include <cuda.h>
 
-#include <mutex>
-
 #include "msda_common.cuh"
 #include "msda_launch.h"
 
@@ -413,11 +411,11 @@ cudaError_t launch_linear_tf32x3(const float* x, const float* w, const float* w_
     if (!make_map(&map_x, x, M, K) || !make_map(&map_wh, w, N, K) || !make_map(&map_wl, w_lo, N, K) ||
         !make_map(&map_y, y, M, N, 32))
         return cudaErrorNotSupported;
-    static std::once_flag once;
-    std::call_once(once, [] {
+    static unsigned long long configured = 0;
+    if (first_use_on_device(&configured)) {
         cudaFuncSetAttribute(linear_tf32x3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmem));
         cudaFuncSetAttribute(linear_tf32x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmem));
-    });
+    }
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int out_tiles = (N / kBN) * ((M + kBM - 1) / kBM);

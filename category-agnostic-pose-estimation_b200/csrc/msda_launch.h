@@ -115,4 +115,8 @@ cudaError_t launch_token_step(const float* cls_logits, const float* reg, int64_t
 
 void count_launch();
 
+// True the first time it is called for the current device with this `flags` word (one word per kernel family): function
+// attributes such as the dynamic shared-memory opt-in are per device, so a once-per-process flag is not enough.
+bool first_use_on_device(unsigned long long* flags);
+
 }  // namespace cape
