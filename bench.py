@@ -267,11 +267,13 @@ def train_step(dev, rank, world, accumulation=4, steps=2, amp=False, linear_mode
     cdist.barrier(dev)
     torch.cuda.synchronize(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    allocs0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
     e0.record()
     for _ in range(steps):
         optimizer_step()
     e1.record()
     torch.cuda.synchronize(dev)
+    timed_allocs = torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - allocs0
     ms = cdist.max_over_ranks(e0.elapsed_time(e1), dev) / steps
     episodes = world * accumulation * (n // 2)
     n_params = sum(p.numel() for p in params)
@@ -280,7 +282,7 @@ def train_step(dev, rank, world, accumulation=4, steps=2, amp=False, linear_mode
     torch.cuda.empty_cache()
     return {"episodes_per_s": round(episodes / (ms * 1e-3), 2), "ms_per_optimizer_step": round(ms, 2),
             "episodes_per_step": episodes, "accumulation": accumulation, "allreduce_mb": round(n_params * 4 / 2 ** 20, 1),
-            "msda_launches_per_step": int(per_step_launches),
+            "msda_launches_per_step": int(per_step_launches), "cudaMallocs_in_timed_region": int(timed_allocs),
             "dtype": "fp16 autocast + GradScaler (the reference's --use_amp); MSDeformAttn value fp16, accumulation fp32"
             if amp else ("f32; opt-in tcgen05 3xTF32 linears for the MSDeformAttn projections and FFNs (forward + input "
                          "gradient; weight gradient cuBLAS fp32)" if linear_mode == "tf32x3" else "f32 (TF32 off)"),
@@ -707,10 +709,8 @@ def run_b200(args, rank, world, local_rank):
             train_amp = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     train_tc = None
     if not args.no_extras:
-        try:   # two invocations: the first one after a mode switch has measured 310-430 ms, repeats are steady at ~310
-            first = train_step(dev, rank, world, linear_mode="tf32x3")
+        try:
             train_tc = train_step(dev, rank, world, linear_mode="tf32x3")
-            train_tc["ms_per_optimizer_step_runs"] = [first["ms_per_optimizer_step"], train_tc["ms_per_optimizer_step"]]
         except Exception as exc:                                   # noqa: BLE001 - every rank must keep going
             train_tc = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     if rank != 0:

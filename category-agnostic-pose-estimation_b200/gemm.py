@@ -41,11 +41,14 @@ def _weight_lo(weight: torch.Tensor) -> torch.Tensor:
     """lo part of a weight (cached per tensor object and version; recomputed after an in-place update)."""
     key = id(weight)
     hit = _LO_CACHE.get(key)
-    if hit is not None and hit[0]() is weight and hit[1] == weight._version and hit[2] == weight.data_ptr():
+    same_tensor = hit is not None and hit[0]() is weight and hit[2] == weight.data_ptr()
+    if same_tensor and hit[1] == weight._version:
         return hit[3]
     lib = _lib.load()
     w = weight.detach()
-    lo = torch.empty_like(w)
+    # after an optimizer step only the version changes: refill the same buffer (a fresh allocation per weight and step
+    # keeps the caching allocator from settling and costs cudaMallocs inside the training loop)
+    lo = hit[3] if same_tensor and hit[3].shape == w.shape else torch.empty_like(w)
     with torch.cuda.device(w.device):
         _lib.check(lib.cape_tf32_split_lo(_ptr(w), _ptr(lo), w.numel(), _stream(w.device)), "cape_tf32_split_lo")
     if len(_LO_CACHE) > 512:
@@ -86,9 +89,14 @@ def _weight_t(weight: torch.Tensor) -> torch.Tensor:
     """W^T (K, N) contiguous, cached per tensor version: the operand of the input-gradient GEMM g . W."""
     key = id(weight)
     hit = _WT_CACHE.get(key)
-    if hit is not None and hit[0]() is weight and hit[1] == weight._version and hit[2] == weight.data_ptr():
+    same_tensor = hit is not None and hit[0]() is weight and hit[2] == weight.data_ptr()
+    if same_tensor and hit[1] == weight._version:
         return hit[3]
-    wt = weight.detach().t().contiguous()
+    if same_tensor and hit[3].shape == (weight.shape[1], weight.shape[0]):
+        wt = hit[3]
+        wt.copy_(weight.detach().t())                      # in place: same buffer, new version (its lo part follows)
+    else:
+        wt = weight.detach().t().contiguous()
     if len(_WT_CACHE) > 512:
         _WT_CACHE.clear()
     _WT_CACHE[key] = (weakref.ref(weight), weight._version, weight.data_ptr(), wt)

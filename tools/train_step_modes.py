@@ -41,6 +41,6 @@ for mode in sys.argv[1:] or ["fp32", "tf32x3", "fp32", "tf32x3"]:
     reasons = 0
     for _, _, rs in s.samples:
         reasons |= rs
-    print(mode, r["ms_per_optimizer_step"], "ms", r["episodes_per_s"], "episodes/s",
+    print(mode, r["ms_per_optimizer_step"], "ms", r["episodes_per_s"], "episodes/s", "mallocs in timed region", r["cudaMallocs_in_timed_region"],
           f"sm MHz min/med/max {clk[0]}/{clk[len(clk) // 2]}/{clk[-1]}  power W med/max {pw[len(pw) // 2]:.0f}/{pw[-1]:.0f}  throttle reasons {reasons:#x}",
           flush=True)
