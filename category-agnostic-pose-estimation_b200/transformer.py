@@ -527,14 +527,9 @@ class AutoregressiveGenerator(IncrementalDecoder):
         steps = min(steps, int(st.step.item()))
         logits = st.pred_logits[:, :steps].clone()
         coords = st.pred_coords[:, :steps].clone()
-        kind = st.gen_kind[:, :steps].cpu().numpy()
-        xy = st.gen_xy[:, :steps].cpu().numpy()
-        gen_out = []
-        for j in range(kind.shape[0]):
-            row = []
-            for t in range(steps):
-                row.append([xy[j, t, 0], xy[j, t, 1]] if kind[j, t] == 0 else int(kind[j, t]))
-            gen_out.append(row)
+        kind = st.gen_kind[:, :steps].cpu().tolist()                 # one D2H copy each, then plain Python lists
+        xy = st.gen_xy[:, :steps].cpu().tolist()
+        gen_out = [[p if k == 0 else k for k, p in zip(kinds, points)] for kinds, points in zip(kind, xy)]
         return {"pred_logits": logits, "pred_coords": coords, "gen_out": gen_out, "sequences": logits.argmax(-1),
                 "steps": steps}
 
