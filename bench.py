@@ -306,15 +306,19 @@ def _time_us(fn, reps):
 
 
 def op_sweep(lib, dev):
-    """BASELINE.json configs[1]: a few points of the op sweep (1k-20k queries, fp32 and bf16 value), raw ABI calls."""
+    """BASELINE.json configs[1] / SURVEY.md §8d: the op sweep (1k-20k queries, N in {2, 4, 20}, fp32 and bf16 value, the
+    spatially coherent "encoder" location distribution and the worst-case "uniform" one), raw ABI calls."""
     import torch
     import cape_b200
     from cape_b200 import _lib
     p = lambda t: ctypes.c_void_p(t.data_ptr())
     sp = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     rows = []
-    for n, lq in ((2, 1000), (2, 5440), (2, 20000), (4, 5440), (20, 200)):
-        inp = cape_b200.synthetic.make_inputs(n, lq, dist="encoder", seed=1, device=dev)
+    grid = [(2, 1000, "encoder"), (2, 1360, "encoder"), (2, 2000, "encoder"), (2, 5440, "encoder"), (2, 10000, "encoder"),
+            (2, 20000, "encoder"), (4, 5440, "encoder"), (20, 200, "encoder"), (20, 5440, "encoder"),
+            (2, 5440, "uniform"), (4, 5440, "uniform"), (20, 5440, "uniform")]
+    for n, lq, dist in grid:
+        inp = cape_b200.synthetic.make_inputs(n, lq, dist=dist, seed=1, device=dev)
         loc, attn = inp["sampling_locations"], inp["attention_weights"]
         shapes, starts = inp["spatial_shapes"], inp["level_start_index"]
         gvalue = torch.empty(inp["value"].shape, device=dev)
@@ -330,7 +334,7 @@ def op_sweep(lib, dev):
                                                             sp), "bwd")
             t_f, t_b = _time_us(fwd, 20), _time_us(bwd, 20)
             a_f, a_b = cape_b200.synthetic.algorithmic_bytes(n, lq, 5440, e_value=ev)
-            rows.append({"N": n, "Lq": lq, "dtype": name, "fwd_us": round(t_f, 1), "bwd_us": round(t_b, 1),
+            rows.append({"N": n, "Lq": lq, "dist": dist, "dtype": name, "fwd_us": round(t_f, 1), "bwd_us": round(t_b, 1),
                          "gbs": round((a_f + a_b) / (t_f + t_b) / 1e3, 1)})
     return rows
 

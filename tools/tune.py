@@ -56,7 +56,9 @@ if which in ("fwd", "both"):
         os.environ["CAPE_FWD_THREADS"], os.environ["CAPE_FWD_QPC"] = str(th), str(qpc)
         print(f"fwd threads={th:4d} qpc={qpc:4d}  {timeit(fwd):8.1f} us", flush=True)
 if which in ("bwd", "both"):
-    for th, qpc in itertools.product((128, 256, 512), (64, 128, 256, 512, 1024)):
+    ths = [int(v) for v in os.environ.get("TUNE_THREADS", "128,256,512").split(",")]
+    qpcs = [int(v) for v in os.environ.get("TUNE_QPCS", "64,128,256,512,1024").split(",")]
+    for th, qpc in itertools.product(ths, qpcs):
         os.environ["CAPE_BWD_THREADS"], os.environ["CAPE_BWD_QPC"] = str(th), str(qpc)
         gvalue.zero_()
         print(f"bwd threads={th:4d} qpc={qpc:4d}  {timeit(bwd):8.1f} us", flush=True)
