@@ -173,7 +173,8 @@ class _LinearTF32x3(torch.autograd.Function):
 
 def linear(module: torch.nn.Linear, x: torch.Tensor, relu: bool = False) -> torch.Tensor:
     """``module(x)`` (optionally followed by ReLU), routed to the tensor-core kernel when the mode allows it."""
-    if _MODE == "tf32x3" and supported(x, module.weight) and x.numel() // x.shape[-1] >= 128:
+    if _MODE == "tf32x3" and supported(x, module.weight) and x.numel() // x.shape[-1] >= 128 \
+            and not torch.is_autocast_enabled():          # under AMP nn.Linear runs in fp16 / bf16: leave that to autocast
         if not torch.is_grad_enabled():
             return linear_tf32x3(x, module.weight, module.bias, relu)
         y = _LinearTF32x3.apply(x, module.weight, module.bias)

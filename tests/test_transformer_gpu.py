@@ -373,6 +373,8 @@ def test_linear_mode_routes_inference_only_and_tracks_weight_updates():
             assert rel_err(y2.cpu(), lin(x).cpu()) < 1e-5
             small = gemm.linear(lin, x[:1, :3])                          # tiny inputs stay on nn.Linear
             assert torch.equal(small, lin(x[:1, :3]))
+            with torch.autocast("cuda", dtype=torch.float16):            # AMP keeps its own (half-precision) Linear
+                assert gemm.linear(lin, x).dtype == torch.float16
     finally:
         cape_b200.set_linear_mode(old)
     assert cape_b200.linear_mode() == old
