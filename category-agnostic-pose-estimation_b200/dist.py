@@ -72,45 +72,293 @@ def barrier(device=None):
             dist.barrier()
 
 
-class FlatGradAllreduce:
-    """One all-reduce (sum, then / world) of every trainable parameter's gradient through a flat fp32 bucket.
+class GradBuckets:
+    """Gradients of every trainable parameter live as VIEWS of one flat fp32 buffer, cut into buckets that are
+    all-reduced (sum, then / world) asynchronously from inside the backward pass as soon as every gradient of a bucket has
+    been accumulated — so the collective of the tail buckets overlaps the rest of backward, there is no pack / unpack
+    launch per parameter and no host synchronisation.
 
-    Slots are fixed at construction from ``params`` order, so every rank reduces the same layout whether or not a
-    given parameter produced a gradient this step (``grad is None`` -> zeros in, and the averaged slot is written
-    back only if some rank had a gradient, mirroring what a single-process run would leave as ``None``).
+    Slots are fixed, so every rank reduces the same layout whether or not a given parameter produced a gradient
+    (``CAPEModel`` has 38 trainable tensors that never do): such parameters contribute zeros and end the
+    step with ``grad = None`` exactly as in a single-process run (AdamW then skips them, weight decay included).
+
+    Gradient accumulation: call :meth:`begin_micro_batch` with ``sync=False`` for all but the last micro-batch of an
+    optimizer step (local accumulation only, the ``no_sync`` of stock DDP), ``sync=True`` for the last.
+    ``zero_grad()`` (also installed on a wrapped optimizer by :meth:`wrap_optimizer`) zeroes the flat buffer with one
+    memset and keeps the views in place.
+
+    Which parameters a bucket has to wait for is learned from the first optimizer step (every bucket is launched at the
+    end of backward until then), after which the flat layout is re-sorted into the observed gradient order so buckets
+    complete front to back.  The set of used parameters must not change between steps (``static_graph`` semantics);
+    a violation raises instead of reducing a half-written bucket.
     """
 
-    def __init__(self, params: Iterable[torch.nn.Parameter]):
+    def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 32 << 20, overlap: bool = True):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
-        self.offsets: List[int] = []
-        total = 0
-        for p in self.params:
-            self.offsets.append(total)
-            total += p.numel()
-        self.numel = total
+        if any(p.dtype != torch.float32 for p in self.params):
+            raise TypeError("GradBuckets expects fp32 parameters (AMP keeps fp32 master weights under autocast)")
+        self.index = {id(p): i for i, p in enumerate(self.params)}
+        self.bucket_bytes = int(bucket_bytes)
+        self.overlap = overlap
+        self.sync = True
+        self.known = False                       # which parameters produce gradients: learned during the first step
+        self.ever_fired = [False] * len(self.params)
+        self.fire_order: List[int] = []
+        self._relayout_pending = False
+        self._handles = []
+        self._layout(list(range(len(self.params)))[::-1])     # backward visits parameters roughly in reverse order
+        self._reset_step_state()
+
+    # -- layout ------------------------------------------------------------------------------------------------------
+    def _layout(self, order: Sequence[int]) -> None:
         device = self.params[0].device if self.params else torch.device("cpu")
-        self.flat = torch.zeros(total + len(self.params), dtype=torch.float32, device=device)
+        total = sum(self.params[i].numel() for i in order)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=device)
+        self.views: List[torch.Tensor] = [None] * len(self.params)
+        self.bucket_of = [0] * len(self.params)
+        self.buckets: List[List[int]] = [[]]
+        self.bucket_range: List[List[int]] = [[0, 0]]
+        off, limit = 0, max(1, self.bucket_bytes // 4)
+        for i in order:
+            n = self.params[i].numel()
+            if self.buckets[-1] and off + n - self.bucket_range[-1][0] > limit:
+                self.buckets.append([])
+                self.bucket_range.append([off, off])
+            self.views[i] = self.flat[off:off + n].view_as(self.params[i])
+            self.bucket_of[i] = len(self.buckets) - 1
+            self.buckets[-1].append(i)
+            off += n
+            self.bucket_range[-1][1] = off
+        self.numel = total
+
+    def _reset_step_state(self) -> None:
+        self.fired_now = [False] * len(self.params)
+        self.pending = [sum(1 for i in b if self.ever_fired[i]) for b in self.buckets]
+        self.launched = [False] * len(self.buckets)
+        self.works = []
+        self._callback_queued = False
+
+    # -- installation ------------------------------------------------------------------------------------------------
+    def install(self) -> "GradBuckets":
+        """Point every ``p.grad`` at its view and register the post-accumulate hooks."""
+        for i, p in enumerate(self.params):
+            if p.grad is not None:
+                self.views[i].copy_(p.grad)
+            p.grad = self.views[i]
+        if not self._handles:
+            self._handles = [p.register_post_accumulate_grad_hook(self._hook) for p in self.params]
+        return self
+
+    def remove(self) -> None:
+        for h in self._handles:
+            h.remove()
+        self._handles = []
+
+    def wrap_optimizer(self, optimizer):
+        """Make ``optimizer.zero_grad()`` — which the reference's loop calls (``engine_cape.py:88,258``) and which would
+        otherwise drop the views (``set_to_none=True``) — zero the flat buffer instead."""
+        optimizer.zero_grad = lambda set_to_none=True: self.zero_grad()
+        return optimizer
+
+    def zero_grad(self) -> None:
+        if self._relayout_pending:               # gradients are being discarded anyway: free to move the slots
+            order = self.fire_order + [i for i in range(len(self.params)) if not self.ever_fired[i]]
+            self._layout(order)
+            self._relayout_pending = False
+            self._reset_step_state()
+        else:
+            self.flat.zero_()
+        for i, p in enumerate(self.params):
+            if self.ever_fired[i] or not self.known:
+                p.grad = self.views[i]
+
+    def begin_micro_batch(self, sync: bool) -> None:
+        """Call before every forward/backward: ``sync`` says whether this backward ends an optimizer step."""
+        self.sync = bool(sync)
+        self.fired_now = [False] * len(self.params)
+
+    # -- backward-time machinery ---------------------------------------------------------------------------------------
+    def _hook(self, p: torch.nn.Parameter) -> None:
+        i = self.index[id(p)]
+        v = self.views[i]
+        g = p.grad
+        if g is None:
+            return
+        if g.data_ptr() != v.data_ptr():         # someone dropped the view (an external zero_grad(set_to_none=True))
+            v.copy_(g)
+            p.grad = v
+        if not self.ever_fired[i]:
+            if self.known:
+                raise RuntimeError("GradBuckets: a parameter that produced no gradient during the first optimizer step "
+                                   "produced one now; the set of used parameters must be static")
+            self.ever_fired[i] = True
+            self.fire_order.append(i)
+        if self.fired_now[i]:
+            return
+        self.fired_now[i] = True
+        if not self.sync:
+            return
+        if not self._callback_queued:
+            torch.autograd.Variable._execution_engine.queue_callback(self._finalize)
+            self._callback_queued = True
+        if self.known and self.overlap and world_size() > 1:
+            b = self.bucket_of[i]
+            self.pending[b] -= 1
+            if self.pending[b] == 0 and not self.launched[b]:
+                self._launch(b)
+
+    def _launch(self, b: int) -> None:
+        lo, hi = self.bucket_range[b]
+        self.launched[b] = True
+        if hi > lo:
+            self.works.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+
+    def _finalize(self) -> None:
+        """End of the synchronising backward: launch what is left, join, average."""
+        world = world_size()
+        if world > 1:
+            for b in range(len(self.buckets)):
+                if not self.launched[b]:
+                    self._launch(b)
+            for w in self.works:
+                w.wait()
+            self.flat.div_(world)
+        if not self.known:
+            self.known = True
+            self._relayout_pending = True
+        for i, p in enumerate(self.params):
+            if not self.ever_fired[i]:
+                p.grad = None                    # what a single-process run leaves behind for a never-used parameter
+        self._reset_step_state()
+
+    def reduce_now(self) -> None:
+        """Manual mode (no hooks, or after a backward that ran with ``sync=False``): reduce everything in one go."""
+        for i, p in enumerate(self.params):
+            if p.grad is not None and p.grad.data_ptr() != self.views[i].data_ptr():
+                self.views[i].copy_(p.grad)
+                p.grad = self.views[i]
+                if not self.ever_fired[i]:
+                    self.ever_fired[i] = True
+                    self.fire_order.append(i)
+        self._finalize()
+
+
+class FlatGradAllreduce:
+    """One all-reduce (sum, then / world) of every trainable parameter's gradient, call-style interface kept from round 1
+    (``allreduce()`` after the last backward of an optimizer step).  Now a thin front of :class:`GradBuckets`: gradients
+    are views of the flat buffer, so the call is the collective itself — no per-parameter pack / unpack launches and no
+    host read of per-parameter flags."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter]):
+        self.buckets = GradBuckets(params, overlap=False)
+        self.params = self.buckets.params
+        self.numel = self.buckets.numel
+        self._seen = [False] * len(self.params)
 
     def __call__(self) -> None:
-        world = world_size()
-        n = self.numel
-        flags = self.flat[n:]
-        self.flat.zero_()
-        for i, (p, off) in enumerate(zip(self.params, self.offsets)):
+        b = self.buckets
+        for i, p in enumerate(self.params):
             if p.grad is not None:
-                self.flat[off:off + p.numel()].copy_(p.grad.reshape(-1))
-                flags[i] = 1.0
-        if world > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-            self.flat[:n].div_(world)
-        has_grad = flags.tolist()
-        for i, (p, off) in enumerate(zip(self.params, self.offsets)):
-            if has_grad[i] > 0:
-                g = self.flat[off:off + p.numel()].view_as(p).to(p.dtype)
-                if p.grad is None:
-                    p.grad = g.clone()
-                else:
-                    p.grad.copy_(g)
+                b.ever_fired[i] = True
+                if not self._seen[i]:
+                    self._seen[i] = True
+                    b.fire_order.append(i)
+            elif b.ever_fired[i]:
+                b.views[i].zero_()               # had gradients before, none this step: contributes zeros
+        b.known = False                          # manual mode: usage is re-read from p.grad every call
+        b.reduce_now()
+        b._relayout_pending = False
+        for i, p in enumerate(self.params):      # leave plain .grad tensors behind (callers may set_to_none afterwards)
+            if b.ever_fired[i] and p.grad is None:
+                p.grad = b.views[i]
+
+
+class ShardedEpisodeLoader:
+    """Per-rank view of an episodic loader for data-parallel training around the reference's unmodified
+    ``train_one_epoch_episodic`` (``engine_cape.py:48-301``).
+
+    * sharding: every rank iterates the same global loader (same seed) and keeps episodes ``rank::world`` of each collated
+      batch (rows ``e*K .. (e+1)*K`` of every ``(B*K, ...)`` tensor and list, ``episodic_collate_fn``'s layout) — the
+      global batch equals the single-process one.  With ``shard=False`` the loader is assumed to be per-rank already
+      (built with :func:`rank_seed`);
+    * it tells the :class:`GradBuckets` which micro-batches end an optimizer step — ``(batch_idx + 1) % accumulation_steps
+      == 0`` or the last batch of the epoch, the two places the reference calls ``optimizer.step()`` (:230-258, :276-290)."""
+
+    def __init__(self, loader, buckets: "GradBuckets | None", accumulation_steps: int = 1, rank: int = 0, world: int = 1,
+                 queries_per_episode: int = 2, shard: bool = True):
+        self.loader, self.buckets = loader, buckets
+        self.accumulation_steps = max(1, int(accumulation_steps))
+        self.rank, self.world, self.k, self.shard = rank, world, queries_per_episode, shard
+
+    def __len__(self):
+        return len(self.loader)
+
+    def __iter__(self):
+        it = iter(self.loader)
+        try:
+            nxt = next(it)
+        except StopIteration:
+            return
+        idx = 0
+        while True:
+            cur = nxt
+            try:
+                nxt = next(it)
+                last = False
+            except StopIteration:
+                last = True
+            if self.buckets is not None:
+                self.buckets.begin_micro_batch(last or (idx + 1) % self.accumulation_steps == 0)
+            yield shard_batch(cur, self.rank, self.world, self.k) if self.shard and self.world > 1 else cur
+            idx += 1
+            if last:
+                return
+
+
+def shard_batch(batch: dict, rank: int, world: int, queries_per_episode: int) -> dict:
+    """Rows of a collated episodic batch that belong to episodes ``rank::world`` (``episodic_collate_fn`` puts the K
+    queries of episode e — and its repeated support — at rows ``e*K .. (e+1)*K``, episodic_sampler.py:432-470)."""
+    k = queries_per_episode
+    n = None
+    for v in batch.values():
+        if isinstance(v, torch.Tensor):
+            n = v.shape[0]
+            break
+    if n is None or n % k:
+        raise ValueError("batch has no (B*K, ...) tensor or B*K is not a multiple of queries_per_episode")
+    rows = [e * k + j for e in shard_episodes(n // k, rank, world) for j in range(k)]
+    index = torch.tensor(rows, dtype=torch.long)
+
+    def take(v):
+        if isinstance(v, torch.Tensor) and v.dim() > 0 and v.shape[0] == n:
+            return v.index_select(0, index.to(v.device))
+        if isinstance(v, (list, tuple)) and len(v) == n:
+            return type(v)(v[r] for r in rows)
+        if isinstance(v, dict):
+            return {kk: take(vv) for kk, vv in v.items()}
+        return v
+    return {key: take(v) for key, v in batch.items()}
+
+
+def rank_seed(seed: int, rank: int) -> int:
+    """Seed of rank ``rank``'s own episodic sampler (``EpisodicSampler(seed=...)``, episodic_sampler.py:17-36) when every
+    rank draws its own episodes instead of slicing a global batch."""
+    return int(seed) + int(rank)
+
+
+def train_one_epoch_data_parallel(train_one_epoch, model, criterion, loader, optimizer, device, epoch: int,
+                                  buckets: GradBuckets, accumulation_steps: int = 1, max_norm: float = 0.0, scaler=None,
+                                  queries_per_episode: int = 2, shard: bool = True, **kwargs):
+    """Run the reference's own ``train_one_epoch_episodic`` (passed in as ``train_one_epoch``; engine_cape.py:48) as one
+    rank of a data-parallel job: the loader is sharded per rank, gradients are averaged over ranks from inside the last
+    backward of every accumulation window (before the loop's ``clip_grad_norm_`` and ``optimizer.step()``), and
+    ``optimizer.zero_grad()`` keeps the flat gradient views.  The loop itself is not edited."""
+    rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+    buckets.install()
+    buckets.wrap_optimizer(optimizer)
+    sharded = ShardedEpisodeLoader(loader, buckets, accumulation_steps, rank, world_size(), queries_per_episode, shard)
+    return train_one_epoch(model, criterion, sharded, optimizer, device, epoch, max_norm=max_norm,
+                           accumulation_steps=accumulation_steps, scaler=scaler, **kwargs)
 
 
 def shard_sizes(total: int, world: int) -> Sequence[int]:

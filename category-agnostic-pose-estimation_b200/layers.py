@@ -285,8 +285,13 @@ class IncrementalDecoder:
         if self._sup_mask is not None:
             self._sup_mask.copy_(support_mask)
         self._ctx = (self._shapes, self._starts, self._sup, self._sup_mask)
+        # derived weights are re-derived for every batch (a generator reused across optimizer steps must not decode
+        # with stale copies); they are written INTO the existing buffers so the captured graph's pointers survive
+        fresh = [self._prepare_layer(layer) for layer in self.layers]
         if getattr(self, "_prep", None) is None:
-            self._prep = [self._prepare_layer(layer) for layer in self.layers]
+            self._prep = fresh
+        elif not self._refresh(self._prep, fresh):
+            self.graph = None
         if self._sup is not None:   # support keys / values are constant while decoding: project them once per batch
             heads = self.layers[0].support_attn.num_heads
             if getattr(self, "_sup_k", None) is None or self._sup_k[0].shape[0] != n \
@@ -305,9 +310,43 @@ class IncrementalDecoder:
         self.pos.zero_()
 
     def invalidate(self):
-        """Forget derived weights and the captured graph (call after the layers' parameters change)."""
+        """Forget derived weights and the captured graph.  Not needed after ordinary weight updates (``reset`` refreshes
+        the derived tensors in place); use it after replacing layers or changing their shapes."""
         self._prep = None
         self.graph = None
+
+    @classmethod
+    def _refresh(cls, old, new) -> bool:
+        """Bring the derived-weight structure ``old`` up to date with the freshly derived ``new`` without changing any
+        tensor address a captured graph may hold: a tensor that is a live view of a parameter (same address) is left
+        alone, a derived copy is overwritten in place.  Returns False when an entry had to be REPLACED (different
+        shape / dtype / a re-allocated parameter), i.e. when the captured graph is no longer valid."""
+        stable = True
+        keys = old.keys() if isinstance(old, dict) else range(len(old))
+        for k in keys:
+            a, b = old[k], new[k]
+            if isinstance(a, torch.Tensor) and isinstance(b, torch.Tensor):
+                if a.data_ptr() == b.data_ptr() and a.shape == b.shape:
+                    continue
+                if a.shape == b.shape and a.dtype == b.dtype and a.device == b.device and a.is_contiguous() \
+                        and not isinstance(a, nn.Parameter) and a._base is None:
+                    a.copy_(b)
+                else:
+                    old[k] = b
+                    stable = False
+            elif isinstance(a, (dict, list)) and type(a) is type(b):
+                stable &= cls._refresh(a, b)
+            elif isinstance(a, tuple) and isinstance(b, tuple):      # (weight, bias, eps) of a LayerNorm: live parameters
+                same = len(a) == len(b) and all(
+                    (x.data_ptr() == y.data_ptr()) if isinstance(x, torch.Tensor) and isinstance(y, torch.Tensor) else x == y
+                    for x, y in zip(a, b))
+                if not same:
+                    old[k] = b
+                    stable = False
+            elif a is not b and a != b:
+                old[k] = b
+                stable = False
+        return stable
 
     def _prepare_layer(self, layer):
         """Per-layer constants of a decode step, derived once per ``reset`` from the layer's own parameters:

@@ -67,8 +67,15 @@ def _meta(t: torch.Tensor, device) -> torch.Tensor:
 def _aux(loc, attn, value_dtype):
     """The kernels take loc/attn either both fp32 or both in the value dtype."""
     if loc.dtype == attn.dtype and (loc.dtype == torch.float32 or loc.dtype == value_dtype):
-        return loc.contiguous(), attn.contiguous()
-    return loc.float().contiguous(), attn.float().contiguous()
+        return _c16(loc), _c16(attn)
+    return _c16(loc.float()), _c16(attn.float())
+
+
+def _c16(t: torch.Tensor) -> torch.Tensor:
+    """Contiguous AND 16-byte aligned (the kernels use 128-bit accesses): ``.contiguous()`` is a no-op on a contiguous
+    view with a storage offset (``loc[1:]``, a slice of a fused buffer), which the ABI would reject as misaligned."""
+    t = t.contiguous()
+    return t.clone() if t.data_ptr() % 16 else t
 
 
 def _ptr(t) -> ctypes.c_void_p:
@@ -86,7 +93,7 @@ def ms_deform_attn(value: torch.Tensor, spatial_shapes: torch.Tensor, level_star
     _check_shapes(value, spatial_shapes, level_start_index, sampling_locations, attention_weights)
     if value.dtype not in _DTYPE_CODE:
         raise TypeError(f"unsupported value dtype {value.dtype}")
-    value = value.contiguous()
+    value = _c16(value)
     loc, attn = _aux(sampling_locations, attention_weights, value.dtype)
     shapes = _meta(spatial_shapes, value.device)
     starts = _meta(level_start_index, value.device)
@@ -112,12 +119,12 @@ def ms_deform_attn_backward(grad_out: torch.Tensor, value: torch.Tensor, spatial
                             attention_weights: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     lib = _lib.load()
     _check_shapes(value, spatial_shapes, level_start_index, sampling_locations, attention_weights)
-    value = value.contiguous()
+    value = _c16(value)
     loc, attn = _aux(sampling_locations, attention_weights, value.dtype)
     shapes = _meta(spatial_shapes, value.device)
     starts = _meta(level_start_index, value.device)
     dims = _dims(value, loc)
-    grad_out = grad_out.to(value.dtype).contiguous()
+    grad_out = _c16(grad_out.to(value.dtype))
     grad_value = torch.empty(value.shape, dtype=torch.float32, device=value.device)   # zeroed by the library
     grad_loc = torch.empty_like(loc)
     grad_attn = torch.empty_like(attn)
@@ -166,10 +173,10 @@ def ms_deform_attn_decode(value_cache: torch.Tensor, spatial_shapes: torch.Tenso
         raise ValueError("attention_logits must have B*k*M*L*P elements")
     if value_cache.dtype not in _DTYPE_CODE:
         raise TypeError(f"unsupported value dtype {value_cache.dtype}")
-    value_cache = value_cache.contiguous()
-    ref = reference_points.float().contiguous()
-    off = sampling_offsets.float().contiguous()
-    logits = attention_logits.float().contiguous()
+    value_cache = _c16(value_cache)
+    ref = _c16(reference_points.float())
+    off = _c16(sampling_offsets.float())
+    logits = _c16(attention_logits.float())
     shapes = _meta(spatial_shapes, value_cache.device)
     starts = _meta(level_start_index, value_cache.device)
     dims = _lib.Dims(b, value_cache.shape[1], m, value_cache.shape[3], k, l, p)
@@ -195,14 +202,14 @@ def ms_deform_attn_fused_backward(grad_out: torch.Tensor, value: torch.Tensor, s
                                   ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     lib = _lib.load()
     b, k, m, l, p, _ = sampling_offsets.shape
-    value = value.contiguous()
+    value = _c16(value)
     dims = _lib.Dims(b, value.shape[1], m, value.shape[3], k, l, p)
     shapes = _meta(spatial_shapes, value.device)
     starts = _meta(level_start_index, value.device)
-    ref = reference_points.float().contiguous()
-    off = sampling_offsets.float().contiguous()
-    logits = attention_logits.float().contiguous()
-    grad_out = grad_out.to(value.dtype).contiguous()
+    ref = _c16(reference_points.float())
+    off = _c16(sampling_offsets.float())
+    logits = _c16(attention_logits.float())
+    grad_out = _c16(grad_out.to(value.dtype))
     if lib.cape_msda_fused_supported(ctypes.byref(dims)):
         grad_value = torch.empty(value.shape, dtype=torch.float32, device=value.device)
         grad_off = torch.empty_like(off)

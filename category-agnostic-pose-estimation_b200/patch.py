@@ -3,19 +3,35 @@
 ``MSDeformAttn.forward`` looks ``ms_deform_attn_core_pytorch`` up in its module's globals at call time
 (``/root/reference/models/deformable_transformer.py:112``), so rebinding that one name swaps the hot path under an
 unmodified ``CAPEModel`` — parameters, ``state_dict`` keys, ``forward`` / ``forward_inference`` API all untouched.
+
+Three levels, each a superset of the previous one:
+
+* ``patch_reference()``                              the sampling core only (training and inference);
+* ``patch_reference(swap_module_class=True)``        also the ``MSDeformAttn`` class for models built afterwards
+                                                     (fused prologue, ``use_cache`` honoured);
+* ``patch_reference(swap_forward_inference=True)``   also ``RoomFormerV2.forward_inference`` (``roomformer_v2.py:385-677``):
+                                                     the autoregressive loop runs device-resident on a mirror bound to the
+                                                     live module's own parameter tensors, and returns the reference's dict,
+                                                     so ``CAPEModel.forward_inference`` (``cape_model.py:142-209``) is
+                                                     called unchanged.
 """
 from __future__ import annotations
 
 import importlib
 from typing import Optional
 
+import torch
+import torch.nn.functional as F
+
 from . import functional as CF
 from .modules import MSDeformAttn
 
 _ORIGINALS = {}
+_INFERENCE_ORIGINALS = {}
+_GEN_ATTR = "_cape_b200_generation"      # plain attribute on the live module: never a submodule, buffer or parameter
 
 
-def patch_reference(module=None, swap_module_class: bool = False):
+def patch_reference(module=None, swap_module_class: bool = False, swap_forward_inference: bool = False):
     """Rebind the reference's sampling core to the B200 op.
 
     module: the imported ``models.deformable_transformer`` module object (or its dotted name; default
@@ -23,6 +39,8 @@ def patch_reference(module=None, swap_module_class: bool = False):
     swap_module_class: also replace the ``MSDeformAttn`` class (in that module and in
         ``models.deformable_transformer_v2``, which imports it by name, :17) by the mirror that honours
         ``use_cache`` and fuses the decode prologue.  Only affects models built after the call.
+    swap_forward_inference: also replace ``RoomFormerV2.forward_inference`` in the sibling ``roomformer_v2`` module
+        by :func:`forward_inference` below.  Affects existing model objects too (the method is looked up on the class).
     Returns the patched module.
     """
     if module is None or isinstance(module, str):
@@ -31,15 +49,23 @@ def patch_reference(module=None, swap_module_class: bool = False):
     if key not in _ORIGINALS:
         _ORIGINALS[key] = (module, module.ms_deform_attn_core_pytorch, getattr(module, "MSDeformAttn", None))
     module.ms_deform_attn_core_pytorch = CF.ms_deform_attn_core_pytorch
+    package = module.__name__.rsplit(".", 1)[0] if "." in module.__name__ else ""
+    sibling = lambda name: importlib.import_module((package + "." if package else "") + name)
     if swap_module_class:
         module.MSDeformAttn = MSDeformAttn
         try:
-            v2 = importlib.import_module(module.__name__.rsplit(".", 1)[0] + ".deformable_transformer_v2")
+            v2 = sibling("deformable_transformer_v2")
             if hasattr(v2, "MSDeformAttn"):
                 _ORIGINALS.setdefault(id(v2), (v2, None, v2.MSDeformAttn))
                 v2.MSDeformAttn = MSDeformAttn
         except Exception:
             pass
+    if swap_forward_inference:
+        rf = sibling("roomformer_v2")
+        cls = rf.RoomFormerV2
+        if id(cls) not in _INFERENCE_ORIGINALS:
+            _INFERENCE_ORIGINALS[id(cls)] = (cls, cls.forward_inference)
+            cls.forward_inference = _make_forward_inference(rf, cls.forward_inference)
     return module
 
 
@@ -53,3 +79,88 @@ def unpatch_reference(module: Optional[object] = None):
                 mod.ms_deform_attn_core_pytorch = core
             if cls is not None:
                 mod.MSDeformAttn = cls
+    if module is None:
+        for cls, original in _INFERENCE_ORIGINALS.values():
+            cls.forward_inference = original
+        _INFERENCE_ORIGINALS.clear()
+
+
+# ---- RoomFormerV2.forward_inference, device-resident ----------------------------------------------------------------
+def _feature_pyramid(model, samples, rf):
+    """Backbone + input projections + extra levels: what ``forward_inference`` does before the decoder part
+    (roomformer_v2.py:403-440).  Uses the live model's own backbone / ``input_proj`` modules."""
+    nested = rf.NestedTensor
+    if not isinstance(samples, nested):
+        samples = rf.nested_tensor_from_tensor_list(samples)
+    features, pos = model.backbone(samples)
+    srcs, masks = [], []
+    for l, feat in enumerate(features):
+        src, mask = feat.decompose()
+        src = model.input_proj[l](src)
+        srcs.append(src)
+        if model.patch_size != 1:
+            mask = F.interpolate(mask[None].float(), size=src.shape[-2:]).to(torch.bool)[0]
+            pos[l] = model.backbone[1](nested(src, mask)).to(src.dtype)
+        masks.append(mask)
+    for l in range(len(srcs), model.num_feature_levels):
+        src = model.input_proj[l](features[-1].tensors if l == len(features) else srcs[-1])
+        mask = F.interpolate(samples.mask[None].float(), size=src.shape[-2:]).to(torch.bool)[0]
+        pos.append(model.backbone[1](nested(src, mask)).to(src.dtype))
+        srcs.append(src)
+        masks.append(mask)
+    return srcs, masks, pos
+
+
+def _generation_state(model, batch: int, device):
+    """Mirror transformer bound to ``model.transformer``'s own tensors + one generator per batch size, cached on the
+    live module as a plain attribute (``state_dict()`` unaffected).  Rebuilt when the live parameters were re-allocated."""
+    from .sequence import TokenizerSpec
+    from .transformer import AutoregressiveGenerator, mirror_from_reference, mirror_is_current
+    state = model.__dict__.get(_GEN_ATTR)
+    if state is None or not mirror_is_current(state["mirror"], model.transformer):
+        state = {"mirror": mirror_from_reference(model.transformer), "generators": {}}
+        model.__dict__[_GEN_ATTR] = state
+    mirror = state["mirror"]
+    mirror.train(False)
+    key = (batch, str(device))
+    gen = state["generators"].get(key)
+    if gen is None:
+        spec = TokenizerSpec.from_tokenizer(model.tokenizer)
+        gen = AutoregressiveGenerator(mirror, spec, batch, device)
+        state["generators"] = {key: gen}          # one resident generator: its K/V + value caches are batch-sized
+    return mirror, gen
+
+
+def _make_forward_inference(rf, original):
+    def forward_inference(self, samples, use_cache=True, support_graphs=None, support_mask=None):
+        """Drop-in for ``RoomFormerV2.forward_inference`` (roomformer_v2.py:385-677): same arguments, same result dict
+        (``pred_logits`` (B, steps, n_classes), ``pred_coords`` (B, steps, 2), ``gen_out``).  The decoder part — the
+        ``while i < max_len and unfinish_flag.any()`` loop with its per-sample Python bookkeeping (:481-598) — runs as
+        one CUDA graph per token on the device.  Configurations outside the mirror (CPU tensors, ``cape_mode`` with an
+        internal support encoder, room classes, ``use_cache=False``, decoder layers other than v1) take the reference's
+        own loop, which still samples through the patched core."""
+        tensors = samples.tensors if hasattr(samples, "tensors") else samples
+        unsupported = (not isinstance(tensors, torch.Tensor) or not tensors.is_cuda or not use_cache
+                       or (getattr(self, "cape_mode", False) and support_graphs is not None)
+                       or getattr(self, "room_class_embed", None) is not None or self.query_embed is None
+                       or getattr(self, "tokenizer", None) is None)
+        if not unsupported:
+            try:
+                from .transformer import _reference_transformer_config
+                _reference_transformer_config(self.transformer)
+            except NotImplementedError:
+                unsupported = True
+        if unsupported:
+            return original(self, samples, use_cache=use_cache, support_graphs=support_graphs, support_mask=support_mask)
+        with torch.no_grad():
+            srcs, masks, pos = _feature_pyramid(self, samples, rf)
+            bs = srcs[0].shape[0]
+            mirror, gen = _generation_state(self, bs, srcs[0].device)
+            dec = self.transformer.decoder
+            out = gen.generate(srcs, masks, pos, self.query_embed.weight,
+                               support_features=getattr(dec, "support_features", None),
+                               support_mask=getattr(dec, "support_mask", None))
+        return {"pred_logits": out["pred_logits"], "pred_coords": out["pred_coords"], "gen_out": out["gen_out"]}
+
+    forward_inference.__wrapped__ = original
+    return forward_inference

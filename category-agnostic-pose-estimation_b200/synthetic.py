@@ -149,3 +149,75 @@ def fill_parameters_(module, seed: int = 0, gain: float = 1.0) -> float:
             p.copy_(torch.from_numpy(w).to(p.device, p.dtype))
             total += float(abs(w.astype("float64")).sum())
     return total
+
+
+# ---- synthetic MP-100-shaped episodes (BASELINE.json configs 1, 3, 4, 5) ---------------------------
+def tokenize_keypoints(kpts_norm, num_bins: int = 44, seq_len: int = 200) -> dict:
+    """Targets of one query exactly as the reference's dataset builds them (``datasets/mp100_cape.py:625-832`` with
+    ``DiscreteTokenizerV2(num_bins, seq_len)``, ``datasets/discrete_tokenizer.py``): 4 index sequences + 4 deltas for the
+    bilinear token embedding, ``target_seq``, ``token_labels`` (0 coord, 2 eos, -1 pad), ``mask``, ``visibility_mask``.
+    ``kpts_norm``: (K, 2) float64 array of (x, y) in [0, 1]; all keypoints visible."""
+    import numpy as np
+    k = int(kpts_norm.shape[0])
+    vocab = num_bins * num_bins
+    bos, pad = vocab, vocab + 3
+    q = np.clip(np.asarray(kpts_norm, dtype=np.float64) * (num_bins - 1), 0, num_bins - 1)
+    fl = np.clip(np.floor(q), 0, num_bins - 1).astype(np.int64)
+    ce = np.clip(np.ceil(q), 0, num_bins - 1).astype(np.int64)
+
+    def seq(ix, iy):
+        body = (ix * num_bins + iy).tolist()
+        if 1 + len(body) + 1 > seq_len:                       # the tokenizer drops a polygon that does not fit
+            body = []
+        out = [bos] + body
+        return torch.tensor(out + [pad] * (seq_len - len(out)), dtype=torch.long)
+
+    def padded(values, fill, dtype):
+        values = list(values)
+        return torch.tensor(np.array(values + [fill] * (seq_len - len(values))), dtype=dtype)
+
+    labels = [0] * k + [2]                                    # coords then <eos> (the last <sep> becomes <eos>)
+    target = [list(map(float, p)) for p in np.asarray(kpts_norm, dtype=np.float64)] + [[0.0, 0.0]]
+    mask = torch.zeros(seq_len, dtype=torch.bool)
+    mask[:len(labels)] = True
+    vis = torch.zeros(seq_len, dtype=torch.bool)
+    vis[:k + 1] = True                                        # every keypoint visible + the first <eos>
+    dx = [0.0] + (q[:, 0] - np.floor(q[:, 0])).tolist()
+    dy = [0.0] + (q[:, 1] - np.floor(q[:, 1])).tolist()
+    delta_x1, delta_y1 = padded(dx, 0, torch.float32), padded(dy, 0, torch.float32)
+    poly_labels = torch.full((seq_len,), -1, dtype=torch.long)
+    poly_labels[:min(k, seq_len)] = 0
+    return {"seq11": seq(fl[:, 0], fl[:, 1]), "seq21": seq(ce[:, 0], fl[:, 1]), "seq12": seq(fl[:, 0], ce[:, 1]),
+            "seq22": seq(ce[:, 0], ce[:, 1]), "target_seq": padded(target, [0.0, 0.0], torch.float32),
+            "token_labels": padded(labels, -1, torch.long), "mask": mask, "visibility_mask": vis,
+            "target_polygon_labels": poly_labels, "delta_x1": delta_x1, "delta_x2": 1 - delta_x1,
+            "delta_y1": delta_y1, "delta_y2": 1 - delta_y1}
+
+
+def make_episode_batch(num_episodes: int, queries_per_episode: int = 2, num_keypoints: int = 17, shots: int = 1,
+                       image_size: int = 512, seed: int = 0, num_bins: int = 44, seq_len: int = 200,
+                       with_images: bool = True) -> dict:
+    """One collated batch of synthetic MP-100-shaped episodes, laid out like ``episodic_collate_fn``'s output
+    (``datasets/episodic_sampler.py:353-480``): every tensor has first dimension episodes x queries; the support of an
+    episode is the mean of its ``shots`` support draws (:439-442) repeated once per query; mask convention True = ignore
+    (:280-284), all keypoints valid; chain skeleton.  Query images U(0, 1); query keypoints = support + N(0, 0.05)."""
+    import numpy as np
+    rng = np.random.RandomState(seed)
+    n = num_episodes * queries_per_episode
+    support = rng.uniform(0.05, 0.95, size=(num_episodes, shots, num_keypoints, 2)).mean(1)      # (B, K, 2)
+    support_coords = torch.from_numpy(np.repeat(support, queries_per_episode, axis=0)).float()
+    support_masks = torch.zeros(n, num_keypoints, dtype=torch.bool)
+    skeleton = [[i, i + 1] for i in range(num_keypoints - 1)]
+    targets = []
+    for e in range(num_episodes):
+        for _ in range(queries_per_episode):
+            kp = np.clip(support[e] + rng.normal(0, 0.05, size=(num_keypoints, 2)), 0.0, 1.0)
+            targets.append(tokenize_keypoints(kp, num_bins, seq_len))
+    batch = {"support_images": None, "support_coords": support_coords, "support_masks": support_masks,
+             "support_skeletons": [skeleton for _ in range(n)],
+             "query_targets": {k: torch.stack([t[k] for t in targets]) for k in targets[0]},
+             "category_ids": torch.arange(num_episodes).repeat_interleave(queries_per_episode)}
+    if with_images:
+        g = torch.Generator().manual_seed(seed)
+        batch["query_images"] = torch.rand(n, 3, image_size, image_size, generator=g)
+    return batch

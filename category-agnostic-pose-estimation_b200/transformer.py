@@ -471,10 +471,13 @@ class AutoregressiveGenerator(IncrementalDecoder):
             self.valid_ratios = torch.empty_like(enc_cache["valid_ratios"])
             self.graph = None
         self.valid_ratios.copy_(enc_cache["valid_ratios"])
-        self.ref_table.copy_(query_embed.sigmoid())                                          # :227
+        self.ref_table.copy_(query_embed[:self.spec.seq_len].sigmoid())                      # :227 (the loop stops at tokenizer.seq_len)
         if self.fused:
+            fresh = self._prepare_fused()                 # re-derived per batch, written into the captured buffers
             if self._fprep is None:
-                self._fprep = self._prepare_fused()
+                self._fprep = fresh
+                self.graph = None
+            elif not self._refresh(self._fprep, fresh):
                 self.graph = None
             if self._sup is not None:   # support K / V as (B, T, C) rows for the attention kernel
                 to_rows = lambda t: t.transpose(1, 2).reshape(t.shape[0], t.shape[2], -1)
@@ -605,3 +608,65 @@ def load_reference_checkpoint(transformer: DeformableTransformer, model_state: d
     missing, unexpected = transformer.load_state_dict(state, strict=False)
     query = model_state.get((outer or "") + "query_embed.weight")
     return query, list(missing), list(unexpected)
+
+
+# ---- binding the mirror to a live reference model (patch_reference(..., swap_forward_inference=True)) -------------
+_ACTIVATION_NAMES = {F.relu: "relu", F.gelu: "gelu", F.glu: "glu"}
+
+
+def _reference_transformer_config(ref) -> dict:
+    """Constructor arguments of the reference ``DeformableTransformer`` (deformable_transformer_v2.py:56-62) read back
+    from a live instance.  Raises NotImplementedError for the configurations the mirror does not cover."""
+    dec, enc = ref.decoder, ref.encoder
+    layer0 = dec.layers[0]
+    if type(layer0).__name__ != "TransformerDecoderLayer":
+        raise NotImplementedError(f"decoder layer {type(layer0).__name__}: only 'v1' is mirrored (the only one CAPE can run)")
+    if getattr(ref, "inject_cls_embed", False) or getattr(dec, "room_class_embed", None) is not None:
+        raise NotImplementedError("inject_cls_embed / room classes are outside the CAPE path")
+    ca = layer0.cross_attn
+    return dict(
+        d_model=ref.d_model, nhead=ref.nhead, num_encoder_layers=enc.num_layers, num_decoder_layers=dec.num_layers,
+        dim_feedforward=layer0.linear1.out_features, dropout=float(layer0.dropout1.p),
+        activation=_ACTIVATION_NAMES[layer0.activation], poly_refine=bool(ref.poly_refine),
+        return_intermediate_dec=bool(dec.return_intermediate), aux_loss=bool(dec.aux_loss),
+        num_feature_levels=int(ref.level_embed.shape[0]), dec_n_points=int(ca.n_points),
+        enc_n_points=int(enc.layers[0].self_attn.n_points), query_pos_type=dec.query_pos_type,
+        vocab_size=int(dec.token_embed.num_embeddings), seq_len=int(ref.pos_embed.shape[1]),
+        pre_decoder_pos_embed=bool(ref.pre_decoder_pos_embed), learnable_dec_pe=bool(ref.pos_embed.requires_grad),
+        dec_attn_concat_src=bool(ref.dec_attn_concat_src), dec_qkv_proj=isinstance(layer0.attn_q, nn.Linear),
+        dec_layer_type="v1", pad_idx=dec.token_embed.padding_idx, use_anchor=bool(ref.use_anchor))
+
+
+def _live_transformer_state(ref) -> dict:
+    """``ref.state_dict()`` without the cache buffers the reference's ``_setup_caches`` registers on every
+    ``forward_inference`` and without the heads (attached as live modules instead)."""
+    return {k: v for k, v in ref.state_dict().items()
+            if ".kv_cache." not in k and ".cross_attn.cache." not in k
+            and not k.startswith(("decoder.class_embed.", "decoder.coords_embed."))}
+
+
+def mirror_from_reference(ref) -> DeformableTransformer:
+    """A :class:`DeformableTransformer` whose parameters ARE the live reference transformer's tensors (same storage:
+    ``load_state_dict(assign=True)``), so optimizer steps and in-place loads on the reference are seen without a copy.
+    The prediction heads are the reference's own modules (roomformer_v2.py:245-246).  Use :func:`mirror_is_current`
+    to detect a re-allocation (``model.to(...)``, a non-in-place load) and rebuild."""
+    with torch.device("meta"):
+        mirror = DeformableTransformer(**_reference_transformer_config(ref))
+    state = _live_transformer_state(ref)
+    missing, unexpected = mirror.load_state_dict(state, strict=False, assign=True)
+    missing = [k for k in missing if not k.startswith(("decoder.class_embed.", "decoder.coords_embed."))]
+    if missing or unexpected:
+        raise RuntimeError(f"reference transformer does not match the mirror: missing {missing[:5]}, "
+                           f"unexpected {unexpected[:5]}")
+    mirror.attach_heads(ref.decoder.class_embed, ref.decoder.coords_embed)
+    mirror.train(ref.training)
+    mirror._bound_ptrs = {k: v.data_ptr() for k, v in state.items()}
+    return mirror
+
+
+def mirror_is_current(mirror: DeformableTransformer, ref) -> bool:
+    ptrs = getattr(mirror, "_bound_ptrs", None)
+    if ptrs is None:
+        return False
+    state = _live_transformer_state(ref)
+    return len(state) == len(ptrs) and all(ptrs.get(k) == v.data_ptr() for k, v in state.items())

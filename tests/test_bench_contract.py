@@ -25,7 +25,12 @@ def test_reference_arm_prints_one_contract_line():
     assert d["impl"] == "reference" and d["metric"] == "msda_fwd_bwd_achieved_hbm_gbps" and d["unit"] == "GB/s"
     assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["dtype"] == "f32"
     assert d["e2e"] == {"value": d["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    # the unmodified reference function when it is staged (baseline/_ref) or present (/root/reference), else the port
+    sys.path.insert(0, os.path.join(REPO, "tools"))
+    import stage_reference
+    assert d["cpu_baseline"]["kind"] == ("reference" if stage_reference.available() else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and "N=20" in d["cpu_baseline"]["sample"]
+    assert "N=20" in d["config"]["workload"]                       # the arm runs the configuration it states
     assert "workload" in d["config"] and "model" not in d["config"]
     assert d["value"] > 0
 

@@ -1,0 +1,200 @@
+"""The UNMODIFIED reference model (CAPEModel around RoomFormerV2, staged by tools/stage_reference.py) with the hot path
+swapped in by ``patch_reference`` — SURVEY.md §8c items (iii) module-swapped parity and (iv) model parity:
+``CAPEModel.forward`` outputs / loss / gradients, ``state_dict().keys()``, and ``CAPEModel.forward_inference`` token
+sequences, patched vs unpatched on the same GPU, same weights, same seeded synthetic episodes (eval mode: dropout off).
+
+Runs on the GPU box from ``baseline/_ref`` (git-ignored, staged in the build container); skipped when the reference is
+not available.
+"""
+import os
+import sys
+
+import pytest
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(REPO, "tools"))
+import stage_reference  # noqa: E402
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not stage_reference.available(),
+                                                  reason="reference not staged (python tools/stage_reference.py)")]
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return torch.device("cuda", 0)
+
+
+def _perturb(model, seed=5):
+    """Default init leaves the MSDeformAttn offset / weight projections at zero (uniform weights, fixed offsets): add
+    seeded noise so sampling locations and attention weights depend on the queries."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if "sampling_offsets.weight" in name or "attention_weights.weight" in name:
+                p.add_((torch.randn(p.shape, generator=g) * 0.05).to(p.device))
+            elif "class_embed" in name and name.endswith("weight"):
+                p.mul_(8.0)                      # make the token-type argmax depend on the hidden state
+
+
+@pytest.fixture(scope="module")
+def built(dev):
+    import cape_b200
+    model, criterion, args, tok = stage_reference.build_cape_model(dev, seed=0)
+    _perturb(model)
+    model.eval()
+    criterion.eval()
+    batch = cape_b200.synthetic.make_episode_batch(2, 2, num_keypoints=17, shots=1, seed=3)
+    return model, criterion, args, tok, batch
+
+
+def _to(batch, dev):
+    targets = {k: v.to(dev) for k, v in batch["query_targets"].items()}
+    return (batch["query_images"].to(dev), batch["support_coords"].to(dev), batch["support_masks"].to(dev),
+            targets, batch["support_skeletons"])
+
+
+def _loss(criterion, outputs, targets):
+    loss_dict = criterion(outputs, targets)
+    w = criterion.weight_dict
+    return sum(loss_dict[k] * w[k] for k in loss_dict if k in w)
+
+
+def _rel(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+
+def test_forward_loss_and_gradients_match_the_unpatched_model(built, dev):
+    """CAPEModel.forward (cape_model.py:79-141) + CAPESetCriterion, teacher forced, N = 4 queries."""
+    import cape_b200
+    model, criterion, _, _, batch = built
+    images, sup, mask, targets, skel = _to(batch, dev)
+    watch = ["base_model.input_proj.0.0.weight", "base_model.transformer.encoder.layers.0.self_attn.value_proj.weight",
+             "base_model.transformer.encoder.layers.5.self_attn.sampling_offsets.weight",
+             "base_model.transformer.decoder.layers.2.cross_attn.attention_weights.weight",
+             "base_model.transformer.level_embed", "base_model.query_embed.weight"]
+    params = dict(model.named_parameters())
+
+    def run():
+        model.zero_grad(set_to_none=True)
+        out = model(samples=images, support_coords=sup, support_mask=mask, targets=targets, skeleton_edges=skel)
+        loss = _loss(criterion, out, targets)
+        loss.backward()
+        return out, loss.detach(), {k: params[k].grad.detach().clone() for k in watch}
+
+    keys_before = list(model.state_dict().keys())
+    want_out, want_loss, want_g = run()
+    launches0 = cape_b200.launch_count()
+    cape_b200.patch_reference(sys.modules["models.deformable_transformer"])
+    try:
+        got_out, got_loss, got_g = run()
+    finally:
+        cape_b200.unpatch_reference()
+    assert cape_b200.launch_count() - launches0 >= 24            # 12 MSDeformAttn modules, forward + backward kernels
+    assert list(model.state_dict().keys()) == keys_before
+    assert _rel(got_out["pred_logits"], want_out["pred_logits"]) < 1e-4
+    assert _rel(got_out["pred_coords"], want_out["pred_coords"]) < 1e-4
+    assert len(got_out["aux_outputs"]) == len(want_out["aux_outputs"])
+    assert abs(float(got_loss) - float(want_loss)) < 1e-4 * abs(float(want_loss))
+    for k in watch:
+        assert _rel(got_g[k], want_g[k]) < 2e-3, k               # fp32 through 12 layers + ResNet; atomics order differs
+
+
+def test_swapped_module_class_builds_the_same_model(built, dev):
+    """patch_reference(swap_module_class=True): a model built afterwards uses the mirror MSDeformAttn (fused prologue,
+    use_cache honoured), has the same state_dict layout and produces the same outputs from the same weights."""
+    import cape_b200
+    model, _, _, _, batch = built
+    images, sup, mask, targets, skel = _to(batch, dev)
+    with torch.no_grad():
+        want = model(samples=images, support_coords=sup, support_mask=mask, targets=targets, skeleton_edges=skel)
+    cape_b200.patch_reference(sys.modules["models.deformable_transformer"], swap_module_class=True)
+    try:
+        swapped, _, _, _ = stage_reference.build_cape_model(dev, seed=1)
+        mods = [m for m in swapped.modules() if type(m).__name__ == "MSDeformAttn"]
+        assert len(mods) == 12 and all(isinstance(m, cape_b200.MSDeformAttn) for m in mods)
+        assert list(swapped.state_dict().keys()) == list(model.state_dict().keys())
+        swapped.load_state_dict(model.state_dict())
+        swapped.eval()
+        with torch.no_grad():
+            got = swapped(samples=images, support_coords=sup, support_mask=mask, targets=targets, skeleton_edges=skel)
+    finally:
+        cape_b200.unpatch_reference()
+    assert _rel(got["pred_logits"], want["pred_logits"]) < 1e-4
+    assert _rel(got["pred_coords"], want["pred_coords"]) < 1e-4
+
+
+def _same_tokens(got, want, want_logits):
+    """Token sequences must agree wherever the reference's own argmax is not a numerical coin flip."""
+    top2 = want_logits.float().topk(2, dim=-1).values
+    decided = (top2[..., 0] - top2[..., 1]) > 1e-3
+    steps = min(got.shape[1], want.shape[1])
+    return bool((got[:, :steps] == want[:, :steps])[decided[:, :steps]].all()), float(decided.float().mean())
+
+
+def test_forward_inference_tokens_match_the_unpatched_model(built, dev):
+    """CAPEModel.forward_inference (cape_model.py:142-209) called UNCHANGED: (a) reference loop + patched core,
+    (b) patch_reference(swap_forward_inference=True): the device-resident generator behind the same method."""
+    import cape_b200
+    model, _, _, tok, batch = built
+    images, sup, mask, _, skel = _to(batch, dev)
+    keys_before = [k for k in model.state_dict().keys() if "cache" not in k]
+
+    def run():
+        with torch.no_grad():
+            return model.forward_inference(images, sup, mask, skeleton_edges=skel)
+    want = run()
+    assert want["logits"].shape[1] == tok.seq_len or want["logits"].shape[1] >= 7
+    mod = sys.modules["models.deformable_transformer"]
+    cape_b200.patch_reference(mod)
+    try:
+        core = run()
+        cape_b200.patch_reference(mod, swap_forward_inference=True)
+        launches0 = cape_b200.launch_count()
+        fast = run()
+        fast_again = run()                                        # second call reuses the captured graph
+        assert cape_b200.launch_count() > launches0
+    finally:
+        cape_b200.unpatch_reference()
+    assert sys.modules["models.roomformer_v2"].RoomFormerV2.forward_inference.__name__ == "forward_inference"
+    assert not hasattr(sys.modules["models.roomformer_v2"].RoomFormerV2.forward_inference, "__wrapped__")
+    for name, got in (("core", core), ("fast", fast), ("fast_again", fast_again)):
+        assert set(got) == {"sequences", "coordinates", "logits"}, name
+        assert got["logits"].shape == want["logits"].shape, (name, got["logits"].shape, want["logits"].shape)
+        ok, decided = _same_tokens(got["sequences"], want["sequences"], want["logits"])
+        assert ok and decided > 0.95, (name, decided)
+        assert _rel(got["coordinates"], want["coordinates"]) < 1e-3, name
+        assert _rel(got["logits"], want["logits"]) < 1e-3, name
+    assert [k for k in model.state_dict().keys() if "cache" not in k] == keys_before
+
+
+def test_generator_follows_weight_updates_without_invalidate(built, dev):
+    """a generator reused after an optimizer step must decode with the NEW weights (derived tensors are
+    refreshed in place on every batch)."""
+    import cape_b200
+    model, _, _, _, batch = built
+    images, sup, mask, _, skel = _to(batch, dev)
+    mod = sys.modules["models.deformable_transformer"]
+    cape_b200.patch_reference(mod, swap_forward_inference=True)
+    try:
+        with torch.no_grad():
+            before = model.forward_inference(images, sup, mask, skeleton_edges=skel)
+            layer = model.base_model.transformer.decoder.layers[0]
+            saved = {n: p.detach().clone() for n, p in layer.named_parameters()}
+            g = torch.Generator().manual_seed(9)
+            for p in layer.parameters():                          # what an optimizer step does: in-place update
+                p.add_((torch.randn(p.shape, generator=g) * 0.05).to(dev))
+            after = model.forward_inference(images, sup, mask, skeleton_edges=skel)
+            cape_b200.unpatch_reference()
+            cape_b200.patch_reference(mod)                        # reference loop, patched core: the checker here
+            want = model.forward_inference(images, sup, mask, skeleton_edges=skel)
+            for n, p in layer.named_parameters():
+                p.copy_(saved[n])
+    finally:
+        cape_b200.unpatch_reference()
+    assert _rel(after["logits"], want["logits"]) < 1e-3
+    assert _rel(after["logits"], before["logits"]) > 1e-2         # the update really changed the result

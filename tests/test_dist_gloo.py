@@ -149,3 +149,106 @@ def test_checkpoint_layout_is_the_reference_dict_and_resume_restores_everything(
     assert opt2.param_groups[0]["lr"] == opt.param_groups[0]["lr"] and sched2.last_epoch == sched.last_epoch
     got = (torch.rand(3), np.random.rand(3), random.random())
     assert torch.equal(got[0], expect[0]) and np.array_equal(got[1], expect[1]) and got[2] == expect[2]
+
+
+# ---- GradBuckets: gradients as views, all-reduce launched from inside the last backward of an accumulation window ------
+def _toy_batches(n_batches, episodes=4, k=2):
+    g = torch.Generator().manual_seed(7)
+    return [{"x": torch.randn(episodes * k, 4, generator=g), "tag": [f"b{i}r{r}" for r in range(episodes * k)],
+             "nested": {"y": torch.randn(episodes * k, 2, generator=g)}} for i in range(n_batches)]
+
+
+def _toy_model():
+    torch.manual_seed(11)
+    model = torch.nn.Sequential(torch.nn.Linear(4, 8), torch.nn.Tanh(), torch.nn.Linear(8, 2))
+    model.register_parameter("never_used", torch.nn.Parameter(torch.ones(5)))
+    return model
+
+
+def _reference_shaped_loop(model, loader, optimizer, accumulation_steps, max_norm):
+    """The control flow of engine_cape.py:88-290: zero_grad, backward per micro-batch with the loss divided by the
+    accumulation steps, clip + step + zero_grad every `accumulation_steps` batches and once more for a ragged tail."""
+    optimizer.zero_grad()
+    idx = -1
+    for idx, batch in enumerate(loader):
+        loss = ((model(batch["x"]) - batch["nested"]["y"]) ** 2).mean()
+        (loss / accumulation_steps).backward()
+        if (idx + 1) % accumulation_steps == 0:
+            torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm)
+            optimizer.step()
+            optimizer.zero_grad()
+    if (idx + 1) % accumulation_steps != 0:
+        torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm)
+        optimizer.step()
+        optimizer.zero_grad()
+
+
+def _bucket_worker(rank, world, port, out):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from cape_b200 import dist as cdist
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    cdist.init_from_env("gloo")
+    model = _toy_model()
+    opt = torch.optim.AdamW(model.parameters(), lr=0.05, weight_decay=0.1)
+    buckets = cdist.GradBuckets(model.parameters(), bucket_bytes=64)          # several tiny buckets
+    n_buckets_first = len(buckets.buckets)
+    loader = _toy_batches(7)                                                   # 7 batches, accumulation 3: ragged tail
+
+    def engine(model, criterion, loader, optimizer, device, epoch, max_norm=0, accumulation_steps=1, scaler=None):
+        _reference_shaped_loop(model, loader, optimizer, accumulation_steps, max_norm)
+
+    cdist.train_one_epoch_data_parallel(engine, model, None, loader, opt, "cpu", 0, buckets, accumulation_steps=3,
+                                        max_norm=0.5, queries_per_episode=2)
+    cdist.barrier()
+    out.put((rank, {k: v.tolist() for k, v in model.state_dict().items()}, n_buckets_first, buckets.known,
+             model.never_used.grad is None))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(240)
+def test_grad_buckets_overlapped_allreduce_matches_single_process_training():
+    """Two ranks, each on its episodes rank::2 of every global batch, must end with the weights of ONE process training
+    on the whole batches — through gradient accumulation, clipping, a ragged last window and a never-used parameter."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = sorted((q.get(timeout=200) for _ in procs), key=lambda r: r[0])
+    for p in procs:
+        p.join(30)
+        assert p.exitcode == 0
+    # single process on the full batches: mean over 8 rows == mean of the two ranks' 4-row means
+    model = _toy_model()
+    opt = torch.optim.AdamW(model.parameters(), lr=0.05, weight_decay=0.1)
+    _reference_shaped_loop(model, _toy_batches(7), opt, 3, 0.5)
+    want = model.state_dict()
+    for rank, state, n_buckets, known, unused_none in results:
+        assert n_buckets > 1 and known and unused_none
+        for k in want:
+            assert torch.allclose(torch.tensor(state[k]), want[k], atol=1e-6), (rank, k)
+    assert torch.equal(want["never_used"], torch.ones(5))                      # untouched: no decay on a None gradient
+
+
+def test_shard_batch_and_sync_schedule():
+    from cape_b200 import dist as cdist
+    batch = _toy_batches(1, episodes=3, k=2)[0]
+    s1 = cdist.shard_batch(batch, 1, 2, 2)
+    assert s1["tag"] == ["b0r2", "b0r3"] and torch.equal(s1["x"], batch["x"][2:4])
+    assert torch.equal(s1["nested"]["y"], batch["nested"]["y"][2:4])
+    s0 = cdist.shard_batch(batch, 0, 2, 2)
+    assert s0["tag"] == ["b0r0", "b0r1", "b0r4", "b0r5"]
+
+    class Spy:
+        def __init__(self):
+            self.flags = []
+
+        def begin_micro_batch(self, sync):
+            self.flags.append(sync)
+    spy = Spy()
+    assert len(list(cdist.ShardedEpisodeLoader(_toy_batches(5), spy, accumulation_steps=2))) == 5
+    assert spy.flags == [False, True, False, True, True]                       # step after 2, 4 and the ragged 5th
+    assert cdist.rank_seed(42, 3) == 45

@@ -1,0 +1,130 @@
+"""Host logic around the unmodified reference model that needs no GPU: staging recipe, synthetic episodes vs the
+reference's own tokenisation, binding the mirror transformer to a live model's tensors, and the feature-pyramid
+prologue of the ``forward_inference`` drop-in vs what the reference hands its transformer."""
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(REPO, "tools"))
+import stage_reference  # noqa: E402
+
+pytestmark = pytest.mark.skipif(not stage_reference.available(), reason="reference not available on this machine")
+
+
+@pytest.fixture(scope="module")
+def model():
+    m, _, _, _ = stage_reference.build_cape_model("cpu", seed=0)
+    return m.eval()
+
+
+def test_staged_tree_is_ignored_by_git_and_complete():
+    root = stage_reference.root()
+    for rel in ("models/deformable_transformer.py", "models/cape_model.py", "models/engine_cape.py", "util/misc.py",
+                "datasets/discrete_tokenizer.py"):
+        assert os.path.exists(os.path.join(root, rel)), rel
+    with open(os.path.join(REPO, ".gitignore")) as f:
+        assert "baseline/_ref/" in f.read()
+    ignore = os.path.join(REPO, ".gpurunignore")
+    if os.path.exists(ignore):
+        with open(ignore) as f:
+            assert "baseline" not in f.read()              # the staged reference must travel to the GPU box
+
+
+def test_synthetic_targets_equal_the_reference_tokenisation():
+    import cape_b200
+    stage_reference.activate()
+    from datasets.discrete_tokenizer import DiscreteTokenizerV2
+    from datasets.mp100_cape import MP100CAPE
+    fake = types.SimpleNamespace(tokenizer=DiscreteTokenizerV2(44, 200, add_cls=False))
+    rng = np.random.RandomState(0)
+    for k in (1, 9, 17, 100):
+        kp = rng.uniform(0, 1, size=(k, 2))
+        kp[0] = [1.0, 0.0]                                   # clamp edge: ceil(43) stays inside the vocabulary
+        want = MP100CAPE._tokenize_keypoints(fake, [[x * 512, y * 512] for x, y in kp], 512, 512)
+        got = cape_b200.synthetic.tokenize_keypoints(kp, 44, 200)
+        assert set(got) == set(want)
+        for key in want:
+            assert got[key].dtype == want[key].dtype and got[key].shape == want[key].shape, key
+            assert torch.allclose(got[key].float(), want[key].float(), atol=1e-6), (k, key)
+    batch = cape_b200.synthetic.make_episode_batch(3, 2, num_keypoints=9, shots=5, seed=1, image_size=64)
+    assert batch["query_images"].shape == (6, 3, 64, 64) and batch["support_coords"].shape == (6, 9, 2)
+    assert torch.equal(batch["support_coords"][0], batch["support_coords"][1])       # support repeated per query
+    assert not batch["support_masks"].any() and len(batch["support_skeletons"]) == 6
+    assert batch["query_targets"]["seq11"].shape == (6, 200)
+
+
+def test_mirror_binds_to_the_live_tensors(model):
+    import cape_b200
+    from cape_b200.transformer import mirror_from_reference, mirror_is_current
+    ref = model.base_model.transformer
+    mirror = mirror_from_reference(ref)
+    assert mirror_is_current(mirror, ref)
+    ref_params = dict(ref.named_parameters())
+    for name, p in mirror.named_parameters():
+        assert not p.is_meta and p.data_ptr() == ref_params[name].data_ptr(), name
+    assert mirror.decoder.class_embed is ref.decoder.class_embed
+    with torch.no_grad():                                    # an optimizer-style in-place update is seen, no copy
+        ref.level_embed.add_(1.0)
+    assert torch.equal(mirror.level_embed, ref.level_embed)
+    keys = list(model.state_dict().keys())
+    model.base_model.transformer.float()                     # no-op cast keeps storage
+    assert mirror_is_current(mirror, ref)
+    ref.level_embed.data = ref.level_embed.data.clone()      # a re-allocation (model.to(...), assign-load) is detected
+    assert not mirror_is_current(mirror, ref)
+    assert list(model.state_dict().keys()) == keys
+
+
+def test_feature_pyramid_prologue_equals_what_the_reference_hands_its_transformer(model):
+    import cape_b200
+    from cape_b200 import patch
+    stage_reference.activate()
+    rf = sys.modules["models.roomformer_v2"]
+    from datasets.discrete_tokenizer import DiscreteTokenizerV2
+    base = model.base_model
+    saved_tok = base.tokenizer
+    base.tokenizer = DiscreteTokenizerV2(44, 2, add_cls=False)      # two decode steps are enough to reach the call
+    seen = {}
+
+    def grab(module, args, kwargs):
+        if "srcs" not in seen:
+            seen["srcs"], seen["masks"], seen["pos"] = args[0], args[1], args[2]
+    handle = base.transformer.register_forward_pre_hook(grab, with_kwargs=True)
+    images = torch.rand(1, 3, 512, 512, generator=torch.Generator().manual_seed(0))
+    try:
+        with torch.no_grad():
+            base.forward_inference(images, use_cache=True)
+            srcs, masks, pos = patch._feature_pyramid(base, images, rf)
+    finally:
+        handle.remove()
+        base.tokenizer = saved_tok
+        for layer in base.transformer.decoder.layers:        # drop the cache modules the reference registered (A.2)
+            layer.kv_cache = None
+            if hasattr(layer.cross_attn, "cache"):
+                del layer.cross_attn.cache
+    assert [tuple(s.shape[-2:]) for s in srcs] == [(64, 64), (32, 32), (16, 16), (8, 8)]
+    for a, b in zip(srcs + masks + pos, seen["srcs"] + seen["masks"] + seen["pos"]):
+        assert torch.equal(a, b)
+
+
+def test_patch_and_unpatch_forward_inference_swap():
+    import cape_b200
+    stage_reference.activate()
+    import models.deformable_transformer as dt
+    import models.roomformer_v2 as rf
+    original = rf.RoomFormerV2.forward_inference
+    core = dt.ms_deform_attn_core_pytorch
+    cape_b200.patch_reference(dt, swap_forward_inference=True)
+    try:
+        assert rf.RoomFormerV2.forward_inference is not original
+        assert rf.RoomFormerV2.forward_inference.__wrapped__ is original
+        assert dt.ms_deform_attn_core_pytorch is cape_b200.ms_deform_attn_core_pytorch
+        cape_b200.patch_reference(dt, swap_forward_inference=True)          # idempotent
+        assert rf.RoomFormerV2.forward_inference.__wrapped__ is original
+    finally:
+        cape_b200.unpatch_reference()
+    assert rf.RoomFormerV2.forward_inference is original and dt.ms_deform_attn_core_pytorch is core
