@@ -52,6 +52,8 @@ _SIGNATURES = {
     "cape_abi_version": (ctypes.c_int, []),
     "cape_last_error": (ctypes.c_char_p, []),
     "cape_launch_count": (ctypes.c_uint64, []),
+    "cape_set_tuning": (_i, [ctypes.c_char_p, _i]),
+    "cape_get_tuning": (_i, [ctypes.c_char_p]),
     "cape_msda_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(Dims), _i, _i, _vp]),
     "cape_msda_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(Dims), _i, _i, _i, _vp]),
     "cape_msda_decode": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(Dims), _i, _vp]),
@@ -124,3 +126,9 @@ def check(rc: int, what: str) -> None:
 
 def launch_count() -> int:
     return int(load().cape_launch_count())
+
+
+def set_tuning(name: str, value: int) -> None:
+    """Override a launch-geometry / kernel-selection knob at run time (``CAPE_<NAME>`` environment variables are read
+    once per process by the library); ``value <= 0`` restores the default."""
+    check(load().cape_set_tuning(name.encode(), int(value)), f"cape_set_tuning({name})")

@@ -2,6 +2,7 @@
 // the kernels live in msda_forward.cu / msda_backward.cu.  No allocation, no device synchronisation, no CPU path.
 #include <atomic>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -79,6 +80,36 @@ int check_ptr(const void* p, const char* name, bool empty_ok, unsigned align = 1
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+namespace {
+const char* const kTuneNames[kTuneCount] = {"FWD_THREADS", "FWD_QPC", "FWD_POINT_MAX_QM", "FWD_STAGED", "FWD_STAGED_MIN_QM",
+                                            "FWD_STAGED_KB", "BWD_THREADS", "BWD_QPC", "BWD_MODE", "BWD_STAGED_KB"};
+std::atomic<int> g_tune[kTuneCount];
+std::once_flag g_tune_once;
+
+void load_tuning_from_env() {
+    for (int i = 0; i < kTuneCount; ++i) {
+        char name[64];
+        snprintf(name, sizeof(name), "CAPE_%s", kTuneNames[i]);
+        const char* v = std::getenv(name);
+        g_tune[i].store(v && *v ? std::atoi(v) : 0, std::memory_order_relaxed);
+    }
+}
+
+int tune_index(const char* name) {
+    if (!name) return -1;
+    if (!std::strncmp(name, "CAPE_", 5)) name += 5;
+    for (int i = 0; i < kTuneCount; ++i)
+        if (!std::strcmp(name, kTuneNames[i])) return i;
+    return -1;
+}
+}  // namespace
+
+int tuning(Tune knob, int fallback) {
+    std::call_once(g_tune_once, load_tuning_from_env);
+    const int v = g_tune[knob].load(std::memory_order_relaxed);
+    return v > 0 ? v : fallback;
+}
+
 bool first_use_on_device(unsigned long long* flags) {
     static std::mutex mu;
     int dev = 0;
@@ -101,6 +132,21 @@ int cape_abi_version(void) { return CAPE_ABI_VERSION; }
 const char* cape_last_error(void) { return t_error; }
 
 uint64_t cape_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int cape_set_tuning(const char* name, int value) {
+    const int i = tune_index(name);
+    if (i < 0) return fail(CAPE_ERR_BAD_DIMS, "unknown tuning knob %s", name ? name : "(null)");
+    std::call_once(g_tune_once, load_tuning_from_env);
+    g_tune[i].store(value, std::memory_order_relaxed);
+    return 0;
+}
+
+int cape_get_tuning(const char* name) {
+    const int i = tune_index(name);
+    if (i < 0) return -1;
+    std::call_once(g_tune_once, load_tuning_from_env);
+    return g_tune[i].load(std::memory_order_relaxed);
+}
 
 int cape_msda_forward(const void* value, const int64_t* spatial_shapes_dev, const int64_t* level_start_index_dev,
                       const void* sampling_locations, const void* attention_weights, void* out,

@@ -25,13 +25,6 @@ namespace cape {
 
 namespace {
 
-int env_int(const char* name, int fallback) {
-    const char* v = std::getenv(name);
-    if (!v || !*v) return fallback;
-    const int x = std::atoi(v);
-    return x > 0 ? x : fallback;
-}
-
 constexpr int kBwdMaxThreads = 512;
 
 template <typename VT, int L>
@@ -288,11 +281,11 @@ cudaError_t launch_typed(const BwdArgs& a, cudaStream_t stream) {
     AT* gloc = static_cast<AT*>(a.grad_loc);
     AT* gattn = static_cast<AT*>(a.grad_attn);
     if (d.D == 32 && d.P == 4 && d.L >= 1 && d.L <= 4) {
-        int threads = env_int("CAPE_BWD_THREADS", 256);
+        int threads = tuning(kTuneBwdThreads, 256);
         threads = (threads / 32) * 32;
         if (threads < 32) threads = 32;
         if (threads > kBwdMaxThreads) threads = kBwdMaxThreads;
-        int q_per_cta = env_int("CAPE_BWD_QPC", 128);
+        int q_per_cta = tuning(kTuneBwdQpc, 128);
         while (q_per_cta > 1 && static_cast<int64_t>(d.N) * d.M * ((d.Lq + q_per_cta - 1) / q_per_cta) < 148 * 4) q_per_cta >>= 1;
         if (q_per_cta > d.Lq) q_per_cta = d.Lq;
         if (q_per_cta < 1) q_per_cta = 1;

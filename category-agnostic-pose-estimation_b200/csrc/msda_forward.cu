@@ -311,27 +311,19 @@ msda_fwd_generic_kernel(const VT* __restrict__ value, const int64_t* __restrict_
 }
 
 // Launch geometry of the fast path.  Default: 512-thread CTAs (16 warps) over 512 consecutive queries — two CTAs per
-// SM at 64 registers, each sweeping a compact window of the (n, m) value rows.  CAPE_FWD_THREADS / CAPE_FWD_QPC
-// override it for tuning runs.
+// SM at 64 registers, each sweeping a compact window of the (n, m) value rows.  The FWD_THREADS / FWD_QPC tuning knobs
+// (msda_launch.h) override it for tuning runs.
 struct FastGeometry {
     int threads, q_per_cta, q_tiles;
     int64_t grid;
 };
 
-int env_int(const char* name, int fallback) {
-    const char* v = std::getenv(name);
-    if (!v || !*v) return fallback;
-    const int x = std::atoi(v);
-    return x > 0 ? x : fallback;
-}
-
-FastGeometry fast_geometry(const cape_msda_dims& d, const char* env_threads, const char* env_qpc, int def_threads,
-                           int def_qpc) {
-    int threads = env_int(env_threads, def_threads);
+FastGeometry fast_geometry(const cape_msda_dims& d, Tune knob_threads, Tune knob_qpc, int def_threads, int def_qpc) {
+    int threads = tuning(knob_threads, def_threads);
     threads = (threads / 32) * 32;
     if (threads < 32) threads = 32;
     if (threads > kFwdMaxThreads) threads = kFwdMaxThreads;
-    int q_per_cta = env_int(env_qpc, def_qpc);
+    int q_per_cta = tuning(knob_qpc, def_qpc);
     // small problems (decode: Lq = 1..k): shrink the tile until the grid covers the chip a few times over
     while (q_per_cta > 1 && static_cast<int64_t>(d.N) * d.M * ((d.Lq + q_per_cta - 1) / q_per_cta) < 148 * 4) q_per_cta >>= 1;
     if (q_per_cta > d.Lq) q_per_cta = d.Lq;
@@ -364,7 +356,7 @@ cudaError_t launch_typed(const FwdArgs& a, cudaStream_t stream) {
     const cape_msda_dims& d = a.d;
     const int64_t total_qm = static_cast<int64_t>(d.N) * d.Lq * d.M;
     if (total_qm == 0) return cudaSuccess;
-    if (d.D == 32 && d.P == 4 && d.L >= 1 && d.L <= 4 && total_qm <= env_int("CAPE_FWD_POINT_MAX_QM", 148 * 64)) {
+    if (d.D == 32 && d.P == 4 && d.L >= 1 && d.L <= 4 && total_qm <= tuning(kTuneFwdPointMaxQm, 148 * 64)) {
         // small problem (decode): one warp per (n, q, m), everything in flight at once
         const int warps = 4;
         const unsigned grid = static_cast<unsigned>((total_qm + warps - 1) / warps);
@@ -383,7 +375,7 @@ cudaError_t launch_typed(const FwdArgs& a, cudaStream_t stream) {
         }
 #undef CAPE_POINT_CASE
     } else if (d.D == 32 && d.P == 4 && d.L >= 1 && d.L <= 4) {
-        const FastGeometry g = fast_geometry(d, "CAPE_FWD_THREADS", "CAPE_FWD_QPC", 512, 512);
+        const FastGeometry g = fast_geometry(d, kTuneFwdThreads, kTuneFwdQpc, 512, 512);
         if (g.grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
         switch (d.L) {
             case 1: launch_fast<VT, AT, FUSED, 1>(a, g, stream); break;
@@ -413,6 +405,11 @@ cudaError_t launch_value_typed(const FwdArgs& a, cudaStream_t stream) {
 }  // namespace
 
 cudaError_t launch_forward(const FwdArgs& a, cudaStream_t stream) {
+    if (tuning(kTuneFwdStaged, 1) == 1) {   // large problems: coarse levels staged in shared memory (msda_forward_staged.cu)
+        const cudaError_t e = launch_forward_staged(a, stream);
+        if (e == cudaSuccess) count_launch();
+        if (e != cudaErrorNotSupported) return e;
+    }
     switch (a.value_dtype) {
         case CAPE_DTYPE_F32: return launch_value_typed<float>(a, stream);
         case CAPE_DTYPE_BF16: return launch_value_typed<__nv_bfloat16>(a, stream);

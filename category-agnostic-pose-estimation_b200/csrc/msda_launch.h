@@ -67,6 +67,8 @@ struct SeqEmbedArgs {
 // Each returns cudaGetLastError() after the launch and bumps the launch counter.
 cudaError_t launch_forward(const FwdArgs& a, cudaStream_t stream);
 cudaError_t launch_backward(const BwdArgs& a, cudaStream_t stream);
+// shared-memory staged variants (persistent, TMA): return cudaErrorNotSupported for configurations they do not cover
+cudaError_t launch_forward_staged(const FwdArgs& a, cudaStream_t stream);
 cudaError_t launch_query_pool_forward(const FwdArgs& a, cudaStream_t stream);     // fp32 only
 cudaError_t launch_query_pool_backward(const BwdArgs& a, cudaStream_t stream);    // fp32 only
 cudaError_t launch_points_sample_forward(const float* x, const float* pos, float* out, const PointsDims& p,
@@ -114,6 +116,14 @@ cudaError_t launch_token_step(const float* cls_logits, const float* reg, int64_t
                               const cape_tokenizer& tk, int B, int n_classes, cudaStream_t stream);
 
 void count_launch();
+
+// Tuning knobs: read once per process from the environment variable "CAPE_<NAME>" (std::call_once), changeable at run
+// time through cape_set_tuning() (tools/tune.py).  Values <= 0 mean "default".
+enum Tune {
+    kTuneFwdThreads, kTuneFwdQpc, kTuneFwdPointMaxQm, kTuneFwdStaged, kTuneFwdStagedMinQm, kTuneFwdStagedKb,
+    kTuneBwdThreads, kTuneBwdQpc, kTuneBwdMode, kTuneBwdStagedKb, kTuneCount
+};
+int tuning(Tune knob, int fallback);
 
 // True the first time it is called for the current device with this `flags` word (one word per kernel family): function
 // attributes such as the dynamic shared-memory opt-in are per device, so a once-per-process flag is not enough.

@@ -122,10 +122,10 @@ def _generation_state(model, batch: int, device):
         model.__dict__[_GEN_ATTR] = state
     mirror = state["mirror"]
     mirror.train(False)
-    key = (batch, str(device))
+    spec = TokenizerSpec.from_tokenizer(model.tokenizer)
+    key = (batch, str(device), spec.seq_len, spec.num_bins, spec.add_cls)
     gen = state["generators"].get(key)
     if gen is None:
-        spec = TokenizerSpec.from_tokenizer(model.tokenizer)
         gen = AutoregressiveGenerator(mirror, spec, batch, device)
         state["generators"] = {key: gen}          # one resident generator: its K/V + value caches are batch-sized
     return mirror, gen
@@ -137,12 +137,12 @@ def _make_forward_inference(rf, original):
         (``pred_logits`` (B, steps, n_classes), ``pred_coords`` (B, steps, 2), ``gen_out``).  The decoder part — the
         ``while i < max_len and unfinish_flag.any()`` loop with its per-sample Python bookkeeping (:481-598) — runs as
         one CUDA graph per token on the device.  Configurations outside the mirror (CPU tensors, ``cape_mode`` with an
-        internal support encoder, room classes, ``use_cache=False``, decoder layers other than v1) take the reference's
+        internal support encoder, ``inject_cls_embed``, ``use_cache=False``, decoder layers other than v1) take the reference's
         own loop, which still samples through the patched core."""
         tensors = samples.tensors if hasattr(samples, "tensors") else samples
         unsupported = (not isinstance(tensors, torch.Tensor) or not tensors.is_cuda or not use_cache
                        or (getattr(self, "cape_mode", False) and support_graphs is not None)
-                       or getattr(self, "room_class_embed", None) is not None or self.query_embed is None
+                       or getattr(self, "inject_cls_embed", False) or self.query_embed is None
                        or getattr(self, "tokenizer", None) is None)
         if not unsupported:
             try:
@@ -160,7 +160,12 @@ def _make_forward_inference(rf, original):
             out = gen.generate(srcs, masks, pos, self.query_embed.weight,
                                support_features=getattr(dec, "support_features", None),
                                support_mask=getattr(dec, "support_mask", None))
-        return {"pred_logits": out["pred_logits"], "pred_coords": out["pred_coords"], "gen_out": out["gen_out"]}
+            result = {"pred_logits": out["pred_logits"], "pred_coords": out["pred_coords"], "gen_out": out["gen_out"]}
+            if getattr(self, "room_class_embed", None) is not None:          # :647-654 (semantic_classes > 0, the CAPE default)
+                result = {"pred_logits": out["pred_logits"], "pred_coords": out["pred_coords"],
+                          "pred_room_logits": self.room_class_embed(out["hidden"]), "gen_out": out["gen_out"],
+                          "anchors": self.query_embed.weight.detach()}
+        return result
 
     forward_inference.__wrapped__ = original
     return forward_inference

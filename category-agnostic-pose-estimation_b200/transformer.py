@@ -338,6 +338,9 @@ class AutoregressiveGenerator(IncrementalDecoder):
         self.state = TokenState(max_batch_size, spec, self.n_classes, device)
         self.pos = self.state.step                      # the K/V write position IS the generation step counter
         self.ref_table = torch.zeros(spec.seq_len, 2, device=self.device)
+        # last-layer hidden state of every step (what the reference collects in output_hs_list, roomformer_v2.py:519-524,
+        # for heads applied after the loop such as room_class_embed, :647-654)
+        self.hidden = torch.zeros(max_batch_size, spec.seq_len, transformer.d_model, device=self.device)
         self.valid_ratios = None
         layer0 = dec.layers[0]
         can_fuse = (transformer.d_model == 256 and transformer.d_model // transformer.nhead == 32
@@ -427,6 +430,7 @@ class AutoregressiveGenerator(IncrementalDecoder):
             c = K.skinny_linear(x, w["wt_c1"], w["b_c1"], relu=True)
             ref, ref_levels = K.coord_head_refine(c, w["wt_c2"], w["b_c2"], w["w_c3"], w["b_c3"], ref, self.valid_ratios)
         cls = K.tiny_linear(x, fp["w_cls"], fp["b_cls"])                                       # :1117-1121
+        self.hidden.index_copy_(1, self.pos, x.view(n, 1, -1))
         st.advance(cls, ref)
         return x
 
@@ -446,6 +450,7 @@ class AutoregressiveGenerator(IncrementalDecoder):
             x = self._layer_step(lid, layer, x, qpos, mask, ref_input.contiguous())
             ref = dec.refine(lid, x, ref)
         cls = dec.class_embed[-1](x)                                                         # :1117-1121
+        self.hidden.index_copy_(1, self.pos, x.view(n, 1, -1))
         st.advance(cls.contiguous(), ref.contiguous())
         return x
 
@@ -534,7 +539,7 @@ class AutoregressiveGenerator(IncrementalDecoder):
         xy = st.gen_xy[:, :steps].cpu().tolist()
         gen_out = [[p if k == 0 else k for k, p in zip(kinds, points)] for kinds, points in zip(kind, xy)]
         return {"pred_logits": logits, "pred_coords": coords, "gen_out": gen_out, "sequences": logits.argmax(-1),
-                "steps": steps}
+                "steps": steps, "hidden": self.hidden[:, :steps].clone()}
 
 
 @torch.no_grad()

@@ -304,6 +304,15 @@ CAPE_API int cape_msda_forward_backward_host(const float* value_host, const int6
 /* Counts kernels this library has launched since load (bench.py reports it as gpu_launches). */
 CAPE_API uint64_t cape_launch_count(void);
 
+/*
+ * Launch-geometry / kernel-selection overrides for tuning and profiling runs.  Every knob is also read ONCE per process
+ * from the environment variable of the same name (CAPE_FWD_THREADS, CAPE_FWD_QPC, CAPE_FWD_POINT_MAX_QM, CAPE_FWD_STAGED,
+ * CAPE_BWD_THREADS, CAPE_BWD_QPC, CAPE_BWD_MODE ...); this call changes it at run time (value <= 0: back to the
+ * default).  Returns 0, or CAPE_ERR_BAD_DIMS for an unknown name.  Not part of the reference-facing interface.
+ */
+CAPE_API int cape_set_tuning(const char* name, int value);
+CAPE_API int cape_get_tuning(const char* name);
+
 #ifdef __cplusplus
 }
 #endif

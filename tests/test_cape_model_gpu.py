@@ -158,6 +158,22 @@ def test_forward_inference_tokens_match_the_unpatched_model(built, dev):
         fast = run()
         fast_again = run()                                        # second call reuses the captured graph
         assert cape_b200.launch_count() > launches0
+        state = model.base_model.__dict__.get("_cape_b200_generation")
+        assert state is not None and len(state["generators"]) == 1, "the device-resident generator did not run"
+        assert next(iter(state["generators"].values())).graph is not None
+        # the full result dict of RoomFormerV2.forward_inference, room-class head included (:647-654)
+        with torch.no_grad():
+            model.base_model.transformer.decoder.support_features = model.support_encoder(sup, ~mask.bool(), skel)
+            model.base_model.transformer.decoder.support_mask = mask.bool()
+            raw_fast = model.base_model.forward_inference(images)
+            raw_ref = model.base_model.forward_inference.__wrapped__(model.base_model, images)
+            model.base_model.transformer.decoder.support_features = None
+            model.base_model.transformer.decoder.support_mask = None
+        assert set(raw_fast) == set(raw_ref) and "pred_room_logits" in raw_ref
+        assert raw_fast["pred_room_logits"].shape == raw_ref["pred_room_logits"].shape
+        assert _rel(raw_fast["pred_room_logits"], raw_ref["pred_room_logits"]) < 1e-3
+        assert torch.equal(raw_fast["anchors"], raw_ref["anchors"])
+        assert [len(g) for g in raw_fast["gen_out"]] == [len(g) for g in raw_ref["gen_out"]]
     finally:
         cape_b200.unpatch_reference()
     assert sys.modules["models.roomformer_v2"].RoomFormerV2.forward_inference.__name__ == "forward_inference"

@@ -1,4 +1,4 @@
-"""Sweep launch geometry of the fast kernels on the bench workload (CAPE_{FWD,BWD}_{THREADS,QPC} env overrides).
+"""Sweep launch geometry of the fast kernels on the bench workload (cape_set_tuning: FWD/BWD_THREADS, FWD/BWD_QPC).
 Development tool; prints one line per configuration."""
 import ctypes
 import itertools
@@ -53,12 +53,12 @@ def timeit(fn, reps=20):
 which = sys.argv[1] if len(sys.argv) > 1 else "both"
 if which in ("fwd", "both"):
     for th, qpc in itertools.product((128, 256, 512), (128, 256, 512, 1024, 2048)):
-        os.environ["CAPE_FWD_THREADS"], os.environ["CAPE_FWD_QPC"] = str(th), str(qpc)
+        _lib.set_tuning("FWD_THREADS", th), _lib.set_tuning("FWD_QPC", qpc)
         print(f"fwd threads={th:4d} qpc={qpc:4d}  {timeit(fwd):8.1f} us", flush=True)
 if which in ("bwd", "both"):
     ths = [int(v) for v in os.environ.get("TUNE_THREADS", "128,256,512").split(",")]
     qpcs = [int(v) for v in os.environ.get("TUNE_QPCS", "64,128,256,512,1024").split(",")]
     for th, qpc in itertools.product(ths, qpcs):
-        os.environ["CAPE_BWD_THREADS"], os.environ["CAPE_BWD_QPC"] = str(th), str(qpc)
+        _lib.set_tuning("BWD_THREADS", th), _lib.set_tuning("BWD_QPC", qpc)
         gvalue.zero_()
         print(f"bwd threads={th:4d} qpc={qpc:4d}  {timeit(bwd):8.1f} us", flush=True)
