@@ -54,6 +54,7 @@ _SIGNATURES = {
     "cape_launch_count": (ctypes.c_uint64, []),
     "cape_set_tuning": (_i, [ctypes.c_char_p, _i]),
     "cape_get_tuning": (_i, [ctypes.c_char_p]),
+    "cape_debug_counters": (_i, [ctypes.POINTER(ctypes.c_longlong), _i]),
     "cape_msda_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(Dims), _i, _i, _vp]),
     "cape_msda_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(Dims), _i, _i, _i, _vp]),
     "cape_msda_decode": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(Dims), _i, _vp]),

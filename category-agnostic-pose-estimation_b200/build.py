@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcape_msda.so")
-SOURCES = ["cape_abi.cu", "msda_forward.cu", "msda_forward_staged.cu", "msda_backward.cu", "msda_variants.cu", "seq_tokens.cu", "decode_step.cu", "linear_tf32x3.cu"]
+SOURCES = ["cape_abi.cu", "msda_forward.cu", "msda_forward_staged.cu", "msda_backward.cu", "msda_backward_staged.cu", "msda_variants.cu", "seq_tokens.cu", "decode_step.cu", "linear_tf32x3.cu"]
 HEADERS = ["msda_common.cuh", "msda_launch.h", "async_copy.cuh", os.path.join("..", "..", "include", "cape_msda.h")]
 
 NVCC_FLAGS = [

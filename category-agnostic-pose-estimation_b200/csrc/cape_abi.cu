@@ -82,7 +82,7 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 namespace {
 const char* const kTuneNames[kTuneCount] = {"FWD_THREADS", "FWD_QPC", "FWD_POINT_MAX_QM", "FWD_STAGED", "FWD_STAGED_MIN_QM",
-                                            "FWD_STAGED_KB", "BWD_THREADS", "BWD_QPC", "BWD_MODE", "BWD_STAGED_KB"};
+                                            "FWD_STAGED_KB", "BWD_THREADS", "BWD_QPC", "BWD_MODE", "BWD_STAGED_KB", "PROFILE"};
 std::atomic<int> g_tune[kTuneCount];
 std::once_flag g_tune_once;
 
@@ -139,6 +139,12 @@ int cape_set_tuning(const char* name, int value) {
     std::call_once(g_tune_once, load_tuning_from_env);
     g_tune[i].store(value, std::memory_order_relaxed);
     return 0;
+}
+
+int cape_debug_counters(long long* out16, int reset) {
+    if (!out16) return fail(CAPE_ERR_NULL_PTR, "out16 is NULL");
+    const cudaError_t e = read_backward_staged_cycles(out16, reset != 0);
+    return e == cudaSuccess ? 0 : fail_cuda(e, "cape_debug_counters");
 }
 
 int cape_get_tuning(const char* name) {

@@ -76,13 +76,13 @@ __device__ __forceinline__ void scatter_level(const VT* __restrict__ vbase, floa
     const float ahy = a * hy, aly = a * ly;
 #ifndef CAPE_EXP_NO_RED   // profiling-only variant (tools/, never shipped) drops the scatter
     float c = ahy * hx;
-    red_add4_if(gbase + o00, y0ok & x0ok, c * g.x, c * g.y, c * g.z, c * g.w);
+    { const float4 cg = mul4(c, g); red_add4_if(gbase + o00, y0ok & x0ok, cg.x, cg.y, cg.z, cg.w); }
     c = ahy * lx;
-    red_add4_if(gbase + o00 + rowStride, y0ok & x1ok, c * g.x, c * g.y, c * g.z, c * g.w);
+    { const float4 cg = mul4(c, g); red_add4_if(gbase + o00 + rowStride, y0ok & x1ok, cg.x, cg.y, cg.z, cg.w); }
     c = aly * hx;
-    red_add4_if(gbase + o10, y1ok & x0ok, c * g.x, c * g.y, c * g.z, c * g.w);
+    { const float4 cg = mul4(c, g); red_add4_if(gbase + o10, y1ok & x0ok, cg.x, cg.y, cg.z, cg.w); }
     c = aly * lx;
-    red_add4_if(gbase + o10 + rowStride, y1ok & x1ok, c * g.x, c * g.y, c * g.z, c * g.w);
+    { const float4 cg = mul4(c, g); red_add4_if(gbase + o10 + rowStride, y1ok & x1ok, cg.x, cg.y, cg.z, cg.w); }
 #else
     (void)gbase;
     (void)ahy;
@@ -335,6 +335,12 @@ cudaError_t launch_value_typed(const BwdArgs& a, cudaStream_t stream) {
 }  // namespace
 
 cudaError_t launch_backward(const BwdArgs& a, cudaStream_t stream) {
+    const int mode = tuning(kTuneBwdMode, 1);      // 1: L1 kernel + REDs; 2: staged rows + tensor-core scatter; 3: staged rows
+    if (mode == 2 || mode == 3) {
+        const cudaError_t e = launch_backward_staged(a, mode, stream);
+        if (e == cudaSuccess) count_launch();
+        if (e != cudaErrorNotSupported) return e;
+    }
     switch (a.value_dtype) {
         case CAPE_DTYPE_F32: return launch_value_typed<float>(a, stream);
         case CAPE_DTYPE_BF16: return launch_value_typed<__nv_bfloat16>(a, stream);

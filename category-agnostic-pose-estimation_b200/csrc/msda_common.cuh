@@ -68,11 +68,26 @@ __device__ __forceinline__ float4 ld4_or_zero(const __half* p, bool pred) {
     const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
     return make_float4(a.x, a.y, b.x, b.y);
 }
+// acc += w * v as two packed FFMA2 (sm_100 `fma.rn.f32x2`, scalar operand broadcast): same rounding as four FFMA, half
+// the issue slots — the sampling kernels are issue-limited as much as LSU-limited.
 __device__ __forceinline__ void fma4(float w, const float4& v, float4& acc) {
-    acc.x = fmaf(w, v.x, acc.x);
-    acc.y = fmaf(w, v.y, acc.y);
-    acc.z = fmaf(w, v.z, acc.z);
-    acc.w = fmaf(w, v.w, acc.w);
+    asm("{\n\t.reg .b64 a, b, c;\n\t"
+        "mov.b64 a, {%4, %4};\n\t"
+        "mov.b64 b, {%5, %6};\n\tmov.b64 c, {%0, %1};\n\tfma.rn.f32x2 c, a, b, c;\n\tmov.b64 {%0, %1}, c;\n\t"
+        "mov.b64 b, {%7, %8};\n\tmov.b64 c, {%2, %3};\n\tfma.rn.f32x2 c, a, b, c;\n\tmov.b64 {%2, %3}, c;\n\t}"
+        : "+f"(acc.x), "+f"(acc.y), "+f"(acc.z), "+f"(acc.w)
+        : "f"(w), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
+}
+// c * g as two packed FMUL2
+__device__ __forceinline__ float4 mul4(float c, const float4& g) {
+    float4 r;
+    asm("{\n\t.reg .b64 a, b, d;\n\t"
+        "mov.b64 a, {%4, %4};\n\t"
+        "mov.b64 b, {%5, %6};\n\tmul.rn.f32x2 d, a, b;\n\tmov.b64 {%0, %1}, d;\n\t"
+        "mov.b64 b, {%7, %8};\n\tmul.rn.f32x2 d, a, b;\n\tmov.b64 {%2, %3}, d;\n\t}"
+        : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+        : "f"(c), "f"(g.x), "f"(g.y), "f"(g.z), "f"(g.w));
+    return r;
 }
 __device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ void st4(__nv_bfloat16* p, const float4& v) {
@@ -134,8 +149,16 @@ __device__ __forceinline__ float pixel_coord(float loc, float dimf) {
 // Warp index that the compiler can prove uniform (so shuffles in warp-uniform loops need no reconvergence code).
 __device__ __forceinline__ int uniform_warp_id() { return __shfl_sync(kFullMask, static_cast<int>(threadIdx.x >> 5), 0); }
 
+// <a, b> over 4 channels: one FMUL2 + one FFMA2 + one FADD  ((a.x b.x + a.z b.z) + (a.y b.y + a.w b.w))
 __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
-    return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+    float lo, hi;
+    asm("{\n\t.reg .b64 p, q, t;\n\t"
+        "mov.b64 p, {%2, %3};\n\tmov.b64 q, {%6, %7};\n\tmul.rn.f32x2 t, p, q;\n\t"
+        "mov.b64 p, {%4, %5};\n\tmov.b64 q, {%8, %9};\n\tfma.rn.f32x2 t, p, q, t;\n\t"
+        "mov.b64 {%0, %1}, t;\n\t}"
+        : "=f"(lo), "=f"(hi)
+        : "f"(a.z), "f"(a.w), "f"(a.x), "f"(a.y), "f"(b.z), "f"(b.w), "f"(b.x), "f"(b.y));
+    return lo + hi;
 }
 
 }  // namespace cape

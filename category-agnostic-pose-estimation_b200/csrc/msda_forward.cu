@@ -36,14 +36,20 @@ constexpr int kFwdMaxThreads = 512;
 template <typename VT, int L>
 struct FwdLevels {
     int H[L], W[L];
-    const VT* base[L];   // first row of the level for this (n, m, channel quad)
+    const VT* img;       // row 0 of this (n, m, channel quad)
+    int off[L];          // element offset of the level's first row (S*M*D < 2^31, checked by the ABI): 32-bit address math
     __device__ __forceinline__ void load(const int64_t* __restrict__ shapes, const int64_t* __restrict__ starts,
-                                         const VT* vbase, int rowStride) {
+                                         const VT* vbase, int rowStride, int S) {
+        img = vbase;
 #pragma unroll
         for (int l = 0; l < L; ++l) {
             H[l] = static_cast<int>(__ldg(shapes + 2 * l));
             W[l] = static_cast<int>(__ldg(shapes + 2 * l + 1));
-            base[l] = vbase + static_cast<int64_t>(__ldg(starts + l)) * rowStride;
+            const long long s0 = __ldg(starts + l);
+            // a level that does not fit inside S (the reference asserts sum(H*W) == S, deformable_transformer.py:94)
+            // contributes nothing instead of being read out of bounds
+            if (s0 < 0 || H[l] < 0 || W[l] < 0 || s0 + static_cast<long long>(H[l]) * W[l] > S) H[l] = W[l] = 0;
+            off[l] = H[l] > 0 ? static_cast<int>(s0) * rowStride : 0;
         }
     }
     // map dimension that loc float `lane` (= [l][p][xy]) is scaled by: W_l for x, H_l for y
@@ -58,7 +64,7 @@ struct FwdLevels {
 
 // One sample per 8-lane group (4 per warp instruction), 4 corners each.  (px, py) are pixel coordinates from pixel_coord().
 template <typename VT>
-__device__ __forceinline__ void gather_level(const VT* __restrict__ base, int rowStride, int H, int W, float px,
+__device__ __forceinline__ void gather_level(const VT* __restrict__ img, int levelOff, int rowStride, int H, int W, float px,
                                              float py, float a, float4& acc) {
     const float xf = floorf(px), yf = floorf(py);
     const float lx = px - xf, ly = py - yf;
@@ -67,8 +73,8 @@ __device__ __forceinline__ void gather_level(const VT* __restrict__ base, int ro
     const bool x1ok = static_cast<unsigned>(x0 + 1) < static_cast<unsigned>(W);
     const bool y0ok = static_cast<unsigned>(y0) < static_cast<unsigned>(H);
     const bool y1ok = static_cast<unsigned>(y0 + 1) < static_cast<unsigned>(H);
-    const VT* p00 = base + static_cast<int64_t>(y0 * W + x0) * rowStride;
-    const VT* p10 = p00 + static_cast<int64_t>(W) * rowStride;
+    const VT* p00 = img + (levelOff + (y0 * W + x0) * rowStride);
+    const VT* p10 = p00 + W * rowStride;
     const float ahy = a * (1.f - ly), aly = a * ly, hx = 1.f - lx;
     const float4 v00 = ld4_or_zero(p00, y0ok & x0ok);
     const float4 v01 = ld4_or_zero(p00 + rowStride, y0ok & x1ok);
@@ -110,7 +116,7 @@ __device__ __forceinline__ void load_raw(const HT* locp, const HT* attnp, int64_
 
 // MC: compile-time head count (row stride = MC * 32 elements) or 0 for a run-time stride.
 template <typename VT, typename AT, int L, bool FUSED, int MC>
-__global__ void __launch_bounds__(kFwdMaxThreads)
+__global__ void __launch_bounds__(kFwdMaxThreads, 2)
 msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                      const int64_t* __restrict__ starts, const void* __restrict__ locp,
                      const void* __restrict__ attnp, const float* __restrict__ refp, VT* __restrict__ out, int N, int S,
@@ -126,7 +132,7 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
     const int m = bid % M, n = bid / M;
     const int rowStride = M * D;
     FwdLevels<VT, L> lv;
-    lv.load(shapes, starts, value + (static_cast<int64_t>(n) * S * M + m) * D + k * 4, rowStride);
+    lv.load(shapes, starts, value + (static_cast<int64_t>(n) * S * M + m) * D + k * 4, rowStride, S);
     // dimensions of the level whose samples this lane converts (level k >> 1)
     float ownW = 1.f, ownH = 1.f;
 #pragma unroll
@@ -180,7 +186,7 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
                 const float px = __shfl_sync(kFullMask, (s & 1) ? px1 : px0, src);
                 const float py = __shfl_sync(kFullMask, (s & 1) ? py1 : py0, src);
                 const float a = __shfl_sync(kFullMask, (s & 1) ? cur.attn.y : cur.attn.x, src);
-                gather_level(lv.base[l], rowStride, lv.H[l], lv.W[l], px, py, a, acc);
+                gather_level(lv.img, lv.off[l], rowStride, lv.H[l], lv.W[l], px, py, a, acc);
             }
         }
         if (on) st4(out + (nq * M + m) * D + k * 4, acc);
@@ -209,7 +215,7 @@ msda_fwd_point_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
     const int64_t nq = qm / M, n = nq / Lq;
     const int rowStride = M * D;
     FwdLevels<VT, L> lv;
-    lv.load(shapes, starts, value + (n * S * M + m) * D + k * 4, rowStride);
+    lv.load(shapes, starts, value + (n * S * M + m) * D + k * 4, rowStride, S);
     const float dimf = lv.lane_dim(lane);
     float loc = 0.f, attn = FUSED ? -INFINITY : 0.f;
     if (lane < L * 8) loc = to_f32(static_cast<const LT*>(locp)[qm * (L * 8) + lane]);
@@ -232,7 +238,7 @@ msda_fwd_point_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
         const float px = __shfl_sync(kFullMask, loc, l * 8 + p * 2);
         const float py = __shfl_sync(kFullMask, loc, l * 8 + p * 2 + 1);
         const float a = __shfl_sync(kFullMask, attn, l * 4 + p);
-        gather_level(lv.base[l], rowStride, lv.H[l], lv.W[l], px, py, a, acc);
+        gather_level(lv.img, lv.off[l], rowStride, lv.H[l], lv.W[l], px, py, a, acc);
     }
 #pragma unroll
     for (int s = 8; s <= 16; s <<= 1) {
@@ -405,7 +411,10 @@ cudaError_t launch_value_typed(const FwdArgs& a, cudaStream_t stream) {
 }  // namespace
 
 cudaError_t launch_forward(const FwdArgs& a, cudaStream_t stream) {
-    if (tuning(kTuneFwdStaged, 1) == 1) {   // large problems: coarse levels staged in shared memory (msda_forward_staged.cu)
+    // Opt-in (FWD_STAGED = 1): coarse levels staged in shared memory by the TMA (msda_forward_staged.cu).  Measured on B200
+    // at the bench shape it is 5 % SLOWER than the L1 kernel below (350 vs 331 us: the staged rows take the L1 capacity
+    // that level 0 needs, and LDS rows cost the same data-stage wavefronts as L1 hits; profiles/r02_forward_staged.txt).
+    if (tuning(kTuneFwdStaged, 2) == 1) {
         const cudaError_t e = launch_forward_staged(a, stream);
         if (e == cudaSuccess) count_launch();
         if (e != cudaErrorNotSupported) return e;

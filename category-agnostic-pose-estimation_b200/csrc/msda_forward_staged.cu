@@ -25,6 +25,7 @@ namespace {
 
 constexpr int kStThreads = 1024;
 constexpr int kBoxRows = 64;          // pixels per TMA box
+constexpr int kMaxDynSmem = 227 * 1024 - 2048;   // opt-in limit minus this kernel's static shared memory (barrier + padding)
 
 // 4 channels from shared memory (zeros when !pred); `addr` is a shared-state-space byte address.
 template <typename VT>
@@ -254,7 +255,7 @@ cudaError_t launch_staged_typed(const FwdArgs& a, const CUtensorMap& vmap, int g
     static unsigned long long configured = 0;
     if (first_use_on_device(&configured)) {
         const cudaError_t e = cudaFuncSetAttribute(msda_fwd_staged_kernel<VT, AT, FUSED>,
-                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64);
+                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
         if (e != cudaSuccess) return e;
     }
     const cape_msda_dims& d = a.d;
@@ -283,7 +284,7 @@ cudaError_t launch_forward_staged(const FwdArgs& a, cudaStream_t stream) {
     if (total < tuning(kTuneFwdStagedMinQm, 148 * 2048)) return cudaErrorNotSupported;   // small problems: latency kernels
     const int esize = a.value_dtype == CAPE_DTYPE_F32 ? 4 : 2;
     const int row_bytes = 32 * esize;
-    const int budget_kb = min(tuning(kTuneFwdStagedKb, 200), 224);
+    const int budget_kb = min(tuning(kTuneFwdStagedKb, 200), kMaxDynSmem / 1024);
     const int cap_rows = (budget_kb * 1024 / (kBoxRows * row_bytes)) * kBoxRows;
     if (cap_rows < kBoxRows) return cudaErrorNotSupported;
     int smem_rows = cap_rows;

@@ -69,6 +69,8 @@ cudaError_t launch_forward(const FwdArgs& a, cudaStream_t stream);
 cudaError_t launch_backward(const BwdArgs& a, cudaStream_t stream);
 // shared-memory staged variants (persistent, TMA): return cudaErrorNotSupported for configurations they do not cover
 cudaError_t launch_forward_staged(const FwdArgs& a, cudaStream_t stream);
+cudaError_t launch_backward_staged(const BwdArgs& a, int mode, cudaStream_t stream);   // mode 2: + tensor-core scatter, 3: staged only
+cudaError_t read_backward_staged_cycles(long long* out16, bool reset);   // PROFILE knob: cycle counters of CTA 0
 cudaError_t launch_query_pool_forward(const FwdArgs& a, cudaStream_t stream);     // fp32 only
 cudaError_t launch_query_pool_backward(const BwdArgs& a, cudaStream_t stream);    // fp32 only
 cudaError_t launch_points_sample_forward(const float* x, const float* pos, float* out, const PointsDims& p,
@@ -121,7 +123,7 @@ void count_launch();
 // time through cape_set_tuning() (tools/tune.py).  Values <= 0 mean "default".
 enum Tune {
     kTuneFwdThreads, kTuneFwdQpc, kTuneFwdPointMaxQm, kTuneFwdStaged, kTuneFwdStagedMinQm, kTuneFwdStagedKb,
-    kTuneBwdThreads, kTuneBwdQpc, kTuneBwdMode, kTuneBwdStagedKb, kTuneCount
+    kTuneBwdThreads, kTuneBwdQpc, kTuneBwdMode, kTuneBwdStagedKb, kTuneProfile, kTuneCount
 };
 int tuning(Tune knob, int fallback);
 

@@ -312,6 +312,9 @@ CAPE_API uint64_t cape_launch_count(void);
  */
 CAPE_API int cape_set_tuning(const char* name, int value);
 CAPE_API int cape_get_tuning(const char* name);
+/* With the PROFILE knob set, CTA 0 of the staged backward kernel accumulates clock64() cycles per phase of its builder warp
+ * (slots 0..8), the batch count (9) and the sampling time of warp 0 (10).  Copies the 16 counters to the host (synchronises). */
+CAPE_API int cape_debug_counters(long long* out16, int reset);
 
 #ifdef __cplusplus
 }

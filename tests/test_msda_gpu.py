@@ -773,6 +773,51 @@ def test_nccl_flat_grad_allreduce_two_gpus():
     assert out.stdout.count("ok") == 2
 
 
+def test_nccl_grad_buckets_overlapped_two_gpus():
+    """GradBuckets over NCCL: per-bucket all-reduces launched from inside the last backward of an accumulation window
+    (async on NCCL's stream, joined before the optimizer), through the reference-shaped loop of tests/test_dist_gloo.py.
+    Both ranks must end with the weights of one process that saw both ranks' batches."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import subprocess
+    import sys
+    code = (
+        "import os, torch, torch.distributed as dist, sys\n"
+        "sys.path.insert(0, os.environ['CAPE_REPO'])\n"
+        "from cape_b200 import dist as cdist\n"
+        "from tests.test_dist_gloo import _toy_model, _toy_batches, _reference_shaped_loop\n"
+        "r, w, lr = cdist.init_from_env('nccl')\n"
+        "dev = torch.device('cuda', lr)\n"
+        "model = _toy_model().to(dev)\n"
+        "opt = torch.optim.AdamW(model.parameters(), lr=0.05, weight_decay=0.1)\n"
+        "buckets = cdist.GradBuckets(model.parameters(), bucket_bytes=64)\n"
+        "move = lambda b: {'x': b['x'].to(dev), 'nested': {'y': b['nested']['y'].to(dev)}, 'tag': b['tag']}\n"
+        "loader = [move(b) for b in _toy_batches(7)]\n"
+        "def engine(model, criterion, loader, optimizer, device, epoch, max_norm=0, accumulation_steps=1, scaler=None):\n"
+        "    _reference_shaped_loop(model, loader, optimizer, accumulation_steps, max_norm)\n"
+        "cdist.train_one_epoch_data_parallel(engine, model, None, loader, opt, dev, 0, buckets, accumulation_steps=3,\n"
+        "                                    max_norm=0.5, queries_per_episode=2)\n"
+        "torch.cuda.synchronize()\n"
+        "ref = _toy_model(); ropt = torch.optim.AdamW(ref.parameters(), lr=0.05, weight_decay=0.1)\n"
+        "_reference_shaped_loop(ref, _toy_batches(7), ropt, 3, 0.5)\n"
+        "for (k, a), (_, b) in zip(model.state_dict().items(), ref.state_dict().items()):\n"
+        "    assert torch.allclose(a.cpu(), b, atol=1e-5), k\n"
+        "assert buckets.known and len(buckets.buckets) > 1 and model.never_used.grad is None\n"
+        "cdist.barrier(dev); dist.destroy_process_group(); print('rank', r, 'ok')\n")
+    import tempfile
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CAPE_REPO=repo, PYTHONPATH=repo + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    with tempfile.NamedTemporaryFile("w", suffix="_nccl_buckets_worker.py", delete=False) as f:
+        f.write(code)
+        script = f.name
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29534", script], env=env,
+                         capture_output=True, text=True, timeout=300)
+    os.unlink(script)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("ok") == 2
+
+
 def test_opcheck_registration():
     inp = synthetic.make_inputs(1, 5, ((4, 4), (2, 2), (1, 1), (1, 1)), device="cuda", seed=3)
     args = (inp["value"].requires_grad_(True), inp["spatial_shapes"], inp["level_start_index"],
