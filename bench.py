@@ -375,7 +375,8 @@ def cape_train_step(dev, rank, world, steps=2, with_reference=False, amp=False):
                 return cdist.train_one_epoch_data_parallel(
                     train_one_epoch_episodic, model, criterion, loader, opt, dev, 0, buckets,
                     accumulation_steps=accumulation, max_norm=margs.clip_max_norm, scaler=scaler,
-                    queries_per_episode=k, shard=False)                            # batches are per-rank already
+                    queries_per_episode=k, shard=False,                            # batches are per-rank already
+                    misc_module=sys.modules.get("util.misc"))
             finally:
                 cape_b200.unpatch_reference()
 
@@ -837,6 +838,49 @@ def gpu_eager_baseline(dev, alg_bytes):
             "sample": "oracle/msda_torch.py on the same B200 (ATen grid_sampler_2d CUDA kernels), full N=20 workload, fp32"}
 
 
+def copy_probe(dev, rank, world, mb=256, reps=4):
+    """Where the end-to-end number saturates at N > 1: pinned host <-> device copy rate of every rank measured ALONE
+    (ranks take turns) and with all ranks copying TOGETHER.  alone ~ the GPU's own PCIe link; together / alone << 1 ~ a
+    shared host-side limit (root complex / host DRAM), which no kernel-side change can lift."""
+    import torch
+    from cape_b200 import dist as cdist
+    host = torch.empty(mb << 20, dtype=torch.uint8).pin_memory()
+    devb = torch.empty(mb << 20, dtype=torch.uint8, device=dev)
+
+    def rate(direction):
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            if direction == "h2d":
+                devb.copy_(host, non_blocking=True)
+            else:
+                host.copy_(devb, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return reps * (mb << 20) / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
+    rate("h2d")
+    out = {}
+    for direction in ("h2d", "d2h"):
+        alone = 0.0
+        for turn in range(world):
+            cdist.barrier(dev)
+            if turn == rank:
+                alone = rate(direction)
+        cdist.barrier(dev)
+        together = rate(direction)
+        out[direction + "_alone_gbs_min_over_ranks"] = round(-cdist.max_over_ranks(-alone, dev), 1)
+        out[direction + "_together_gbs_min_over_ranks"] = round(-cdist.max_over_ranks(-together, dev), 1)
+    try:
+        out["numa_nodes"] = len([d for d in os.listdir("/sys/devices/system/node") if d.startswith("node")])
+    except OSError:
+        out["numa_nodes"] = None
+    out["host_cpus"] = os.cpu_count()
+    out["mb_per_copy"] = mb
+    return out
+
+
 # ---- B200 arm ----------------------------------------------------------------------------------------------------
 def run_b200(args, rank, world, local_rank):
     import torch
@@ -935,6 +979,10 @@ def run_b200(args, rank, world, local_rank):
     h2d = sum(t.numel() * t.element_size() for t in host.values()) + shapes_h.numel() * 8 + starts_h.numel() * 8
     d2h = sum(t.numel() * t.element_size() for t in res.values())
     checksum = float(res["out"].double().sum())           # the result really is on the host
+    try:
+        probe = copy_probe(dev, rank, world)
+    except Exception as exc:                                       # noqa: BLE001
+        probe = {"error": f"{type(exc).__name__}: {exc}"[:200]}
 
     def guarded(fn, *a):
         """Side measurements must never take the contract line down with them."""
@@ -998,7 +1046,7 @@ def run_b200(args, rank, world, local_rank):
         "e2e": {"value": round(alg * e2e_steps / (e2e_ms * 1e-3) / 1e9, 2), "unit": UNIT,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "ms_per_step": round(e2e_ms / e2e_steps, 3), "api": "cape_msda_forward_backward_host (C ABI, pinned host buffers)",
-                "numa_node_rank0": numa_node,
+                "numa_node_rank0": numa_node, "copy_probe": probe,
                 "out_checksum": checksum},
         "gpu_launches": int(launches),
         "clocks": clocks,

@@ -64,6 +64,7 @@ _SIGNATURES = {
     "cape_msda_query_pool_backward": (_i, [_vp] * 9 + [ctypes.POINTER(Dims), _i, _vp]),
     "cape_points_sample_forward": (_i, [_vp] * 3 + [_i] * 7 + [_vp]),
     "cape_points_sample_backward": (_i, [_vp] * 5 + [_i] * 8 + [_vp]),
+    "cape_zero_masked_rows": (_i, [_vp, _vp, ctypes.c_int64, _i, _vp]),
     "cape_seq_embed_forward": (_i, [_vp] * 10 + [ctypes.c_int64, _i, _i, _vp]),
     "cape_seq_embed_backward": (_i, [_vp] * 10 + [ctypes.c_int64, _i, _i, ctypes.c_int64, _i, _vp]),
     "cape_token_step": (_i, [_vp, _vp, _vp, ctypes.POINTER(TokenState), ctypes.POINTER(Tokenizer), _i, _i, _vp]),

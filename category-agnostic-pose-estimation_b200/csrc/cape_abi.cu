@@ -411,6 +411,17 @@ int cape_points_sample_backward(const float* grad_out, const float* x, const flo
     return e == cudaSuccess ? 0 : fail_cuda(e, "cape_points_sample_backward launch");
 }
 
+int cape_zero_masked_rows(void* value, const uint8_t* mask, int64_t rows, int row_bytes, void* stream) {
+    if (rows < 0 || row_bytes < 0 || row_bytes % 16 != 0)
+        return fail(CAPE_ERR_BAD_DIMS, "rows=%lld row_bytes=%d: row_bytes must be a non-negative multiple of 16",
+                    static_cast<long long>(rows), row_bytes);
+    int rc;
+    const bool empty = rows == 0 || row_bytes == 0;
+    if ((rc = check_ptr(value, "value", empty)) || (rc = check_ptr(mask, "mask", empty, 1))) return rc;
+    const cudaError_t e = launch_zero_masked_rows(value, mask, rows, row_bytes, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? 0 : fail_cuda(e, "cape_zero_masked_rows launch");
+}
+
 // ---- sequence side of the decoder ---------------------------------------------------------------------------------
 
 namespace {

@@ -117,6 +117,8 @@ cudaError_t launch_seq_embed_backward(const SeqEmbedArgs& a, cudaStream_t stream
 cudaError_t launch_token_step(const float* cls_logits, const float* reg, int64_t* step_dev, const cape_token_state& st,
                               const cape_tokenizer& tk, int B, int n_classes, cudaStream_t stream);
 
+cudaError_t launch_zero_masked_rows(void* value, const uint8_t* mask, long long rows, int row_bytes, cudaStream_t stream);
+
 void count_launch();
 
 // Tuning knobs: read once per process from the environment variable "CAPE_<NAME>" (std::call_once), changeable at run

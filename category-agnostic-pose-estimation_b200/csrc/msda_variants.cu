@@ -249,4 +249,39 @@ cudaError_t launch_points_sample_backward(const float* gout, const float* x, con
     return cudaGetLastError();
 }
 
+// ---- padding-mask fill of the projected value (MSDeformAttn.forward, /root/reference/models/deformable_transformer.py:96-97) ----
+// value[r, :] = 0 where mask[r].  A CTA owns 256 consecutive rows: it reads their 256 mask bytes and leaves at once when none
+// is set — for the all-False mask CAPE always passes the launch touches N*S bytes instead of reading and re-writing the
+// whole value tensor, with no host-side `mask.any()` synchronisation.
+namespace {
+template <int BYTES_PER_ROW_UNIT>
+__global__ void __launch_bounds__(256)
+zero_masked_rows_kernel(uint4* __restrict__ value, const uint8_t* __restrict__ mask, long long rows, int units_per_row) {
+    const long long r0 = static_cast<long long>(blockIdx.x) * 256;
+    const long long r = r0 + threadIdx.x;
+    const int mine = (r < rows && mask[r]) ? 1 : 0;
+    if (!__syncthreads_or(mine)) return;
+    __shared__ uint8_t flags[256];
+    flags[threadIdx.x] = static_cast<uint8_t>(mine);
+    __syncthreads();
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = 0; i < 256; ++i) {
+        if (!flags[i]) continue;
+        uint4* row = value + (r0 + i) * units_per_row;
+        for (int u = threadIdx.x; u < units_per_row; u += 256) row[u] = z;
+    }
+}
+}  // namespace
+
+cudaError_t launch_zero_masked_rows(void* value, const uint8_t* mask, long long rows, int row_bytes, cudaStream_t stream) {
+    if (rows == 0 || row_bytes == 0) return cudaSuccess;
+    if (row_bytes % 16 != 0) return cudaErrorInvalidValue;
+    const long long grid = (rows + 255) / 256;
+    if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    zero_masked_rows_kernel<16><<<static_cast<unsigned>(grid), 256, 0, stream>>>(static_cast<uint4*>(value), mask, rows,
+                                                                                row_bytes / 16);
+    count_launch();
+    return cudaGetLastError();
+}
+
 }  // namespace cape

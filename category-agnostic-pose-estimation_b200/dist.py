@@ -348,7 +348,7 @@ def rank_seed(seed: int, rank: int) -> int:
 
 def train_one_epoch_data_parallel(train_one_epoch, model, criterion, loader, optimizer, device, epoch: int,
                                   buckets: GradBuckets, accumulation_steps: int = 1, max_norm: float = 0.0, scaler=None,
-                                  queries_per_episode: int = 2, shard: bool = True, **kwargs):
+                                  queries_per_episode: int = 2, shard: bool = True, misc_module=None, **kwargs):
     """Run the reference's own ``train_one_epoch_episodic`` (passed in as ``train_one_epoch``; engine_cape.py:48) as one
     rank of a data-parallel job: the loader is sharded per rank, gradients are averaged over ranks from inside the last
     backward of every accumulation window (before the loop's ``clip_grad_norm_`` and ``optimizer.step()``), and
@@ -357,8 +357,21 @@ def train_one_epoch_data_parallel(train_one_epoch, model, criterion, loader, opt
     buckets.install()
     buckets.wrap_optimizer(optimizer)
     sharded = ShardedEpisodeLoader(loader, buckets, accumulation_steps, rank, world_size(), queries_per_episode, shard)
-    return train_one_epoch(model, criterion, sharded, optimizer, device, epoch, max_norm=max_norm,
-                           accumulation_steps=accumulation_steps, scaler=scaler, **kwargs)
+    # The reference's logging helper cannot run with more than one process: reduce_dict (util/misc.py:128-153) does
+    # torch.stack() over a loss dict that holds Python floats next to tensors and raises TypeError as soon as a process
+    # group exists (the reference never initialises one).  With `misc_module` (the imported util.misc) the
+    # loop's logging is kept per-rank for the duration of the call; gradients are still averaged by `buckets`.
+    saved = {}
+    if misc_module is not None and world_size() > 1:
+        for name, fn in (("get_world_size", lambda: 1), ("is_dist_avail_and_initialized", lambda: False)):
+            saved[name] = getattr(misc_module, name)
+            setattr(misc_module, name, fn)
+    try:
+        return train_one_epoch(model, criterion, sharded, optimizer, device, epoch, max_norm=max_norm,
+                               accumulation_steps=accumulation_steps, scaler=scaler, **kwargs)
+    finally:
+        for name, fn in saved.items():
+            setattr(misc_module, name, fn)
 
 
 def shard_sizes(total: int, world: int) -> Sequence[int]:
@@ -381,6 +394,14 @@ def bind_to_gpu_numa_node(device_index: int) -> int | None:
         with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
             node = int(f.read().strip())
         if node < 0:
+            # single-node topology (the B200 boxes of this pool report numa_node = -1 for every GPU): there is no socket
+            # to stay on; give every rank its own slice of the allowed cores instead so their copy / launch threads do
+            # not migrate onto each other
+            world = world_size()
+            cores = sorted(os.sched_getaffinity(0))
+            if world > 1 and len(cores) >= world:
+                rank = dist.get_rank() if dist.is_initialized() else device_index
+                os.sched_setaffinity(0, set(cores[rank::world]))
             return None
         with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
             cpus = set()

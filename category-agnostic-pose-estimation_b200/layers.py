@@ -22,6 +22,7 @@ from torch import nn
 
 from .gemm import linear as _linear
 from .modules import MSDeformAttn, ValueCache
+from .ops import masked_fill_rows_
 
 
 def _activation(name: str):
@@ -276,7 +277,7 @@ class IncrementalDecoder:
             ca = layer.cross_attn
             v = _linear(ca.value_proj, memory)
             if padding_mask is not None:
-                v = v.masked_fill(padding_mask[..., None], 0.0)
+                v = masked_fill_rows_(v, padding_mask)
             dst.copy_(v.view(dst.shape))
         self._shapes.copy_(spatial_shapes)
         self._starts.copy_(level_start_index)

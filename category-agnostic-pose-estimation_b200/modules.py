@@ -26,6 +26,7 @@ from torch import nn
 
 from . import functional as CF
 from .gemm import linear as _linear
+from .ops import masked_fill_rows_
 
 
 def _is_power_of_2(n) -> bool:
@@ -125,8 +126,10 @@ class MSDeformAttn(nn.Module):
             value = self._cache_load(N, Len_in)
         if value is None:
             value = _linear(self.value_proj, input_flatten)                                 # :95
-            if input_padding_mask is not None:
-                value = value.masked_fill(input_padding_mask[..., None], float(0))          # :96-97
+            if input_padding_mask is not None:                                              # :96-97
+                # in place on the fresh projection, decided per 256-row block on the device: the all-False mask the
+                # reference always passes costs one pass over the mask bytes, no copy of `value`, no host sync
+                value = masked_fill_rows_(value, input_padding_mask)
             value = value.view(N, Len_in, self.n_heads, self.d_model // self.n_heads)       # :98
             if not torch.is_grad_enabled():
                 self._cache_store(value)

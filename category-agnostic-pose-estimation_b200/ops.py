@@ -260,3 +260,51 @@ ms_deform_attn_decode.register_autograd(_fused_backward, setup_context=_fused_se
 # itself.  A blanket cast-to-fp32 rule would copy the whole (B, S, M, D) value — for the decode step that is the entire
 # projected-value cache — on every call.  The result equals the reference's AMP flow, whose fp32 sampling output is
 # rounded to half precision by the next autocast Linear anyway.
+
+
+# ---- padding-mask fill of the projected value (deformable_transformer.py:96-97) ---------------------------------------
+def _zero_masked_rows_(t: torch.Tensor, mask: torch.Tensor) -> None:
+    lib = _lib.load()
+    rows = mask.numel()
+    row_bytes = (t.numel() // max(rows, 1)) * t.element_size()
+    with torch.cuda.device(t.device):
+        rc = lib.cape_zero_masked_rows(_ptr(t), _ptr(mask), rows, row_bytes, _stream(t.device))
+    _lib.check(rc, "cape_zero_masked_rows")
+
+
+class _MaskedFillRows(torch.autograd.Function):
+    """``value.masked_fill(mask[..., None], 0)`` done IN PLACE on a tensor the caller owns (the fresh output of
+    value_proj), forward and backward, by a kernel that inspects the mask on the device and leaves un-masked blocks
+    untouched: for the all-False mask CAPE always passes, neither direction reads or writes the value tensor, and there is
+    no ``mask.any()`` host synchronisation.  The gradient arriving in backward is the freshly allocated ``grad_value`` of
+    the sampling op (single consumer), so it is zeroed in place as well."""
+
+    @staticmethod
+    def forward(ctx, value, mask):
+        ctx.mark_dirty(value)
+        ctx.save_for_backward(mask)
+        _zero_masked_rows_(value, mask)
+        return value
+
+    @staticmethod
+    def backward(ctx, grad):
+        (mask,) = ctx.saved_tensors
+        if not grad.is_contiguous() or grad.data_ptr() % 16:
+            grad = grad.contiguous().clone()
+        _zero_masked_rows_(grad, mask)
+        return grad, None
+
+
+def masked_fill_rows_(value: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """value (..., C) contiguous CUDA tensor produced by the caller (not a leaf, not shared), mask (...) bool."""
+    if mask.dtype != torch.bool:
+        mask = mask.bool()
+    mask = mask.contiguous()
+    row_bytes = value.shape[-1] * value.element_size()
+    if (not value.is_cuda or not value.is_contiguous() or value.data_ptr() % 16 or row_bytes % 16
+            or value.numel() != mask.numel() * value.shape[-1] or value.is_leaf and value.requires_grad):
+        return value.masked_fill(mask[..., None], float(0))
+    if value.requires_grad and torch.is_grad_enabled():
+        return _MaskedFillRows.apply(value, mask)
+    _zero_masked_rows_(value, mask)
+    return value

@@ -645,9 +645,13 @@ def _reference_transformer_config(ref) -> dict:
 def _live_transformer_state(ref) -> dict:
     """``ref.state_dict()`` without the cache buffers the reference's ``_setup_caches`` registers on every
     ``forward_inference`` and without the heads (attached as live modules instead)."""
+    # ... and without the two module lists CAPEModel hangs on the decoder for the duration of a call
+    # (cape_model.py:127-132, 187-194): attribute assignment registers them as sub-modules, the decoder never runs them
+    # (SURVEY.md Appendix A.7)
+    skip = ("decoder.class_embed.", "decoder.coords_embed.", "decoder.support_cross_attn_layers.",
+            "decoder.support_attn_norms.")
     return {k: v for k, v in ref.state_dict().items()
-            if ".kv_cache." not in k and ".cross_attn.cache." not in k
-            and not k.startswith(("decoder.class_embed.", "decoder.coords_embed."))}
+            if ".kv_cache." not in k and ".cross_attn.cache." not in k and not k.startswith(skip)}
 
 
 def mirror_from_reference(ref) -> DeformableTransformer:

@@ -161,6 +161,15 @@ CAPE_API int cape_points_sample_backward(const float* grad_out, const float* x, 
                                          int zero_grad_x, void* stream);
 
 /*
+ * Padding-mask fill of the projected value — `value = value.masked_fill(input_padding_mask[..., None], 0)`,
+ * models/deformable_transformer.py:96-97 — in place: value (rows, row_bytes / elem) row-major, mask (rows,) bytes
+ * (torch.bool), row_bytes % 16 == 0.  Rows are inspected on the device in blocks of 256; a block without a masked row
+ * returns without touching `value`, so the all-False mask CAPE always passes costs one pass over the MASK only and no
+ * host synchronisation.
+ */
+CAPE_API int cape_zero_masked_rows(void* value, const uint8_t* mask, int64_t rows, int row_bytes, void* stream);
+
+/*
  * Sequence side of the decoder: the data formats either side of the decode step, kept on the device.
  *
  * Bilinear token embedding — TransformerDecoder._seq_embed, models/deformable_transformer_v2.py:984-997:

@@ -824,3 +824,28 @@ def test_opcheck_registration():
             inp["sampling_locations"].requires_grad_(True), inp["attention_weights"].requires_grad_(True))
     torch.library.opcheck(torch.ops.cape.ms_deform_attn.default, args,
                           test_utils=("test_schema", "test_faketensor", "test_autograd_registration"))
+
+
+def test_masked_fill_rows_matches_masked_fill_forward_and_backward():
+    """deformable_transformer.py:96-97 done in place with the mask inspected on the device: all-False mask (CAPE's only
+    case) leaves the tensor untouched; masks with True rows give masked_fill's result and gradient."""
+    from cape_b200.ops import masked_fill_rows_
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(3, 700, 256, generator=g).cuda()
+    w = torch.randn(256, 256, generator=g).cuda().requires_grad_(True)
+    for frac in (0.0, 0.02, 1.0):
+        mask = (torch.rand(3, 700, generator=g) < frac).cuda()
+        before = cape_b200.launch_count()
+        got = masked_fill_rows_(x @ w, mask)
+        assert cape_b200.launch_count() == before + 1
+        want = (x @ w).masked_fill(mask[..., None], 0.0)
+        assert torch.equal(got, want)
+        gg, = torch.autograd.grad((got * got).sum(), w)
+        gw, = torch.autograd.grad((want * want).sum(), w)
+        assert torch.allclose(gg, gw, rtol=1e-5, atol=1e-4)
+    half = torch.randn(2, 300, 256, generator=g).cuda().half()
+    mask = (torch.rand(2, 300, generator=g) < 0.3).cuda()
+    assert torch.equal(masked_fill_rows_(half.clone(), mask), half.masked_fill(mask[..., None], 0.0))
+    leaf = torch.randn(2, 5, 32, device="cuda", requires_grad=True)          # a leaf is never modified in place
+    out = masked_fill_rows_(leaf, torch.ones(2, 5, dtype=torch.bool, device="cuda"))
+    assert out is not leaf and float(out.abs().sum()) == 0.0 and float(leaf.abs().sum()) > 0
