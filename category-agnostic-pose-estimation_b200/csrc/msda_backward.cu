@@ -285,7 +285,9 @@ cudaError_t launch_typed(const BwdArgs& a, cudaStream_t stream) {
         threads = (threads / 32) * 32;
         if (threads < 32) threads = 32;
         if (threads > kBwdMaxThreads) threads = kBwdMaxThreads;
-        int q_per_cta = tuning(kTuneBwdQpc, 128);
+        int q_per_cta = tuning(kTuneBwdQpc, 0);
+        if (q_per_cta <= 0)   // default: whole waves of the 4 x 148 resident 256-thread CTAs (an explicit BWD_QPC is taken as is)
+            q_per_cta = balanced_q_per_cta(static_cast<int64_t>(d.N) * d.M, d.Lq, 128, (kBwdMaxThreads / threads) * 2 * 148, 1);
         while (q_per_cta > 1 && static_cast<int64_t>(d.N) * d.M * ((d.Lq + q_per_cta - 1) / q_per_cta) < 148 * 4) q_per_cta >>= 1;
         if (q_per_cta > d.Lq) q_per_cta = d.Lq;
         if (q_per_cta < 1) q_per_cta = 1;
@@ -336,7 +338,7 @@ cudaError_t launch_value_typed(const BwdArgs& a, cudaStream_t stream) {
 
 cudaError_t launch_backward(const BwdArgs& a, cudaStream_t stream) {
     const int mode = tuning(kTuneBwdMode, 1);      // 1: L1 kernel + REDs; 2: staged rows + tensor-core scatter; 3: staged rows
-    if (mode == 2 || mode == 3) {
+    if (mode == 2 || mode == 3 || mode == 4) {   // 4: profiling only (results invalid), see msda_backward_staged.cu
         const cudaError_t e = launch_backward_staged(a, mode, stream);
         if (e == cudaSuccess) count_launch();
         if (e != cudaErrorNotSupported) return e;

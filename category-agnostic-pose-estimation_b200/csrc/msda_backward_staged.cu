@@ -7,18 +7,24 @@
 // per launch at the L2's ~51 G rows/s, with the LSU wavefront pipe right behind.  Here, per CTA
 // (persistent, one per SM, a contiguous range of the (image, head, query) space):
 //
-//   warps 0..30  sample: one query per warp at a time, lane = (point, channel quad).  Levels staged in shared memory are
-//                gathered with LDS.128; the other levels with LDG.128 as before.  grad_loc / grad_attn for all levels;
-//                REDs into grad_value only for the levels the tensor cores do NOT cover.
-//   warp 31      builds, for batches of 32 queries (thread = query), the bilinear weight matrix of the covered levels
-//                Wt[pixel][query] = sum over the query's samples of A * w_corner  (<= 32 non-zeros per column; plain
-//                LDS / FADD / STS read-modify-writes are race-free because a column has one owner), its tf32 "lo" part,
-//                and the transposed grad_out tile G[channel][query] (hi + lo) from a TMA-loaded copy; then lane 0 issues
-//                grad_value[pixel][channel] += Wt . G^T as tcgen05.mma.kind::tf32 (3xTF32: lo*hi + hi*lo + hi*hi, M = 128
-//                pixels, N = 32 channels, K = 8 queries per instruction) into accumulators in TENSOR MEMORY that live for
-//                the whole (image, head) segment.  After the MMAs of a batch complete (tcgen05.commit -> mbarrier) the
-//                touched entries are zeroed again, so the tile is never cleared wholesale.
-//   segment end  warps 0..3 read the accumulators (tcgen05.ld) and add them to grad_value with one RED per row and CTA.
+//   warps 0..30  sample: one query per warp at a time (batch b of a segment = 31 consecutive queries, warp w takes the
+//                w-th), lane = (point, channel quad).  Levels staged in shared memory are gathered with LDS.128, the others
+//                with LDG.128 as before; grad_loc / grad_attn for all levels; REDs into grad_value only for the levels the
+//                tensor cores do NOT cover.  For the covered levels the warp then writes ITS COLUMN of the batch's
+//                bilinear weight matrix Wt[pixel][query] (rows of 128 B = 32 query columns, 128-byte swizzle): lane =
+//                (point, level slot, corner) adds A * w_corner with `red.shared.add.f32` (corners of different points
+//                often coincide), re-reads the sum and stores its tf32 "lo" part in a second tile.  Entries written for
+//                the previous batch are zeroed first, so the tiles are never cleared wholesale.
+//                It also writes its query's column of the transposed grad_out operand G[channel | channel_lo][query]
+//                (lane -> one channel, hi row + lo row).
+//   warp 31      per batch: waits until all 31 columns are in (mbarrier, one arrival per sampling warp), and lane 0 issues
+//                    acc[pixel][0:64]  += Wt_hi . [G_hi | G_lo]        (tcgen05.mma.kind::tf32, M = 128, N = 64, K = 8)
+//                    acc[pixel][0:32]  += Wt_lo . G_hi                 (N = 32)
+//                i.e. 3xTF32 (hi*hi + hi*lo + lo*hi) in two instructions per (8 queries, 128 pixels), into accumulators in
+//                TENSOR MEMORY that live for the whole (image, head) segment; tcgen05.commit -> mbarrier tells the sampling
+//                warps when the tiles may be modified again (they are busy sampling the next batch meanwhile).
+//   segment end  warps 0..3 read the accumulators (tcgen05.ld), add the two column halves and add the result to grad_value
+//                with one RED per row and CTA.
 //
 // Covered levels = the last one or two levels whose pixels fit 384 rows (the CAPE pyramid: 16x16 + 8x8 = 320 pixels,
 // 50 % of all samples, ~21 of the ~51 in-bounds corner rows of a (query, head)).
@@ -30,15 +36,18 @@ namespace cape {
 
 namespace {
 
-constexpr int kBsThreads = 1024;
-constexpr int kSimtWarps = 31;
+#ifndef CAPE_BS_THREADS
+#define CAPE_BS_THREADS 1024
+#endif
+constexpr int kBsThreads = CAPE_BS_THREADS;       // one CTA per SM; -DCAPE_BS_THREADS=896|768 builds trade warps for registers
+constexpr int kSimtWarps = kBsThreads / 32 - 1;
 constexpr int kTcRows = 384;                      // pixels covered by the tensor-core scatter: 3 tiles of 128
-constexpr int kATile = kTcRows * 128;             // bytes of Wt[pixel][32 queries] fp32 (rows of 128 B, 128-byte swizzle)
-constexpr int kBTile = 32 * 128;                  // G[channel][32 queries]
-constexpr int kOffALo = kATile, kOffBHi = 2 * kATile, kOffBLo = kOffBHi + kBTile, kOffG = kOffBLo + kBTile;
-constexpr int kOffStage = kOffG + kBTile;         // staged value rows start here (1024-byte aligned)
+constexpr int kATile = kTcRows * 128;             // bytes of Wt[pixel][32 query columns] fp32 (rows of 128 B, 128-byte swizzle)
+constexpr int kBTile = 64 * 128;                  // G[channel (hi) | channel (lo)][32 query columns]
+constexpr int kOffALo = kATile, kOffB = 2 * kATile;
+constexpr int kOffStage = kOffB + kBTile;         // staged value rows start here (1024-byte aligned)
 constexpr int kBoxRowsB = 64;
-constexpr int kTmemColsB = 128;                   // 3 accumulators x 32 columns, rounded up to a power of two
+constexpr int kTmemColsB = 256;                   // 3 accumulators x 64 columns, rounded up to a power of two
 constexpr int kMaxDynSmemB = 227 * 1024 - 2048;
 
 // Cycle counters of the builder warp's phases (CTA 0 only; read back by cape_debug_counters for profiling runs).
@@ -65,15 +74,16 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
     return (static_cast<uint64_t>(hi) << 32) | lo;
 }
-// kind::tf32, fp32 accumulate, both operands K-major, M = 128, N = 32.
+// kind::tf32, fp32 accumulate, both operands K-major, M = 128; N = 64 ([G_hi | G_lo]) and N = 32 (G_hi).
+constexpr uint32_t kIdescM128N64 = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 constexpr uint32_t kIdescM128N32 = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
 
-__device__ __forceinline__ void umma_tf32_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate) {
+__device__ __forceinline__ void umma_tf32_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(kIdescM128N32), "r"(accumulate)
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit_to(uint32_t bar) {
@@ -161,13 +171,13 @@ msda_bwd_staged_kernel(const __grid_constant__ CUtensorMap vmap, const __grid_co
     constexpr int L = 4, D = 32;
     constexpr int kRowB = D * static_cast<int>(sizeof(VT));
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_storage[3];
+    __shared__ __align__(8) uint64_t bar_storage[4];
     __shared__ uint32_t tmem_slot;
     const uint32_t base = (smem_addr_u32(smem_raw) + 1023u) & ~1023u;       // swizzle atoms need 1024-byte alignment
     const int tid = threadIdx.x, lane = tid & 31, warp = uniform_warp_id();
     const int rowStride = M * D;
     const uint32_t bar_stage = smem_addr_u32(&bar_storage[0]), bar_g = smem_addr_u32(&bar_storage[1]),
-                   bar_mma = smem_addr_u32(&bar_storage[2]);
+                   bar_mma = smem_addr_u32(&bar_storage[2]), bar_full = smem_addr_u32(&bar_storage[3]);
 
     int H[L], W[L], st[L];
 #pragma unroll
@@ -204,7 +214,8 @@ msda_bwd_staged_kernel(const __grid_constant__ CUtensorMap vmap, const __grid_co
             tc_rows = st[L - 1] + tc_rows - st[L - 2];
         }
     }
-    const bool any_tc = tc_rows > 0;
+    const bool drop_only = use_tc == 2;      // PROFILING ONLY (BWD_MODE 4): covered levels' REDs dropped, nothing replaces them
+    const bool any_tc = tc_rows > 0 && !drop_only;
     const int n_mt = (tc_rows + 127) >> 7;
     bool in_smem[L];
     uint32_t lvl_off[L];
@@ -214,15 +225,16 @@ msda_bwd_staged_kernel(const __grid_constant__ CUtensorMap vmap, const __grid_co
         lvl_off[l] = in_smem[l] ? static_cast<uint32_t>(st[l] - base_row) * kRowB : static_cast<uint32_t>(st[l]) * rowStride;
     }
 
-    // ---- one-time set-up: barriers, tensor memory, zeroed weight tiles ------------------------------------------------
+    // ---- one-time set-up: barriers, tensor memory, zeroed weight / operand tiles ---------------------------------------
     if (tid == 0) {
         mbarrier_init(bar_stage, 1);
         mbarrier_init(bar_g, 1);
         mbarrier_init(bar_mma, 1);
+        mbarrier_init(bar_full, kSimtWarps);
         mbarrier_init_fence();
     }
     if (any_tc) {
-        for (int i = tid; i < 2 * kATile / 16; i += kBsThreads)
+        for (int i = tid; i < kOffStage / 16; i += kBsThreads)
             asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};" ::"r"(base + i * 16), "f"(0.f) : "memory");
         fence_proxy_async_shared();
         if (warp == kSimtWarps) {
@@ -236,20 +248,25 @@ msda_bwd_staged_kernel(const __grid_constant__ CUtensorMap vmap, const __grid_co
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = any_tc ? *reinterpret_cast<volatile uint32_t*>(&tmem_slot) : 0u;
+    const uint32_t a_hi = base, a_lo = base + kOffALo, b_tile = base + kOffB;
 
     const long long total = static_cast<long long>(N) * M * Lq;
     long long pos = static_cast<long long>(blockIdx.x) * per_cta;
     const long long end = min(total, pos + per_cta);
-    uint32_t stage_phase = 0, g_phase = 0, mma_phase = 0;
-    uint32_t prev[16];                       // builder: packed tile indices (2 x 16 bit) of the entries written last batch
-#pragma unroll
-    for (int i = 0; i < 16; ++i) prev[i] = 0xffffffffu;
+    const int nsimt = any_tc ? kSimtWarps : kBsThreads / 32;
+    uint32_t stage_phase = 0;
+    uint32_t gb = 0;                         // batches completed by this CTA (same value in every warp): barrier phases
+    uint32_t prev_idx = 0xffffu;             // sampling lanes: tile entry written for the previous batch
+    const bool kProfile = profile && blockIdx.x == 0 && lane == 0;
+    long long cyc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long t_prev = kProfile ? clock64() : 0;
 
     while (pos < end) {
         const int nm = static_cast<int>(pos / Lq);
         const int q_begin = static_cast<int>(pos - static_cast<long long>(nm) * Lq);
         const int q_end = static_cast<int>(min(static_cast<long long>(Lq), q_begin + (end - pos)));
         const int n = nm / M, m = nm - n * M;
+        const int nb = (q_end - q_begin + nsimt - 1) / nsimt;
         __syncthreads();                     // previous segment: rows read, accumulators flushed
         if (rows > 0) {
             if (warp == 0) {
@@ -259,14 +276,13 @@ msda_bwd_staged_kernel(const __grid_constant__ CUtensorMap vmap, const __grid_co
                     tma_load_box_2d(base + kOffStage + b * kBoxRowsB * kRowB, &vmap, bar_stage, m * D,
                                     n * S + base_row + b * kBoxRowsB);
             }
-            if (warp != kSimtWarps || !any_tc) mbarrier_wait(bar_stage, stage_phase);   // the builder never reads value rows
+            if (warp != kSimtWarps || !any_tc) mbarrier_wait(bar_stage, stage_phase);   // the MMA warp never reads value rows
             stage_phase ^= 1;
         }
 
         if (warp < kSimtWarps || !any_tc) {
             // ===== sampling warps ==========================================================================================
             const int p = lane >> 3, k = lane & 7;
-            const int nsimt = any_tc ? kSimtWarps : kBsThreads / 32;
             const int64_t headOff = (static_cast<int64_t>(n) * S * M + m) * D + k * 4;
             const VT* vbase = value + headOff;
             float* gbase = gvalue + headOff;
@@ -275,287 +291,203 @@ msda_bwd_staged_kernel(const __grid_constant__ CUtensorMap vmap, const __grid_co
 #pragma unroll
             for (int l = 0; l < L; ++l)
                 if ((lane >> 3) == l) dimf = static_cast<float>((lane & 1) ? H[l] : W[l]);
-            const long long t_simt = (profile && blockIdx.x == 0 && tid == 0) ? clock64() : 0;
-            for (int q = q_begin + warp; q < q_end; q += nsimt) {
-                const int64_t qm = (static_cast<int64_t>(n) * Lq + q) * M + m;
-                float locv = to_f32(locp[qm * (L * 8) + lane]);
-                float attnv = FUSED ? -INFINITY : 0.f;
-                if (lane < L * 4) attnv = to_f32(attnp[qm * (L * 4) + lane]);
-                const float4 g = ld4(gout + qm * D + k * 4);
-                if (FUSED) {
-                    float mx = attnv;
+            // this lane's entry of the weight tile: point p, level slot k >> 2 (of the two covered levels), corner k & 3
+            const int li = k >> 2;
+            const bool e_tc = li ? tc[L - 1] : tc[L - 2];
+            const int e_W = li ? W[L - 1] : W[L - 2], e_H = li ? H[L - 1] : H[L - 2];
+            const int e_row0 = (li ? st[L - 1] : st[L - 2]) - tc_base;
+            for (int i = 0; i < nb; ++i) {
+                const int q = q_begin + i * nsimt + warp;
+                const bool active = q < q_end;
+                float e_px = -4.f, e_py = -4.f, e_a = 0.f;      // this lane's sample of the covered levels (point p, level slot li)
+                float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (active) {
+                    const int64_t qm = (static_cast<int64_t>(n) * Lq + q) * M + m;
+                    float locv = to_f32(locp[qm * (L * 8) + lane]);
+                    float attnv = FUSED ? -INFINITY : 0.f;
+                    if (lane < L * 4) attnv = to_f32(attnp[qm * (L * 4) + lane]);
+                    g = ld4(gout + qm * D + k * 4);
+                    if (FUSED) {
+                        float mx = attnv;
 #pragma unroll
-                    for (int s = 8; s >= 1; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFullMask, mx, s));
-                    const float e = (lane < L * 4) ? expf(attnv - mx) : 0.f;
-                    float sum = e;
+                        for (int s = 8; s >= 1; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFullMask, mx, s));
+                        const float e = (lane < L * 4) ? expf(attnv - mx) : 0.f;
+                        float sum = e;
 #pragma unroll
-                    for (int s = 8; s >= 1; s >>= 1) sum += __shfl_xor_sync(kFullMask, sum, s);
-                    attnv = e / sum;
-                    locv = __ldg(refp + (static_cast<int64_t>(n) * Lq + q) * (L * 2) + (lane >> 3) * 2 + (lane & 1)) + locv / dimf;
-                }
-                locv = pixel_coord(locv, dimf);
-                float part[12], a_lvl[4];
-#pragma unroll
-                for (int l = 0; l < L; ++l) {
-                    const float px = __shfl_sync(kFullMask, locv, l * 8 + p * 2);
-                    const float py = __shfl_sync(kFullMask, locv, l * 8 + p * 2 + 1);
-                    const float a = __shfl_sync(kFullMask, attnv, l * 4 + p);
-                    const float xf = floorf(px), yf = floorf(py);
-                    const float lx = px - xf, ly = py - yf;
-                    const int x0 = static_cast<int>(xf), y0 = static_cast<int>(yf);
-                    const bool x0ok = static_cast<unsigned>(x0) < static_cast<unsigned>(W[l]);
-                    const bool x1ok = static_cast<unsigned>(x0 + 1) < static_cast<unsigned>(W[l]);
-                    const bool y0ok = static_cast<unsigned>(y0) < static_cast<unsigned>(H[l]);
-                    const bool y1ok = static_cast<unsigned>(y0 + 1) < static_cast<unsigned>(H[l]);
-                    const int r00 = y0 * W[l] + x0;
-                    float4 v00, v01, v10, v11;
-                    if (in_smem[l]) {
-                        const uint32_t a00 = sbase + lvl_off[l] + static_cast<uint32_t>(r00 * kRowB);
-                        const uint32_t a10 = a00 + static_cast<uint32_t>(W[l] * kRowB);
-                        v00 = lds_row4_or_zero<VT>(a00, y0ok & x0ok);
-                        v01 = lds_row4_or_zero<VT>(a00 + kRowB, y0ok & x1ok);
-                        v10 = lds_row4_or_zero<VT>(a10, y1ok & x0ok);
-                        v11 = lds_row4_or_zero<VT>(a10 + kRowB, y1ok & x1ok);
-                    } else {
-                        const int o00 = static_cast<int>(lvl_off[l]) + r00 * rowStride;
-                        const int o10 = o00 + W[l] * rowStride;
-                        v00 = ld4_or_zero(vbase + o00, y0ok & x0ok);
-                        v01 = ld4_or_zero(vbase + o00 + rowStride, y0ok & x1ok);
-                        v10 = ld4_or_zero(vbase + o10, y1ok & x0ok);
-                        v11 = ld4_or_zero(vbase + o10 + rowStride, y1ok & x1ok);
+                        for (int s = 8; s >= 1; s >>= 1) sum += __shfl_xor_sync(kFullMask, sum, s);
+                        attnv = e / sum;
+                        locv = __ldg(refp + (static_cast<int64_t>(n) * Lq + q) * (L * 2) + (lane >> 3) * 2 + (lane & 1)) + locv / dimf;
                     }
-                    const float hx = 1.f - lx, hy = 1.f - ly;
-                    if (!tc[l]) {          // levels the tensor cores do not cover: vector REDs as in msda_bwd_fast_kernel
-                        const int o00 = st[l] * rowStride + r00 * rowStride;
-                        const int o10 = o00 + W[l] * rowStride;
-                        const float ahy = a * hy, aly = a * ly;
-                        float c = ahy * hx;
-                        { const float4 cg = mul4(c, g); red_add4_if(gbase + o00, y0ok & x0ok, cg.x, cg.y, cg.z, cg.w); }
-                        c = ahy * lx;
-                        { const float4 cg = mul4(c, g); red_add4_if(gbase + o00 + rowStride, y0ok & x1ok, cg.x, cg.y, cg.z, cg.w); }
-                        c = aly * hx;
-                        { const float4 cg = mul4(c, g); red_add4_if(gbase + o10, y1ok & x0ok, cg.x, cg.y, cg.z, cg.w); }
-                        c = aly * lx;
-                        { const float4 cg = mul4(c, g); red_add4_if(gbase + o10 + rowStride, y1ok & x1ok, cg.x, cg.y, cg.z, cg.w); }
+                    locv = pixel_coord(locv, dimf);
+                    float part[12], a_lvl[4];
+#pragma unroll
+                    for (int l = 0; l < L; ++l) {
+                        const float px = __shfl_sync(kFullMask, locv, l * 8 + p * 2);
+                        const float py = __shfl_sync(kFullMask, locv, l * 8 + p * 2 + 1);
+                        const float a = __shfl_sync(kFullMask, attnv, l * 4 + p);
+                        if (l >= L - 2 && li == l - (L - 2)) {
+                            e_px = px;
+                            e_py = py;
+                            e_a = a;
+                        }
+                        const float xf = floorf(px), yf = floorf(py);
+                        const float lx = px - xf, ly = py - yf;
+                        const int x0 = static_cast<int>(xf), y0 = static_cast<int>(yf);
+                        const bool x0ok = static_cast<unsigned>(x0) < static_cast<unsigned>(W[l]);
+                        const bool x1ok = static_cast<unsigned>(x0 + 1) < static_cast<unsigned>(W[l]);
+                        const bool y0ok = static_cast<unsigned>(y0) < static_cast<unsigned>(H[l]);
+                        const bool y1ok = static_cast<unsigned>(y0 + 1) < static_cast<unsigned>(H[l]);
+                        const int r00 = y0 * W[l] + x0;
+                        float4 v00, v01, v10, v11;
+                        if (in_smem[l]) {
+                            const uint32_t a00 = sbase + lvl_off[l] + static_cast<uint32_t>(r00 * kRowB);
+                            const uint32_t a10 = a00 + static_cast<uint32_t>(W[l] * kRowB);
+                            v00 = lds_row4_or_zero<VT>(a00, y0ok & x0ok);
+                            v01 = lds_row4_or_zero<VT>(a00 + kRowB, y0ok & x1ok);
+                            v10 = lds_row4_or_zero<VT>(a10, y1ok & x0ok);
+                            v11 = lds_row4_or_zero<VT>(a10 + kRowB, y1ok & x1ok);
+                        } else {
+                            const int o00 = static_cast<int>(lvl_off[l]) + r00 * rowStride;
+                            const int o10 = o00 + W[l] * rowStride;
+                            v00 = ld4_or_zero(vbase + o00, y0ok & x0ok);
+                            v01 = ld4_or_zero(vbase + o00 + rowStride, y0ok & x1ok);
+                            v10 = ld4_or_zero(vbase + o10, y1ok & x0ok);
+                            v11 = ld4_or_zero(vbase + o10 + rowStride, y1ok & x1ok);
+                        }
+                        const float hx = 1.f - lx, hy = 1.f - ly;
+                        if (!tc[l]) {          // levels the tensor cores do not cover: vector REDs as in msda_bwd_fast_kernel
+                            const int o00 = st[l] * rowStride + r00 * rowStride;
+                            const int o10 = o00 + W[l] * rowStride;
+                            const float ahy = a * hy, aly = a * ly;
+                            float c = ahy * hx;
+                            { const float4 cg = mul4(c, g); red_add4_if(gbase + o00, y0ok & x0ok, cg.x, cg.y, cg.z, cg.w); }
+                            c = ahy * lx;
+                            { const float4 cg = mul4(c, g); red_add4_if(gbase + o00 + rowStride, y0ok & x1ok, cg.x, cg.y, cg.z, cg.w); }
+                            c = aly * hx;
+                            { const float4 cg = mul4(c, g); red_add4_if(gbase + o10, y1ok & x0ok, cg.x, cg.y, cg.z, cg.w); }
+                            c = aly * lx;
+                            { const float4 cg = mul4(c, g); red_add4_if(gbase + o10 + rowStride, y1ok & x1ok, cg.x, cg.y, cg.z, cg.w); }
+                        }
+                        const float d00 = dot4(g, v00), d01 = dot4(g, v01), d10 = dot4(g, v10), d11 = dot4(g, v11);
+                        part[l * 3] = hy * (hx * d00 + lx * d01) + ly * (hx * d10 + lx * d11);
+                        const float gx = hy * (d01 - d00) + ly * (d11 - d10);
+                        const float gy = hx * (d10 - d00) + lx * (d11 - d01);
+                        part[l * 3 + 1] = FUSED ? a * gx : a * static_cast<float>(W[l]) * gx;
+                        part[l * 3 + 2] = FUSED ? a * gy : a * static_cast<float>(H[l]) * gy;
+                        a_lvl[l] = a;
                     }
-                    const float d00 = dot4(g, v00), d01 = dot4(g, v01), d10 = dot4(g, v10), d11 = dot4(g, v11);
-                    part[l * 3] = hy * (hx * d00 + lx * d01) + ly * (hx * d10 + lx * d11);
-                    const float gx = hy * (d01 - d00) + ly * (d11 - d10);
-                    const float gy = hx * (d10 - d00) + lx * (d11 - d01);
-                    part[l * 3 + 1] = FUSED ? a * gx : a * static_cast<float>(W[l]) * gx;
-                    part[l * 3 + 2] = FUSED ? a * gy : a * static_cast<float>(H[l]) * gy;
-                    a_lvl[l] = a;
-                }
-                float sum[3];
-                transpose_reduce12s(part, k, sum);
-                const int lvl = k >> 1;
-                const bool owner = !(k & 1);
-                if (FUSED) {
-                    float r_a = 0.f;
+                    float sum[3];
+                    transpose_reduce12s(part, k, sum);
+                    const int lvl = k >> 1;
+                    const bool owner = !(k & 1);
+                    if (FUSED) {
+                        float r_a = 0.f;
 #pragma unroll
-                    for (int l = 0; l < L; ++l)
-                        if (lvl == l) r_a = a_lvl[l];
-                    float dot = owner ? r_a * sum[0] : 0.f;
+                        for (int l = 0; l < L; ++l)
+                            if (lvl == l) r_a = a_lvl[l];
+                        float dot = owner ? r_a * sum[0] : 0.f;
 #pragma unroll
-                    for (int s = 16; s >= 1; s >>= 1) dot += __shfl_xor_sync(kFullMask, dot, s);
-                    sum[0] = r_a * (sum[0] - dot);
+                        for (int s = 16; s >= 1; s >>= 1) dot += __shfl_xor_sync(kFullMask, dot, s);
+                        sum[0] = r_a * (sum[0] - dot);
+                    }
+                    if (owner) {
+                        const int si = lvl * 4 + p;
+                        gattn[qm * (L * 4) + si] = from_f32<AT>(sum[0]);
+                        gloc[(qm * (L * 4) + si) * 2] = from_f32<AT>(sum[1]);
+                        gloc[(qm * (L * 4) + si) * 2 + 1] = from_f32<AT>(sum[2]);
+                    }
                 }
-                if (owner) {
-                    const int si = lvl * 4 + p;
-                    gattn[qm * (L * 4) + si] = from_f32<AT>(sum[0]);
-                    gloc[(qm * (L * 4) + si) * 2] = from_f32<AT>(sum[1]);
-                    gloc[(qm * (L * 4) + si) * 2 + 1] = from_f32<AT>(sum[2]);
+                if (any_tc) {
+                    // ---- this warp's column (index = warp) of the batch's weight tiles ----
+                    const float xf = floorf(e_px), yf = floorf(e_py);
+                    const float lx = e_px - xf, ly = e_py - yf;
+                    const int xc = static_cast<int>(xf) + (k & 1), yc = static_cast<int>(yf) + ((k >> 1) & 1);
+                    const bool valid = e_tc && static_cast<unsigned>(xc) < static_cast<unsigned>(e_W) &&
+                                       static_cast<unsigned>(yc) < static_cast<unsigned>(e_H);
+                    const float wgt = e_a * ((k & 2) ? ly : 1.f - ly) * ((k & 1) ? lx : 1.f - lx);
+                    const uint32_t idx = valid ? tile_index(e_row0 + yc * e_W + xc, warp) : 0xffffu;
+                    if (gb > 0) mbarrier_wait(bar_mma, (gb - 1) & 1);      // the previous batch's MMAs have read the tiles
+                    if (prev_idx != 0xffffu) {
+                        sts_f32(a_hi + prev_idx * 4, 0.f);
+                        sts_f32(a_lo + prev_idx * 4, 0.f);
+                    }
+                    __syncwarp();
+#ifdef CAPE_BS_MATCH
+                    // variant: lanes that target the same entry are summed in registers (match.any + shuffles), plain stores
+                    {
+                        const unsigned peers = __match_any_sync(kFullMask, valid ? idx : (0x10000u + lane));
+                        float wsum = wgt;
+                        unsigned rest = peers & ~(1u << lane);
+                        while (__any_sync(kFullMask, rest != 0)) {
+                            const int src = rest ? (__ffs(rest) - 1) : lane;
+                            const float other = __shfl_sync(kFullMask, wgt, src);
+                            if (rest) {
+                                wsum += other;
+                                rest &= rest - 1;
+                            }
+                        }
+                        if (valid && lane == (__ffs(peers) - 1)) {
+                            sts_f32(a_hi + idx * 4, wsum);
+                            sts_f32(a_lo + idx * 4, tf32_lo_part(wsum));
+                        }
+                    }
+#else
+                    // corners of different points often coincide: shared-memory float add (a CAS loop on sm_100, ATOMS.CAST.SPIN)
+                    if (valid) asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(a_hi + idx * 4), "f"(wgt) : "memory");
+                    __syncwarp();
+                    if (valid) sts_f32(a_lo + idx * 4, tf32_lo_part(lds_f32(a_hi + idx * 4)));
+#endif
+                    prev_idx = idx;
+                    {   // this query's column of the transposed grad_out operand: lane -> channel 4k + p (hi row, lo row)
+                        const int ch = k * 4 + p;
+                        const float gv = p == 0 ? g.x : (p == 1 ? g.y : (p == 2 ? g.z : g.w));
+                        const uint32_t o = static_cast<uint32_t>(ch) * 128u + ((((static_cast<uint32_t>(warp) >> 2) ^ (ch & 7)) << 4) |
+                                                                               ((static_cast<uint32_t>(warp) & 3u) << 2));
+                        sts_f32(b_tile + o, gv);
+                        sts_f32(b_tile + 32 * 128 + o, tf32_lo_part(gv));
+                    }
+                    fence_proxy_async_shared();
+                    __syncwarp();
+                    if (lane == 0) mbarrier_arrive(bar_full);
+                    ++gb;
                 }
             }
-            if (profile && blockIdx.x == 0 && tid == 0)
-                atomicAdd(reinterpret_cast<unsigned long long*>(&g_bs_cycles[10]), static_cast<unsigned long long>(clock64() - t_simt));
         } else {
-            // ===== builder warp: weight tiles of the covered levels + tensor-core scatter ===================================
-            const uint32_t a_hi = base, a_lo = base + kOffALo, b_hi = base + kOffBHi, b_lo = base + kOffBLo, g_st = base + kOffG;
+            // ===== MMA warp: transposed grad_out operand + tensor-core scatter of the batch ================================
             bool first = true;              // first batch of the segment overwrites the accumulators
-            bool mma_pending = false;
-            const bool kProfile = profile && blockIdx.x == 0 && lane == 0;
-            long long cyc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-            long long t_prev = kProfile ? clock64() : 0;
-            for (int qb = q_begin; qb < q_end; qb += 32) {
-                const int q = qb + lane;
-                const bool active = q < q_end;
-                const int64_t qm = (static_cast<int64_t>(n) * Lq + (active ? q : q_begin)) * M + m;
-                constexpr bool kGTma = sizeof(VT) == 4;   // 16-bit grad_out rows are read with plain loads below
-                if (kGTma && lane == 0) {   // this batch's grad_out rows (32 queries x 32 channels of head m), 128-byte swizzle
-                    mbarrier_arrive_expect_tx(bar_g, kBTile);
-                    tma_load_box_2d(g_st, &gmap, bar_g, m * D, n * Lq + qb);
-                }
-                // the query's samples on the covered levels
-                float sx[8], sy[8], sa[8];  // pixel coordinates and weights of samples (level slot, point)
-#pragma unroll
-                for (int li = 0; li < 2; ++li) {
-                    const int l = L - 2 + li;
-#pragma unroll
-                    for (int pt = 0; pt < 4; ++pt) {
-                        sx[li * 4 + pt] = -4.f;
-                        sy[li * 4 + pt] = -4.f;
-                        sa[li * 4 + pt] = 0.f;
-                    }
-                    if (!tc[l] || !active) continue;
-                    const float wl = static_cast<float>(W[l]), hl = static_cast<float>(H[l]);
-#pragma unroll
-                    for (int pt = 0; pt < 4; ++pt) {
-                        float lx_ = to_f32(locp[qm * (L * 8) + l * 8 + pt * 2]);
-                        float ly_ = to_f32(locp[qm * (L * 8) + l * 8 + pt * 2 + 1]);
-                        if (FUSED) {
-                            const float* r = refp + (static_cast<int64_t>(n) * Lq + q) * (L * 2) + l * 2;
-                            lx_ = __ldg(r) + lx_ / wl;
-                            ly_ = __ldg(r + 1) + ly_ / hl;
-                        }
-                        sx[li * 4 + pt] = pixel_coord(lx_, wl);
-                        sy[li * 4 + pt] = pixel_coord(ly_, hl);
-                        if (!FUSED) sa[li * 4 + pt] = to_f32(attnp[qm * (L * 4) + l * 4 + pt]);
-                    }
-                }
-                CAPE_TICK(0);               // sample loads + coordinates
-                if (FUSED && active) {      // softmax over the (q, m)'s 16 logits (deformable_transformer.py:100-101)
-                    float lg[16], mx = -INFINITY;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        lg[i] = to_f32(attnp[qm * 16 + i]);
-                        mx = fmaxf(mx, lg[i]);
-                    }
-                    float sum = 0.f;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        lg[i] = expf(lg[i] - mx);
-                        sum += lg[i];
-                    }
-#pragma unroll
-                    for (int li = 0; li < 2; ++li)
-#pragma unroll
-                        for (int pt = 0; pt < 4; ++pt) sa[li * 4 + pt] = tc[L - 2 + li] ? lg[(L - 2 + li) * 4 + pt] / sum : 0.f;
-                }
-                // the tiles are free once the previous batch's MMAs have completed
-                if (mma_pending) {
-                    mbarrier_wait(bar_mma, mma_phase);
-                    mma_phase ^= 1;
-                    mma_pending = false;
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                }
-                CAPE_TICK(1);               // wait for the previous batch's MMAs
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {          // un-write last batch's entries (hi and lo tiles)
-                    const uint32_t e0 = prev[i] & 0xffffu, e1 = prev[i] >> 16;
-                    if (e0 != 0xffffu) {
-                        sts_f32(a_hi + e0 * 4, 0.f);
-                        sts_f32(a_lo + e0 * 4, 0.f);
-                    }
-                    if (e1 != 0xffffu) {
-                        sts_f32(a_hi + e1 * 4, 0.f);
-                        sts_f32(a_lo + e1 * 4, 0.f);
-                    }
-                }
-                CAPE_TICK(2);               // zeroing
-                // accumulate this query's corner weights into its column (the column has one owner: no race)
-#pragma unroll
-                for (int s = 0; s < 8; ++s) {
-                    const int l = L - 2 + (s >> 2);
-                    const float px = sx[s], py = sy[s], a = sa[s];
-                    const float xf = floorf(px), yf = floorf(py);
-                    const float lx = px - xf, ly = py - yf;
-                    const int x0 = static_cast<int>(xf), y0 = static_cast<int>(yf);
-                    const bool x0ok = static_cast<unsigned>(x0) < static_cast<unsigned>(W[l]);
-                    const bool x1ok = static_cast<unsigned>(x0 + 1) < static_cast<unsigned>(W[l]);
-                    const bool y0ok = static_cast<unsigned>(y0) < static_cast<unsigned>(H[l]);
-                    const bool y1ok = static_cast<unsigned>(y0 + 1) < static_cast<unsigned>(H[l]);
-                    const int r00 = st[l] - tc_base + y0 * W[l] + x0;
-                    const float hx = 1.f - lx, hy = 1.f - ly;
-                    const float ahy = a * hy, aly = a * ly;
-                    const bool ok[4] = {y0ok & x0ok, y0ok & x1ok, y1ok & x0ok, y1ok & x1ok};
-                    const int row[4] = {r00, r00 + 1, r00 + W[l], r00 + W[l] + 1};
-                    const float w[4] = {ahy * hx, ahy * lx, aly * hx, aly * lx};
-                    uint32_t idx[4];
-                    float cur[4];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {       // the 4 corners of one sample are distinct rows: independent RMWs
-                        idx[c] = ok[c] ? tile_index(row[c], lane) : 0xffffu;
-                        cur[c] = ok[c] ? lds_f32(a_hi + idx[c] * 4) : 0.f;
-                    }
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        if (ok[c]) sts_f32(a_hi + idx[c] * 4, cur[c] + w[c]);
-                    prev[s * 2] = idx[0] | (idx[1] << 16);
-                    prev[s * 2 + 1] = idx[2] | (idx[3] << 16);
-                }
-                CAPE_TICK(3);               // read-modify-writes
-                // lo parts of the finished column (idempotent for entries hit more than once)
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const uint32_t e0 = prev[i] & 0xffffu, e1 = prev[i] >> 16;
-                    if (e0 != 0xffffu) sts_f32(a_lo + e0 * 4, tf32_lo_part(lds_f32(a_hi + e0 * 4)));
-                    if (e1 != 0xffffu) sts_f32(a_lo + e1 * 4, tf32_lo_part(lds_f32(a_hi + e1 * 4)));
-                }
-                CAPE_TICK(4);               // lo parts
-                // G^T tile: channel rows, this query's column (zeros for a query slot past the segment)
-                if (kGTma) {
-                    mbarrier_wait(bar_g, g_phase);
-                    g_phase ^= 1;
-                }
-                CAPE_TICK(5);               // wait for the grad_out tile
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (active) {
-                        if (kGTma) {
-                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                         : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                                         : "r"(g_st + lane * 128 + ((j ^ (lane & 7)) << 4))
-                                         : "memory");
-                        } else {
-                            v = ld4(gout + qm * D + j * 4);   // 16-bit grad_out: plain loads (the fp32 tile map does not apply)
-                        }
-                    }
-                    const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const int ch = j * 4 + c;
-                        const uint32_t o = static_cast<uint32_t>(ch) * 128u + ((((static_cast<uint32_t>(lane) >> 2) ^ (ch & 7)) << 4) |
-                                                                               ((static_cast<uint32_t>(lane) & 3u) << 2));
-                        sts_f32(b_hi + o, vv[c]);
-                        sts_f32(b_lo + o, tf32_lo_part(vv[c]));
-                    }
-                }
-                fence_proxy_async_shared();
-                __syncwarp();
-                CAPE_TICK(6);               // G^T tiles
+            for (int i = 0; i < nb; ++i) {
+                const int qb = q_begin + i * kSimtWarps;
+                const int cnt = min(kSimtWarps, q_end - qb);
+                CAPE_TICK(0);
+                mbarrier_wait(bar_full, gb & 1);            // all 31 columns of the weight / grad_out tiles are in
+                CAPE_TICK(4);
                 if (lane == 0) {
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const int ksteps = (min(32, q_end - qb) + 7) >> 3;
+                    const int ksteps = (cnt + 7) >> 3;
                     for (int ks = 0; ks < ksteps; ++ks) {
                         const uint64_t adv = static_cast<uint64_t>(ks * 2);     // 8 tf32 = 32 bytes along K
-                        const uint64_t dbh = umma_desc_sw128(b_hi) + adv, dbl = umma_desc_sw128(b_lo) + adv;
+                        const uint64_t db = umma_desc_sw128(b_tile) + adv;
                         for (int mt = 0; mt < n_mt; ++mt) {
-                            const uint32_t acc = tmem_base + mt * 32;
+                            const uint32_t acc = tmem_base + mt * 64;
                             const uint64_t dah = umma_desc_sw128(a_hi + mt * 128 * 128) + adv;
                             const uint64_t dal = umma_desc_sw128(a_lo + mt * 128 * 128) + adv;
-                            umma_tf32_ss(acc, dal, dbh, (first && ks == 0) ? 0u : 1u);
-                            umma_tf32_ss(acc, dah, dbl, 1u);
-                            umma_tf32_ss(acc, dah, dbh, 1u);
+                            umma_tf32_ss(acc, dah, db, kIdescM128N64, (first && ks == 0) ? 0u : 1u);   // hi*hi | hi*lo
+                            umma_tf32_ss(acc, dal, db, kIdescM128N32, 1u);                             // + lo*hi
                         }
                     }
                     umma_commit_to(bar_mma);
                 }
                 __syncwarp();
-                CAPE_TICK(7);               // MMA issue
+                CAPE_TICK(5);
                 first = false;
-                mma_pending = true;
+                ++gb;
                 if (kProfile) cyc[9] += 1;
             }
-            if (mma_pending) {              // accumulators complete before the segment's flush
-                mbarrier_wait(bar_mma, mma_phase);
-                mma_phase ^= 1;
+            if (nb > 0) {                   // accumulators complete before the segment's flush
+                mbarrier_wait(bar_mma, (gb - 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
-            CAPE_TICK(8);
-            if (kProfile)
-                for (int i = 0; i < 10; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(&g_bs_cycles[i]),
-                                                       static_cast<unsigned long long>(cyc[i]));
+            CAPE_TICK(6);
         }
         // ---- segment end: add the accumulators of the covered levels to grad_value ------------------------------------
         if (any_tc) {
@@ -564,24 +496,31 @@ msda_bwd_staged_kernel(const __grid_constant__ CUtensorMap vmap, const __grid_co
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (warp < 4) {
                 for (int mt = 0; mt < n_mt; ++mt) {
-                    uint32_t r[32];
-                    const uint32_t taddr = tmem_base + mt * 32 + (static_cast<uint32_t>(warp * 32) << 16);
-                    asm volatile(
-                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-                          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-                          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                        : "r"(taddr));
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     const int row = mt * 128 + warp * 32 + lane;
-                    if (row < tc_rows) {
-                        float* dst = gvalue + ((static_cast<int64_t>(n) * S + tc_base + row) * M + m) * D;
+                    float* dst = gvalue + ((static_cast<int64_t>(n) * S + tc_base + row) * M + m) * D;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < 32; c0 += 16) {       // columns c0..c0+15 (hi*hi + lo*hi) and 32+c0.. (hi*lo)
+                        uint32_t r[16], t[16];
+                        const uint32_t taddr = tmem_base + mt * 64 + c0 + (static_cast<uint32_t>(warp * 32) << 16);
+                        asm volatile(
+                            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                            : "r"(taddr));
+                        asm volatile(
+                            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                            : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(t[8]),
+                              "=r"(t[9]), "=r"(t[10]), "=r"(t[11]), "=r"(t[12]), "=r"(t[13]), "=r"(t[14]), "=r"(t[15])
+                            : "r"(taddr + 32));
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        if (row < tc_rows) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            red_add4_if(dst + j, true, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                        __uint_as_float(r[j + 3]));
+                            for (int j = 0; j < 16; j += 4)
+                                red_add4_if(dst + c0 + j, true, __uint_as_float(r[j]) + __uint_as_float(t[j]),
+                                            __uint_as_float(r[j + 1]) + __uint_as_float(t[j + 1]),
+                                            __uint_as_float(r[j + 2]) + __uint_as_float(t[j + 2]),
+                                            __uint_as_float(r[j + 3]) + __uint_as_float(t[j + 3]));
+                        }
                     }
                 }
             }
@@ -589,6 +528,9 @@ msda_bwd_staged_kernel(const __grid_constant__ CUtensorMap vmap, const __grid_co
         }
         pos += q_end - q_begin;
     }
+    if (kProfile)
+        for (int i = 0; i < 10; ++i)
+            atomicAdd(reinterpret_cast<unsigned long long*>(&g_bs_cycles[i]), static_cast<unsigned long long>(cyc[i]));
     __syncthreads();
     if (any_tc && warp == kSimtWarps)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemColsB) : "memory");
@@ -640,7 +582,7 @@ cudaError_t launch_backward_staged(const BwdArgs& a, int mode, cudaStream_t stre
     if (total < tuning(kTuneFwdStagedMinQm, 148 * 2048)) return cudaErrorNotSupported;
     const int esize = a.value_dtype == CAPE_DTYPE_F32 ? 4 : 2;
     const int row_bytes = 32 * esize;
-    const int use_tc = mode == 2 ? 1 : 0;
+    const int use_tc = mode == 2 ? 1 : (mode == 4 ? 2 : 0);
     const int fixed = 1024 + kOffStage;            // alignment slack + the weight / G tiles (laid out in both modes)
     const int budget_kb = min(tuning(kTuneBwdStagedKb, 48), (kMaxDynSmemB - fixed) / 1024);
     int cap_rows = (budget_kb * 1024 / (kBoxRowsB * row_bytes)) * kBoxRowsB;
@@ -654,10 +596,7 @@ cudaError_t launch_backward_staged(const BwdArgs& a, int mode, cudaStream_t stre
                             static_cast<uint64_t>(d.M) * d.D, kBoxRowsB, 32, CU_TENSOR_MAP_SWIZZLE_NONE))
         return cudaErrorNotSupported;
     // grad_out tile for the G^T operand (fp32 only; 16-bit grad_out is read with plain loads by the builder)
-    gmap = vmap;
-    if (esize == 4 && !make_tensor_map_2d(&gmap, a.grad_out, a.value_dtype, static_cast<uint64_t>(d.N) * d.Lq,
-                                          static_cast<uint64_t>(d.M) * d.D, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B))
-        return cudaErrorNotSupported;
+    gmap = vmap;   // (second map parameter kept for ABI stability of the kernel signature; unused)
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     long long per_cta = (total + sms - 1) / sms;

@@ -329,9 +329,11 @@ FastGeometry fast_geometry(const cape_msda_dims& d, Tune knob_threads, Tune knob
     threads = (threads / 32) * 32;
     if (threads < 32) threads = 32;
     if (threads > kFwdMaxThreads) threads = kFwdMaxThreads;
-    int q_per_cta = tuning(knob_qpc, def_qpc);
+    int q_per_cta = tuning(knob_qpc, 0);
+    if (q_per_cta <= 0)   // default: whole waves of the 2 x 148 resident 512-thread CTAs (an explicit FWD_QPC is taken as is)
+        q_per_cta = balanced_q_per_cta(static_cast<int64_t>(d.N) * d.M, d.Lq, def_qpc, 2 * 148, 4);
     // small problems (decode: Lq = 1..k): shrink the tile until the grid covers the chip a few times over
-    while (q_per_cta > 1 && static_cast<int64_t>(d.N) * d.M * ((d.Lq + q_per_cta - 1) / q_per_cta) < 148 * 4) q_per_cta >>= 1;
+    while (q_per_cta > 1 && static_cast<int64_t>(d.N) * d.M * ((d.Lq + q_per_cta - 1) / q_per_cta) < 148 * 2) q_per_cta >>= 1;
     if (q_per_cta > d.Lq) q_per_cta = d.Lq;
     if (q_per_cta < 1) q_per_cta = 1;
     if (threads > ((q_per_cta + 3) / 4) * 32) threads = ((q_per_cta + 3) / 4) * 32;   // a warp takes 4 queries at a time

@@ -121,6 +121,22 @@ cudaError_t launch_zero_masked_rows(void* value, const uint8_t* mask, long long 
 
 void count_launch();
 
+// Tile size (queries per CTA) that fills whole waves: with `slots` CTAs resident on the chip, a grid of N*M*ceil(Lq/qpc)
+// CTAs just over a multiple of `slots` leaves the last wave nearly empty (N = 2, Lq = 5440: 688 CTAs on 592 slots ran the
+// backward at 1.46x its pro-rata time).  Keep the wave count the default tile would need and size the tiles so the grid
+// fills those waves.  `align` = queries a warp sweep covers (4 in the forward).
+inline int balanced_q_per_cta(int64_t nm, int lq, int q_default, int slots, int align) {
+    if (nm <= 0 || lq <= 0) return q_default;
+    const int64_t tiles0 = (lq + q_default - 1) / q_default;
+    const int64_t waves = (nm * tiles0 + slots - 1) / slots;
+    int64_t tiles = (waves * slots) / nm;                   // tiles per (image, head) that fit `waves` full waves
+    if (tiles < 1) tiles = 1;
+    if (tiles > lq) tiles = lq;
+    int qpc = static_cast<int>((lq + tiles - 1) / tiles);
+    if (align > 1) qpc = (qpc + align - 1) / align * align;
+    return qpc < 1 ? 1 : qpc;
+}
+
 // Tuning knobs: read once per process from the environment variable "CAPE_<NAME>" (std::call_once), changeable at run
 // time through cape_set_tuning() (tools/tune.py).  Values <= 0 mean "default".
 enum Tune {

@@ -1,5 +1,5 @@
-"""Where the builder warp of the staged backward kernel (BWD_MODE 2) spends its cycles: per-phase clock64() totals of
-CTA 0 (cape_debug_counters).  Development tool."""
+"""Where the MMA warp of the staged backward kernel (BWD_MODE 2) spends its cycles: per-phase clock64() totals of CTA 0
+(cape_debug_counters).  Development tool."""
 import ctypes
 import os
 import sys
@@ -29,8 +29,7 @@ _lib.check(lib.cape_debug_counters(out, 1), "dbg")
 bwd()
 torch.cuda.synchronize()
 _lib.check(lib.cape_debug_counters(out, 1), "dbg")
-names = ["loads+coords", "wait prev MMAs", "zeroing", "RMW", "lo parts", "wait G tile", "G^T tiles", "MMA issue", "tail wait",
-         "batches", "SIMT warp 0 cycles"]
+names = ["loop top", "wait prev MMAs", "-", "-", "wait 31 columns", "MMA issue", "tail wait", "-", "-", "batches", "-"]
 batches = max(1, out[9])
 for i, n in enumerate(names):
     print(f"{n:20s} {out[i]:12d}   per batch {out[i] / batches:10.1f}")
