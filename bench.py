@@ -910,6 +910,25 @@ def copy_probe(dev, rank, world, mb=256, reps=4):
         together = rate(direction)
         out[direction + "_alone_gbs_min_over_ranks"] = round(-cdist.max_over_ranks(-alone, dev), 1)
         out[direction + "_together_gbs_min_over_ranks"] = round(-cdist.max_over_ranks(-together, dev), 1)
+    # both directions at once on this GPU (what the chunk-pipelined e2e path does): the PCIe link is full duplex, but the
+    # two directions together do not reach 2x the one-way rate
+    host2 = torch.empty(mb << 20, dtype=torch.uint8).pin_memory()
+    dev2 = torch.empty(mb << 20, dtype=torch.uint8, device=dev)
+    side = torch.cuda.Stream(device=dev)
+    cdist.barrier(dev)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    side.wait_stream(torch.cuda.current_stream(dev))
+    for _ in range(reps):
+        devb.copy_(host, non_blocking=True)
+        with torch.cuda.stream(side):
+            host2.copy_(dev2, non_blocking=True)
+    torch.cuda.current_stream(dev).wait_stream(side)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    bidir = 2 * reps * (mb << 20) / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    out["bidirectional_together_gbs_min_over_ranks"] = round(-cdist.max_over_ranks(-bidir, dev), 1)
     try:
         out["numa_nodes"] = len([d for d in os.listdir("/sys/devices/system/node") if d.startswith("node")])
     except OSError:

@@ -761,17 +761,39 @@ int cape_msda_forward_backward_host(const float* value_host, const int64_t* spat
     int chunks = bytes_in > (static_cast<size_t>(32) << 20) ? (d.N < kMaxChunks ? d.N : kMaxChunks) : 1;
     HelperStreams hs;
     if (chunks > 1 && !get_helper_streams(&hs)) chunks = 1;
+    // Events are owned by a guard so that every exit path (including the CAPE_TRY early returns) destroys them and joins
+    // the helper streams back into the caller's stream.
+    struct EventGuard {
+        cudaEvent_t ev[2 + 2 * kMaxChunks] = {};
+        int n = 0;
+        cudaStream_t caller = nullptr, in = nullptr, out = nullptr;
+        bool forked = false;
+        cudaError_t make(cudaEvent_t* e) {
+            const cudaError_t rc_ = cudaEventCreateWithFlags(e, cudaEventDisableTiming);
+            if (rc_ == cudaSuccess) ev[n++] = *e;
+            return rc_;
+        }
+        ~EventGuard() {
+            if (forked && n > 0) {               // error path: whatever the helper streams got must finish before the caller's stream goes on
+                if (cudaEventRecord(ev[0], in) == cudaSuccess) cudaStreamWaitEvent(caller, ev[0], 0);
+                if (n > 1 && cudaEventRecord(ev[1], out) == cudaSuccess) cudaStreamWaitEvent(caller, ev[1], 0);
+            }
+            for (int i = 0; i < n; ++i) cudaEventDestroy(ev[i]);
+        }
+    } guard;
     cudaEvent_t fork = nullptr, in_done[kMaxChunks] = {}, k_done[kMaxChunks] = {}, out_done = nullptr;
     if (chunks > 1) {
-        CAPE_TRY(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming), "event")
-        CAPE_TRY(cudaEventCreateWithFlags(&out_done, cudaEventDisableTiming), "event")
+        guard.caller = s, guard.in = hs.in, guard.out = hs.out;
+        CAPE_TRY(guard.make(&fork), "event")
+        CAPE_TRY(guard.make(&out_done), "event")
         for (int c = 0; c < chunks; ++c) {
-            CAPE_TRY(cudaEventCreateWithFlags(&in_done[c], cudaEventDisableTiming), "event")
-            CAPE_TRY(cudaEventCreateWithFlags(&k_done[c], cudaEventDisableTiming), "event")
+            CAPE_TRY(guard.make(&in_done[c]), "event")
+            CAPE_TRY(guard.make(&k_done[c]), "event")
         }
         CAPE_TRY(cudaEventRecord(fork, s), "fork")
         CAPE_TRY(cudaStreamWaitEvent(hs.in, fork, 0), "fork")
         CAPE_TRY(cudaStreamWaitEvent(hs.out, fork, 0), "fork")
+        guard.forked = true;
     }
     cudaStream_t s_in = chunks > 1 ? hs.in : s, s_out = chunks > 1 ? hs.out : s;
     const int per = (d.N + chunks - 1) / chunks;
@@ -825,12 +847,7 @@ int cape_msda_forward_backward_host(const float* value_host, const int64_t* spat
     if (chunks > 1) {   // join: the caller's stream completes only after the last D2H and the last H2D
         CAPE_TRY(cudaEventRecord(out_done, s_out), "join")
         CAPE_TRY(cudaStreamWaitEvent(s, out_done, 0), "join")
-        cudaEventDestroy(fork);
-        cudaEventDestroy(out_done);
-        for (int c = 0; c < chunks; ++c) {
-            cudaEventDestroy(in_done[c]);
-            cudaEventDestroy(k_done[c]);
-        }
+        guard.forked = false;                    // joined: the guard only destroys the events
     }
 #undef CAPE_TRY
     return 0;

@@ -300,7 +300,10 @@ CAPE_API int cape_linear_tf32x3_wgrad(const float* grad_out, const float* x, flo
  * Large batches are split into up to 8 chunks along N and software-pipelined: the H2D copy of chunk c+1 and the D2H copy
  * of chunk c-1 run on two library-owned helper streams (created once per device) while chunk c's kernels run on
  * `stream`; `stream` is joined to both before the call's work counts as complete, so the caller still only
- * synchronises `stream`.  This is the one place the library owns CUDA resources (two streams per device).
+ * synchronises `stream`.  This is the one place the library owns CUDA resources (two streams per device; concurrent
+ * callers on different streams of one device serialise through them).  The host buffers must be PINNED for the copies to
+ * overlap the kernels (pageable buffers work but every cudaMemcpyAsync then blocks).  On any error the events created for
+ * the call are destroyed and the helper streams are joined back into `stream` before the error code is returned.
  */
 CAPE_API size_t cape_msda_host_workspace_bytes(const cape_msda_dims* dims, int with_backward);
 CAPE_API int cape_msda_forward_backward_host(const float* value_host, const int64_t* spatial_shapes_host,
