@@ -341,7 +341,7 @@ def _force_coordinate_tokens(model):
             head.bias.copy_(torch.tensor([50.0, 0.0, 0.0], device=head.bias.device))
 
 
-def cape_train_step(dev, rank, world, steps=2, with_reference=False, amp=False):
+def cape_train_step(dev, rank, world, steps=2, with_reference=False, amp=False, tensor_core=False):
     """BASELINE.json configs[2] / [4]: CAPE 5-shot episodic training, batch 10 episodes x 2 queries (N = 20) per GPU,
     accumulation 4, AdamW with the reference's two parameter groups, clip 0.1 — the UNMODIFIED reference model
     (ResNet-50 + input_proj + 6 + 6 deformable transformer layers + geometric/GCN support encoder + heads), its own
@@ -356,7 +356,14 @@ def cape_train_step(dev, rank, world, steps=2, with_reference=False, amp=False):
         return {"unavailable": "reference not staged (baseline/_ref)"}
     accumulation, episodes, k, shots, kpts = 4, 10, 2, 5, 17
     with _Quiet():
-        model, criterion, margs, _ = sr.build_cape_model(dev, seed=1234)          # same weights on every rank
+        if tensor_core:   # opt-in: mirror encoder / decoder layer classes (same state_dict) so their linears can be routed
+            sr.activate()
+            import models.deformable_transformer as _dt
+            cape_b200.patch_reference(_dt, swap_layer_classes=True)
+        try:
+            model, criterion, margs, _ = sr.build_cape_model(dev, seed=1234)      # same weights on every rank
+        finally:
+            cape_b200.unpatch_reference()
         from models.engine_cape import train_one_epoch_episodic
     model.train()
     criterion.train()
@@ -371,6 +378,7 @@ def cape_train_step(dev, rank, world, steps=2, with_reference=False, amp=False):
         with _Quiet():
             if patched:
                 cape_b200.patch_reference(sys.modules["models.deformable_transformer"])
+                cape_b200.set_linear_mode("tf32x3" if tensor_core else "fp32")
             try:
                 return cdist.train_one_epoch_data_parallel(
                     train_one_epoch_episodic, model, criterion, loader, opt, dev, 0, buckets,
@@ -379,6 +387,7 @@ def cape_train_step(dev, rank, world, steps=2, with_reference=False, amp=False):
                     misc_module=sys.modules.get("util.misc"))
             finally:
                 cape_b200.unpatch_reference()
+                cape_b200.set_linear_mode("fp32")
 
     def measure(patched):
         opt = sr.build_optimizer(model, margs)
@@ -407,7 +416,9 @@ def cape_train_step(dev, rank, world, steps=2, with_reference=False, amp=False):
            "micro_batch": f"{episodes} episodes x {k} queries (N={episodes * k}), {shots}-shot, {kpts} keypoints, 512x512",
            "trainable_params": n_params, "allreduce_mb": round(n_params * 4 / 2 ** 20, 1), "allreduce_buckets": n_buckets,
            "msda_launches_per_step": int(launches), "loss": round(float(stats.get("loss", float("nan"))), 4),
-           "dtype": "fp16 autocast + GradScaler (--use_amp)" if amp else "f32 (TF32 off)",
+           "dtype": "fp16 autocast + GradScaler (--use_amp)" if amp else (
+               "f32; opt-in: encoder / decoder-layer FFNs and the MSDeformAttn projections on the tcgen05 3xTF32 GEMM "
+               "(patch_reference(swap_layer_classes=True) + set_linear_mode('tf32x3'))" if tensor_core else "f32 (TF32 off)"),
            "scope": "unmodified reference CAPEModel + CAPESetCriterion + train_one_epoch_episodic (engine_cape.py), "
                     "patch_reference() only; synthetic MP-100-shaped episodes, H2D of the images inside the timed region"}
     if with_reference:
@@ -1066,9 +1077,10 @@ def run_b200(args, rank, world, local_rank):
             train_tc = train_step(dev, rank, world, linear_mode="tf32x3")
         except Exception as exc:                                   # noqa: BLE001 - every rank must keep going
             train_tc = {"error": f"{type(exc).__name__}: {exc}"[:300]}
-    cape_train = cape_infer = None
+    cape_train = cape_infer = cape_train_tc = None
     if not args.no_extras:
         for name, fn in (("train", lambda: cape_train_step(dev, rank, world, with_reference=(world == 1))),
+                         ("train_tc", lambda: cape_train_step(dev, rank, world, tensor_core=True)),
                          ("infer", lambda: cape_inference(dev, rank, world, with_reference=(world == 1)))):
             try:
                 res = fn()
@@ -1078,6 +1090,8 @@ def run_b200(args, rank, world, local_rank):
                 res = {"error": f"{type(exc).__name__}: {exc}"[:300]}
             if name == "train":
                 cape_train = res
+            elif name == "train_tc":
+                cape_train_tc = res
             else:
                 cape_infer = res
     if rank != 0:
@@ -1110,6 +1124,8 @@ def run_b200(args, rank, world, local_rank):
     }
     if cape_train is not None:
         line["cape_train_step"] = cape_train
+    if cape_train_tc is not None:
+        line["cape_train_step_tensor_core_linears"] = cape_train_tc
     if cape_infer is not None:
         line["cape_inference"] = cape_infer
     if train is not None:

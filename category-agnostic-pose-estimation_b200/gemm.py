@@ -73,13 +73,13 @@ def linear_tf32x3(x: torch.Tensor, weight: torch.Tensor, bias=None, relu: bool =
     if not x2.is_contiguous() or x2.data_ptr() % 16 != 0:
         x2 = x2.contiguous()
     w = weight.detach()
-    y = torch.empty(x2.shape[0], n, dtype=torch.float32, device=x.device)
+    y = torch.empty(*x.shape[:-1], n, dtype=torch.float32, device=x.device)   # final shape: not a view (callers may write in place)
     b = None if bias is None else bias.detach().contiguous()
     with torch.cuda.device(x.device):
         rc = lib.cape_linear_tf32x3(_ptr(x2), _ptr(w), _ptr(_weight_lo(weight)), None if b is None else _ptr(b), _ptr(y),
                                     x2.shape[0], n, k, 1 if relu else 0, _stream(x.device))
     _lib.check(rc, "cape_linear_tf32x3")
-    return y.view(*x.shape[:-1], n)
+    return y
 
 
 _WT_CACHE: dict = {}

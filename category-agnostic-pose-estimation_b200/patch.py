@@ -4,11 +4,14 @@
 (``/root/reference/models/deformable_transformer.py:112``), so rebinding that one name swaps the hot path under an
 unmodified ``CAPEModel`` — parameters, ``state_dict`` keys, ``forward`` / ``forward_inference`` API all untouched.
 
-Three levels, each a superset of the previous one:
+Levels (combinable):
 
 * ``patch_reference()``                              the sampling core only (training and inference);
 * ``patch_reference(swap_module_class=True)``        also the ``MSDeformAttn`` class for models built afterwards
                                                      (fused prologue, ``use_cache`` honoured);
+* ``patch_reference(swap_layer_classes=True)``       also the encoder layer / encoder / decoder layer v1 classes (mirrors with
+                                                     identical ``state_dict`` keys), which opens their FFNs to the opt-in
+                                                     tensor-core linears;
 * ``patch_reference(swap_forward_inference=True)``   also ``RoomFormerV2.forward_inference`` (``roomformer_v2.py:385-677``):
                                                      the autoregressive loop runs device-resident on a mirror bound to the
                                                      live module's own parameter tensors, and returns the reference's dict,
@@ -28,10 +31,15 @@ from .modules import MSDeformAttn
 
 _ORIGINALS = {}
 _INFERENCE_ORIGINALS = {}
+_LAYER_ORIGINALS = {}
 _GEN_ATTR = "_cape_b200_generation"      # plain attribute on the live module: never a submodule, buffer or parameter
 
 
-def patch_reference(module=None, swap_module_class: bool = False, swap_forward_inference: bool = False):
+_LAYER_CLASSES = ("DeformableTransformerEncoderLayer", "DeformableTransformerEncoder", "TransformerDecoderLayer")
+
+
+def patch_reference(module=None, swap_module_class: bool = False, swap_forward_inference: bool = False,
+                    swap_layer_classes: bool = False):
     """Rebind the reference's sampling core to the B200 op.
 
     module: the imported ``models.deformable_transformer`` module object (or its dotted name; default
@@ -41,6 +49,13 @@ def patch_reference(module=None, swap_module_class: bool = False, swap_forward_i
         ``use_cache`` and fuses the decode prologue.  Only affects models built after the call.
     swap_forward_inference: also replace ``RoomFormerV2.forward_inference`` in the sibling ``roomformer_v2`` module
         by :func:`forward_inference` below.  Affects existing model objects too (the method is looked up on the class).
+    swap_layer_classes: implies ``swap_module_class`` and also replaces the callers either side of the op —
+        ``DeformableTransformerEncoderLayer`` / ``DeformableTransformerEncoder`` (``deformable_transformer.py:155-291``) and
+        decoder layer v1 ``TransformerDecoderLayer`` (``deformable_transformer_v2.py:262-370``) — by the mirrors of
+        ``layers.py`` (same constructor arguments, parameter names and ``state_dict`` keys).  Their ``nn.Linear`` calls
+        go through ``gemm.linear``, so ``cape_b200.set_linear_mode("tf32x3")`` then puts the encoder / decoder FFNs and the
+        MSDeformAttn projections of a model built afterwards on the tcgen05 3xTF32 GEMM.  Only affects models built after
+        the call.
     Returns the patched module.
     """
     if module is None or isinstance(module, str):
@@ -51,6 +66,8 @@ def patch_reference(module=None, swap_module_class: bool = False, swap_forward_i
     module.ms_deform_attn_core_pytorch = CF.ms_deform_attn_core_pytorch
     package = module.__name__.rsplit(".", 1)[0] if "." in module.__name__ else ""
     sibling = lambda name: importlib.import_module((package + "." if package else "") + name)
+    if swap_layer_classes:
+        swap_module_class = True
     if swap_module_class:
         module.MSDeformAttn = MSDeformAttn
         try:
@@ -60,6 +77,19 @@ def patch_reference(module=None, swap_module_class: bool = False, swap_forward_i
                 v2.MSDeformAttn = MSDeformAttn
         except Exception:
             pass
+    if swap_layer_classes:
+        from . import layers as CL
+        targets = [module]
+        try:
+            targets.append(sibling("deformable_transformer_v2"))
+        except Exception:
+            pass
+        for mod in targets:
+            saved = _LAYER_ORIGINALS.setdefault(id(mod), (mod, {}))[1]
+            for name in _LAYER_CLASSES:
+                if hasattr(mod, name) and hasattr(CL, name):
+                    saved.setdefault(name, getattr(mod, name))
+                    setattr(mod, name, getattr(CL, name))
     if swap_forward_inference:
         rf = sibling("roomformer_v2")
         cls = rf.RoomFormerV2
@@ -83,6 +113,10 @@ def unpatch_reference(module: Optional[object] = None):
         for cls, original in _INFERENCE_ORIGINALS.values():
             cls.forward_inference = original
         _INFERENCE_ORIGINALS.clear()
+        for mod, saved in _LAYER_ORIGINALS.values():
+            for name, cls in saved.items():
+                setattr(mod, name, cls)
+        _LAYER_ORIGINALS.clear()
 
 
 # ---- RoomFormerV2.forward_inference, device-resident ----------------------------------------------------------------
