@@ -484,6 +484,17 @@ def cape_inference(dev, rank, world, episodes=64, keypoints=100, with_reference=
            "launches_per_batch": int(launches),
            "scope": "CAPEModel.forward_inference unchanged (ResNet-50, support encoder, encoder, AR decoder with KV + "
                     "value caches, heads); patch_reference(swap_forward_inference=True); images H2D + result D2H timed"}
+    # opt-in tensor-core linears: the drop-in's encoder / value projections on the tcgen05 3xTF32 GEMM (fp32-level accuracy)
+    cape_b200.patch_reference(sys.modules[mod_name], swap_forward_inference=True)
+    cape_b200.set_linear_mode("tf32x3")
+    try:
+        t_tc, _ = timed(2)
+        out["tensor_core_linears"] = {"episodes_per_s": round(world * episodes / t_tc, 2), "s_per_batch": round(t_tc, 4)}
+    except Exception as exc:                                       # noqa: BLE001
+        out["tensor_core_linears"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
+    finally:
+        cape_b200.set_linear_mode("fp32")
+        cape_b200.unpatch_reference()
     if with_reference:
         cape_b200.patch_reference(sys.modules[mod_name])
         try:
@@ -1077,10 +1088,11 @@ def run_b200(args, rank, world, local_rank):
             train_tc = train_step(dev, rank, world, linear_mode="tf32x3")
         except Exception as exc:                                   # noqa: BLE001 - every rank must keep going
             train_tc = {"error": f"{type(exc).__name__}: {exc}"[:300]}
-    cape_train = cape_infer = cape_train_tc = None
+    cape_train = cape_infer = cape_train_tc = cape_train_amp = None
     if not args.no_extras:
         for name, fn in (("train", lambda: cape_train_step(dev, rank, world, with_reference=(world == 1))),
                          ("train_tc", lambda: cape_train_step(dev, rank, world, tensor_core=True)),
+                         ("train_amp", lambda: cape_train_step(dev, rank, world, amp=True)),
                          ("infer", lambda: cape_inference(dev, rank, world, with_reference=(world == 1)))):
             try:
                 res = fn()
@@ -1092,6 +1104,8 @@ def run_b200(args, rank, world, local_rank):
                 cape_train = res
             elif name == "train_tc":
                 cape_train_tc = res
+            elif name == "train_amp":
+                cape_train_amp = res
             else:
                 cape_infer = res
     if rank != 0:
@@ -1126,6 +1140,8 @@ def run_b200(args, rank, world, local_rank):
         line["cape_train_step"] = cape_train
     if cape_train_tc is not None:
         line["cape_train_step_tensor_core_linears"] = cape_train_tc
+    if cape_train_amp is not None:
+        line["cape_train_step_amp"] = cape_train_amp
     if cape_infer is not None:
         line["cape_inference"] = cape_infer
     if train is not None:
