@@ -310,8 +310,8 @@ def train_step(dev, rank, world, accumulation=4, steps=2, amp=False, linear_mode
             "episodes_per_step": episodes, "accumulation": accumulation, "allreduce_mb": round(n_params * 4 / 2 ** 20, 1),
             "msda_launches_per_step": int(per_step_launches), "cudaMallocs_in_timed_region": int(timed_allocs),
             "dtype": "fp16 autocast + GradScaler (the reference's --use_amp); MSDeformAttn value fp16, accumulation fp32"
-            if amp else ("f32; opt-in tcgen05 3xTF32 linears for the MSDeformAttn projections and FFNs (forward + input "
-                         "gradient; weight gradient cuBLAS fp32)" if linear_mode == "tf32x3" else "f32 (TF32 off)"),
+            if amp else ("f32; opt-in tcgen05 3xTF32 linears for the MSDeformAttn projections and FFNs (forward, input "
+                         "gradient and weight gradient)" if linear_mode == "tf32x3" else "f32 (TF32 off)"),
             "scope": "6 encoder + 6 decoder (v1) layers of the deformable transformer, fwd + bwd + NCCL all-reduce + "
                      "AdamW; synthetic features; no backbone / support encoder / heads"}
 

@@ -25,7 +25,7 @@ from .variants import MSDeformablePoints, ms_deform_attn_query_pool, points_samp
 from .sequence import TokenState, TokenizerSpec, seq_embed
 from .transformer import (MLP, AutoregressiveGenerator, DeformableTransformer, TransformerDecoder, build_prediction_heads,
                           generate_eager, load_reference_checkpoint, to_cape_predictions)
-from .gemm import linear_mode, linear_tf32x3, set_linear_mode
+from .gemm import clear_caches as clear_linear_caches, linear_mode, linear_tf32x3, set_linear_mode
 from . import synthetic
 
 __all__ = ["MSDeformAttn", "ValueCache", "MSDeformAttnFunction", "ms_deform_attn", "ms_deform_attn_core_pytorch",
@@ -34,4 +34,4 @@ __all__ = ["MSDeformAttn", "ValueCache", "MSDeformAttnFunction", "ms_deform_attn
            "DeformableTransformerEncoderLayer", "TransformerDecoderLayer", "KVCache", "IncrementalDecoder", "MSDeformablePoints",
            "ms_deform_attn_query_pool", "points_sample", "sample_reference_points", "seq_embed", "TokenizerSpec", "TokenState",
            "TransformerDecoder", "DeformableTransformer", "MLP", "build_prediction_heads", "AutoregressiveGenerator",
-           "generate_eager", "load_reference_checkpoint", "to_cape_predictions", "set_linear_mode", "linear_mode", "linear_tf32x3"]
+           "generate_eager", "load_reference_checkpoint", "to_cape_predictions", "set_linear_mode", "linear_mode", "linear_tf32x3", "clear_linear_caches"]

@@ -75,6 +75,11 @@ __device__ __forceinline__ void scatter_level(const VT* __restrict__ vbase, floa
     const float hx = 1.f - lx, hy = 1.f - ly;
     const float ahy = a * hy, aly = a * ly;
 #ifndef CAPE_EXP_NO_RED   // profiling-only variant (tools/, never shipped) drops the scatter
+#ifdef CAPE_EXP_NO_COARSE_RED
+    if (gbase != nullptr) {
+#else
+    {
+#endif
     float c = ahy * hx;
     { const float4 cg = mul4(c, g); red_add4_if(gbase + o00, y0ok & x0ok, cg.x, cg.y, cg.z, cg.w); }
     c = ahy * lx;
@@ -83,6 +88,7 @@ __device__ __forceinline__ void scatter_level(const VT* __restrict__ vbase, floa
     { const float4 cg = mul4(c, g); red_add4_if(gbase + o10, y1ok & x0ok, cg.x, cg.y, cg.z, cg.w); }
     c = aly * lx;
     { const float4 cg = mul4(c, g); red_add4_if(gbase + o10 + rowStride, y1ok & x1ok, cg.x, cg.y, cg.z, cg.w); }
+    }
 #else
     (void)gbase;
     (void)ahy;
@@ -174,7 +180,11 @@ msda_bwd_fast_kernel(const VT* __restrict__ gout, const VT* __restrict__ value, 
             const float py = __shfl_sync(kFullMask, locv, l * 8 + p * 2 + 1);
             const float a = __shfl_sync(kFullMask, attnv, l * 4 + p);
             float ga, gx, gy;
+#ifdef CAPE_EXP_NO_COARSE_RED   // profiling-only variant (tools/, never shipped): levels >= 2 gather but do not scatter
+            scatter_level(vbase, l >= 2 ? nullptr : gbase, rowStride, lv.off[l], lv.H[l], lv.W[l], px, py, a, g, ga, gx, gy);
+#else
             scatter_level(vbase, gbase, rowStride, lv.off[l], lv.H[l], lv.W[l], px, py, a, g, ga, gx, gy);
+#endif
             part[l * 3] = ga;
             // d loc / d offset = 1 / dim cancels the dim factor of d pixel / d loc in the fused form
             part[l * 3 + 1] = FUSED ? a * gx : a * static_cast<float>(lv.W[l]) * gx;

@@ -412,31 +412,11 @@ msda_bwd_staged_kernel(const __grid_constant__ CUtensorMap vmap, const __grid_co
                         sts_f32(a_lo + prev_idx * 4, 0.f);
                     }
                     __syncwarp();
-#ifdef CAPE_BS_MATCH
-                    // variant: lanes that target the same entry are summed in registers (match.any + shuffles), plain stores
-                    {
-                        const unsigned peers = __match_any_sync(kFullMask, valid ? idx : (0x10000u + lane));
-                        float wsum = wgt;
-                        unsigned rest = peers & ~(1u << lane);
-                        while (__any_sync(kFullMask, rest != 0)) {
-                            const int src = rest ? (__ffs(rest) - 1) : lane;
-                            const float other = __shfl_sync(kFullMask, wgt, src);
-                            if (rest) {
-                                wsum += other;
-                                rest &= rest - 1;
-                            }
-                        }
-                        if (valid && lane == (__ffs(peers) - 1)) {
-                            sts_f32(a_hi + idx * 4, wsum);
-                            sts_f32(a_lo + idx * 4, tf32_lo_part(wsum));
-                        }
-                    }
-#else
-                    // corners of different points often coincide: shared-memory float add (a CAS loop on sm_100, ATOMS.CAST.SPIN)
+                    // corners of different points often coincide: shared-memory float add (a CAS loop on sm_100, ATOMS.CAST.SPIN).
+                    // Summing coinciding lanes in registers first (match.any + shuffles, plain stores) measured the same: 955 vs 943 us.
                     if (valid) asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(a_hi + idx * 4), "f"(wgt) : "memory");
                     __syncwarp();
                     if (valid) sts_f32(a_lo + idx * 4, tf32_lo_part(lds_f32(a_hi + idx * 4)));
-#endif
                     prev_idx = idx;
                     {   // this query's column of the transposed grad_out operand: lane -> channel 4k + p (hi row, lo row)
                         const int ch = k * 4 + p;

@@ -5,9 +5,14 @@ The reference runs the projections around the sampling op (``value_proj`` / ``ou
 ``attention_weights`` of MSDeformAttn, the encoder FFN; ``/root/reference/models/deformable_transformer.py:95-113,219-224``)
 as strict-fp32 ``nn.Linear``, which cuBLAS serves with SIMT kernels on B200.  ``linear()`` is what the mirrors call
 instead of ``module(x)``: by default it IS ``module(x)`` (bit-for-bit the reference's arithmetic); after
-``set_linear_mode("tf32x3")`` inference calls (no autograd) with supported shapes (K % 32 == 0, N % 128 == 0, fp32, CUDA)
-go through the 3xTF32 kernel — max error about 2e-6 of the output scale at K = 256 (cuBLAS fp32: 5e-7), ~5x faster.
-With autograd on, forward and the input gradient use the kernel and the weight gradient stays cuBLAS.
+``set_linear_mode("tf32x3")`` calls with supported shapes (K % 32 == 0, N % 128 == 0, fp32, CUDA, >= 128 rows, no
+autocast) go through the 3xTF32 kernel — max error about 2e-6 of the output scale at K = 256 (cuBLAS fp32: 5e-7), ~5x
+faster.  With autograd on, forward, the input gradient (the same GEMM with W^T) AND the weight gradient (transposed
+operands, reduction split over the SMs, partial tiles added by the TMA) all use the kernel (``_LinearTF32x3``).
+
+Derived operands (the lo part of a weight, W^T) are cached per weight tensor and refreshed when its ``_version`` changes,
+which every optimizer step and ``load_state_dict`` does.  Writes through ``weight.data`` (``w.data.copy_()``, hand-rolled
+EMA) do NOT bump the version: call :func:`clear_caches` after such an update.
 """
 from __future__ import annotations
 
@@ -25,7 +30,7 @@ _LO_CACHE: dict = {}
 
 
 def set_linear_mode(mode: str) -> str:
-    """"fp32" (default: plain nn.Linear) or "tf32x3" (3xTF32 tensor-core kernel for inference).  Returns the old mode."""
+    """"fp32" (default: plain nn.Linear) or "tf32x3" (3xTF32 tensor-core kernel, inference and training).  Returns the old mode."""
     global _MODE
     if mode not in ("fp32", "tf32x3"):
         raise ValueError(f"unknown linear mode {mode!r}")
@@ -35,6 +40,13 @@ def set_linear_mode(mode: str) -> str:
 
 def linear_mode() -> str:
     return _MODE
+
+
+def clear_caches() -> None:
+    """Forget the cached lo parts / transposed weights (needed only after weight updates that bypass the version counter,
+    e.g. writes through ``.data``)."""
+    _LO_CACHE.clear()
+    _WT_CACHE.clear()
 
 
 def _weight_lo(weight: torch.Tensor) -> torch.Tensor:
