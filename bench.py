@@ -1076,18 +1076,6 @@ def run_b200(args, rank, world, local_rank):
             train = train_step(dev, rank, world)
         except Exception as exc:                                   # noqa: BLE001 - every rank must keep going
             train = {"error": f"{type(exc).__name__}: {exc}"[:300]}
-    train_amp = None
-    if not args.no_extras:
-        try:
-            train_amp = train_step(dev, rank, world, amp=True)
-        except Exception as exc:                                   # noqa: BLE001 - every rank must keep going
-            train_amp = {"error": f"{type(exc).__name__}: {exc}"[:300]}
-    train_tc = None
-    if not args.no_extras:
-        try:
-            train_tc = train_step(dev, rank, world, linear_mode="tf32x3")
-        except Exception as exc:                                   # noqa: BLE001 - every rank must keep going
-            train_tc = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     cape_train = cape_infer = cape_train_tc = cape_train_amp = None
     if not args.no_extras:
         for name, fn in (("train", lambda: cape_train_step(dev, rank, world, with_reference=(world == 1))),
@@ -1146,10 +1134,6 @@ def run_b200(args, rank, world, local_rank):
         line["cape_inference"] = cape_infer
     if train is not None:
         line["train_step"] = train
-    if train_amp is not None:
-        line["train_step_amp"] = train_amp
-    if train_tc is not None:
-        line["train_step_tensor_core_linears"] = train_tc
     if world == 1 and not args.no_extras:
         line["sweep"] = guarded(op_sweep, lib, dev)
         line["module"] = guarded(module_step, dev)

@@ -32,12 +32,16 @@ struct BwdLevels {
     int H[L], W[L];
     int off[L];   // element offset of the level's first row inside this batch element's (S, M, D) block (< 2^31)
     __device__ __forceinline__ void load(const int64_t* __restrict__ shapes, const int64_t* __restrict__ starts,
-                                         int rowStride) {
+                                         int rowStride, int S) {
 #pragma unroll
         for (int l = 0; l < L; ++l) {
             H[l] = static_cast<int>(__ldg(shapes + 2 * l));
             W[l] = static_cast<int>(__ldg(shapes + 2 * l + 1));
-            off[l] = static_cast<int>(__ldg(starts + l)) * rowStride;
+            const long long s0 = __ldg(starts + l);
+            // a level that does not fit inside S (the reference asserts sum(H*W) == S, deformable_transformer.py:94) is
+            // skipped: no gathers, no scatters outside value / grad_value
+            if (s0 < 0 || H[l] < 0 || W[l] < 0 || s0 + static_cast<long long>(H[l]) * W[l] > S) H[l] = W[l] = 0;
+            off[l] = H[l] > 0 ? static_cast<int>(s0) * rowStride : 0;
         }
     }
     __device__ __forceinline__ float lane_dim(int lane) const {
@@ -144,7 +148,7 @@ msda_bwd_fast_kernel(const VT* __restrict__ gout, const VT* __restrict__ value, 
     const int m = bid % M, n = bid / M;
     const int rowStride = M * D;
     BwdLevels<VT, L> lv;
-    lv.load(shapes, starts, rowStride);
+    lv.load(shapes, starts, rowStride, S);
     const int64_t headOff = (static_cast<int64_t>(n) * S * M + m) * D + k * 4;
     const VT* vbase = value + headOff;
     float* gbase = gvalue + headOff;
@@ -235,8 +239,10 @@ msda_bwd_generic_kernel(const VT* __restrict__ gout, const VT* __restrict__ valu
         g[ch] = d < D ? to_f32(gout[qm * D + d]) : 0.f;
     }
     for (int l = 0; l < L; ++l) {
-        const int H = static_cast<int>(__ldg(shapes + 2 * l)), W = static_cast<int>(__ldg(shapes + 2 * l + 1));
-        const int start = static_cast<int>(__ldg(starts + l));
+        int H = static_cast<int>(__ldg(shapes + 2 * l)), W = static_cast<int>(__ldg(shapes + 2 * l + 1));
+        const long long start64 = __ldg(starts + l);
+        if (start64 < 0 || H < 0 || W < 0 || start64 + static_cast<long long>(H) * W > S) H = W = 0;   // level outside S: skipped
+        const int start = static_cast<int>(start64);
         for (int p = 0; p < P; ++p) {
             const int64_t si = qm * LP + l * P + p;
             const float locx = to_f32(locp[si * 2]), locy = to_f32(locp[si * 2 + 1]), a = to_f32(attnp[si]);

@@ -276,8 +276,10 @@ msda_fwd_generic_kernel(const VT* __restrict__ value, const int64_t* __restrict_
 #pragma unroll
     for (int c = 0; c < kChunks; ++c) acc[c] = 0.f;
     for (int l = 0; l < L; ++l) {
-        const int H = static_cast<int>(__ldg(shapes + 2 * l)), W = static_cast<int>(__ldg(shapes + 2 * l + 1));
-        const int start = static_cast<int>(__ldg(starts + l));
+        int H = static_cast<int>(__ldg(shapes + 2 * l)), W = static_cast<int>(__ldg(shapes + 2 * l + 1));
+        const long long start64 = __ldg(starts + l);
+        if (start64 < 0 || H < 0 || W < 0 || start64 + static_cast<long long>(H) * W > S) H = W = 0;   // level outside S: skipped
+        const int start = static_cast<int>(start64);
         for (int p = 0; p < P; ++p) {
             float locx, locy, a;
             const int64_t si = qm * LP + l * P + p;

@@ -849,3 +849,36 @@ def test_masked_fill_rows_matches_masked_fill_forward_and_backward():
     leaf = torch.randn(2, 5, 32, device="cuda", requires_grad=True)          # a leaf is never modified in place
     out = masked_fill_rows_(leaf, torch.ones(2, 5, dtype=torch.bool, device="cuda"))
     assert out is not leaf and float(out.abs().sum()) == 0.0 and float(leaf.abs().sum()) > 0
+
+
+@pytest.mark.parametrize("generic", [False, True])
+def test_inconsistent_pyramid_is_skipped_not_read_out_of_bounds(generic):
+    """ADVICE r1: level_start_index / spatial_shapes that do not fit S.  The reference asserts (deformable_transformer.py:94);
+    the kernels cannot raise, so the offending level contributes nothing — forward and backward — instead of gathering /
+    scattering outside value / grad_value (guard zones around the tensors stay intact)."""
+    p = 3 if generic else 4                                              # P = 3 takes the generic kernels
+    inp = synthetic.make_inputs(1, 300, n_points=p, dist="uniform", seed=9)
+    bad_starts = torch.tensor([0, 4096, 5120, 5400])                     # 5400 + 8*8 > S = 5440
+
+    def run(starts, attn):
+        pad = 4096
+        vbuf = torch.full((inp["value"].numel() + 2 * pad,), float("nan"), device="cuda")
+        v = vbuf[pad:-pad].view(inp["value"].shape)
+        v.copy_(inp["value"].cuda())
+        v = v.detach().requires_grad_(True)
+        loc = inp["sampling_locations"].cuda().requires_grad_(True)
+        a = attn.cuda().requires_grad_(True)
+        out = cape_b200.ms_deform_attn(v, inp["spatial_shapes"].cuda(), starts.cuda(), loc, a)
+        gv, gl = torch.autograd.grad(out, (v, loc), inp["grad_output"].cuda())
+        torch.cuda.synchronize()
+        assert torch.isnan(vbuf[:pad]).all() and torch.isnan(vbuf[-pad:]).all()
+        return out.detach(), gv, gl
+
+    off = inp["attention_weights"].clone()
+    off[:, :, :, 3] = 0                                                   # the same result with level 3 switched off
+    out_bad, gv_bad, gl_bad = run(bad_starts, inp["attention_weights"])
+    out_ok, gv_ok, gl_ok = run(inp["level_start_index"], off)
+    assert torch.isfinite(out_bad).all() and torch.allclose(out_bad, out_ok, atol=1e-6)
+    assert torch.allclose(gv_bad, gv_ok, atol=1e-6)
+    assert torch.allclose(gl_bad[:, :, :, :3], gl_ok[:, :, :, :3], atol=1e-5)
+    assert float(gl_bad[:, :, :, 3].abs().max()) == 0.0
