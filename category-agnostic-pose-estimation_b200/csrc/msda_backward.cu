@@ -133,7 +133,7 @@ __device__ __forceinline__ void transpose_reduce12(const float (&v)[12], int k, 
 //                and grad_logits = attn * (grad_attn - sum_j attn_j grad_attn_j) instead, so sampling_locations,
 //                attention_weights and their gradients never exist in HBM.
 template <typename VT, typename AT, int L, int MC, bool FUSED>
-__global__ void __launch_bounds__(kBwdMaxThreads)
+__global__ void __launch_bounds__(kBwdMaxThreads, 2)
 msda_bwd_fast_kernel(const VT* __restrict__ gout, const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                      const int64_t* __restrict__ starts, const AT* __restrict__ locp, const AT* __restrict__ attnp,
                      const float* __restrict__ refp, float* __restrict__ gvalue, AT* __restrict__ gloc,

@@ -36,6 +36,26 @@ __device__ __forceinline__ float4 ld4(const __half* p) {
     const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
     return make_float4(a.x, a.y, b.x, b.y);
 }
+// Streaming loads for tensors that are touched once (sampling_locations, attention_weights, grad_out): read-only path
+// without L1 allocation, so the L1 keeps the value rows that neighbouring queries gather again.
+__device__ __forceinline__ float4 ld4_stream(const float* p) {
+    float4 v;
+    asm("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float2 ld2_stream(const float* p) {
+    float2 v;
+    asm("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ld1_stream(const float* p) {
+    float v;
+    asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ld1_stream(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ float ld1_stream(const __half* p) { return __half2float(*p); }
+
 // 4-channel load that yields zeros when `pred` is false (zeros padding: an out-of-bounds corner contributes nothing).
 // The destination is zero-initialised in C++ and conditionally overwritten by a predicated load inside one asm
 // statement ("+" constraints), which keeps ptxas from loading into temporaries and selecting afterwards.

@@ -98,8 +98,8 @@ __device__ __forceinline__ void load_raw(const float* locp, const float* attnp, 
     r.loc = make_float4(0.f, 0.f, 0.f, 0.f);
     r.attn = make_float2(pad, pad);
     if (on && k < 2 * L) {
-        r.loc = __ldg(reinterpret_cast<const float4*>(locp + qm * (L * 8)) + k);
-        r.attn = __ldg(reinterpret_cast<const float2*>(attnp + qm * (L * 4)) + k);
+        r.loc = ld4_stream(locp + qm * (L * 8) + k * 4);
+        r.attn = ld2_stream(attnp + qm * (L * 4) + k * 2);
     }
 }
 template <typename HT>   // bf16 / fp16 location + weight tensors

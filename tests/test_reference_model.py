@@ -128,3 +128,89 @@ def test_patch_and_unpatch_forward_inference_swap():
     finally:
         cape_b200.unpatch_reference()
     assert rf.RoomFormerV2.forward_inference is original and dt.ms_deform_attn_core_pytorch is core
+
+
+# ---- the data-parallel wrapper around the REAL train_one_epoch_episodic (gloo, world size 2, CPU) ----------------------
+# hidden_dim stays 256: the reference hard-codes 128 sine features per coordinate for the query positions
+# (deformable_transformer_v2.py:1005-1018), other widths do not run
+_SMALL_MODEL = ["--enc_layers", "1", "--dec_layers", "1", "--dim_feedforward", "128", "--dropout", "0.0", "--lr", "1e-3"]
+
+
+def _small_reference_model():
+    model, criterion, args, _ = stage_reference.build_cape_model("cpu", extra_args=_SMALL_MODEL, seed=3)
+    model.train()
+    criterion.train()
+    for m in model.modules():                                    # no stochastic layers: both runs must be deterministic
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+        if isinstance(m, torch.nn.MultiheadAttention):
+            m.dropout = 0.0
+    return model, criterion, args
+
+
+def _episode_batches(n_batches):
+    import cape_b200
+    return [cape_b200.synthetic.make_episode_batch(2, 2, num_keypoints=9, shots=1, image_size=64, seed=50 + i)
+            for i in range(n_batches)]
+
+
+def _dp_engine_worker(rank, world, port, out):
+    import contextlib
+    import io
+    sys.path.insert(0, REPO)
+    sys.path.insert(0, os.path.join(REPO, "tools"))
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port), TQDM_DISABLE="1")
+    import torch.distributed as dist
+    from cape_b200 import dist as cdist
+    cdist.init_from_env("gloo")
+    model, criterion, args = _small_reference_model()
+    import util.misc
+    from models.engine_cape import train_one_epoch_episodic
+    opt = stage_reference.build_optimizer(model, args)
+    buckets = cdist.GradBuckets(model.parameters(), bucket_bytes=1 << 20)
+    with contextlib.redirect_stdout(io.StringIO()):
+        cdist.train_one_epoch_data_parallel(train_one_epoch_episodic, model, criterion, _episode_batches(3), opt, "cpu", 0,
+                                            buckets, accumulation_steps=2, max_norm=args.clip_max_norm,
+                                            queries_per_episode=2, misc_module=util.misc)
+    cdist.barrier()
+    names = ["base_model.transformer.encoder.layers.0.linear1.weight", "base_model.query_embed.weight",
+             "support_encoder.coord_mlp.0.weight" if hasattr(model.support_encoder, "coord_mlp") else "base_model.transformer.level_embed"]
+    state = model.state_dict()
+    out.put((rank, {k: state[k].double().sum().item() for k in names if k in state}, len(buckets.buckets), buckets.known))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(400)
+def test_real_training_loop_data_parallel_equals_single_process():
+    """train_one_epoch_data_parallel drives the reference's UNEDITED train_one_epoch_episodic (engine_cape.py:48-301) on two
+    gloo ranks, each on its episodes rank::2 of every batch: both ranks must end with the weights a single process gets from
+    the whole batches (3 batches, accumulation 2 -> one full and one ragged optimizer step, clipping on)."""
+    import contextlib
+    import io
+    import torch.multiprocessing as mp
+    from tests.test_dist_gloo import _free_port
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dp_engine_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = sorted((q.get(timeout=240) for _ in procs), key=lambda r: r[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    os.environ["TQDM_DISABLE"] = "1"
+    model, criterion, args = _small_reference_model()
+    stage_reference.activate()
+    from models.engine_cape import train_one_epoch_episodic
+    opt = stage_reference.build_optimizer(model, args)
+    with contextlib.redirect_stdout(io.StringIO()):
+        train_one_epoch_episodic(model, criterion, _episode_batches(3), opt, "cpu", 0, max_norm=args.clip_max_norm,
+                                 accumulation_steps=2)
+    state = model.state_dict()
+    for rank, sums, n_buckets, known in results:
+        assert known and n_buckets >= 1 and sums
+        for k, v in sums.items():
+            want = state[k].double().sum().item()
+            assert abs(v - want) <= 1e-4 * max(1.0, abs(want)), (rank, k, v, want)
