@@ -38,10 +38,10 @@ struct BwdLevels {
             H[l] = static_cast<int>(__ldg(shapes + 2 * l));
             W[l] = static_cast<int>(__ldg(shapes + 2 * l + 1));
             const long long s0 = __ldg(starts + l);
+            off[l] = static_cast<int>(s0) * rowStride;
             // a level that does not fit inside S (the reference asserts sum(H*W) == S, deformable_transformer.py:94) is
-            // skipped: no gathers, no scatters outside value / grad_value
-            if (s0 < 0 || H[l] < 0 || W[l] < 0 || s0 + static_cast<long long>(H[l]) * W[l] > S) H[l] = W[l] = 0;
-            off[l] = H[l] > 0 ? static_cast<int>(s0) * rowStride : 0;
+            // skipped: with W = 0 no corner passes the x-range test, so nothing is gathered or scattered for it
+            if (s0 < 0 || H[l] < 0 || W[l] < 0 || s0 + static_cast<long long>(H[l]) * W[l] > S) W[l] = 0;
         }
     }
     __device__ __forceinline__ float lane_dim(int lane) const {
