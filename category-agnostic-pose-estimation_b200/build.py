@@ -48,7 +48,8 @@ def build(force: bool = False, verbose: bool = False, variant: str = "") -> str:
     extra = []
     if variant:
         extra = {"nored": ["-DCAPE_EXP_NO_RED"], "noload": ["-DCAPE_EXP_NO_LOAD"], "t896": ["-DCAPE_BS_THREADS=896"],
-                 "t768": ["-DCAPE_BS_THREADS=768"], "nocoarsered": ["-DCAPE_EXP_NO_COARSE_RED"]}[variant]
+                 "t768": ["-DCAPE_BS_THREADS=768"], "nocoarsered": ["-DCAPE_EXP_NO_COARSE_RED"], "evictlast": ["-DCAPE_EXP_EVICT_LAST"],
+                 "streamstore": ["-DCAPE_EXP_STREAM_STORE"]}[variant]
         lib = os.path.join(os.path.dirname(HERE), "tools", f"libcape_msda_{variant}.so")
         return _compile(lib, extra, verbose, os.path.join(HERE, "build", variant))
     if not force and not _stale():

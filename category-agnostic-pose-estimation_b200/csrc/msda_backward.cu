@@ -157,8 +157,8 @@ msda_bwd_fast_kernel(const VT* __restrict__ gout, const VT* __restrict__ value, 
     for (int q = qt * q_per_cta + warp; q < q_end; q += nwarps) {
         const int64_t qm = (static_cast<int64_t>(n) * Lq + q) * M + m;
         float locv = 0.f, attnv = FUSED ? -INFINITY : 0.f;
-        if (lane < L * 8) locv = to_f32(locp[qm * (L * 8) + lane]);
-        if (lane < L * 4) attnv = to_f32(attnp[qm * (L * 4) + lane]);
+        if (lane < L * 8) locv = ld1_stream(locp + qm * (L * 8) + lane);      // touched once: no L1 allocation
+        if (lane < L * 4) attnv = ld1_stream(attnp + qm * (L * 4) + lane);
         const float4 g = ld4(gout + qm * D + k * 4);
         if (FUSED) {   // softmax over the 4L logits (lanes 0 .. 4L-1) and loc = ref + off / dim
             float mx = attnv;

@@ -61,6 +61,12 @@ __device__ __forceinline__ float ld1_stream(const __half* p) { return __half2flo
 // statement ("+" constraints), which keeps ptxas from loading into temporaries and selecting afterwards.
 __device__ __forceinline__ float4 ld4_or_zero(const float* p, bool pred) {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#ifdef CAPE_EXP_EVICT_LAST   // profiling variant: keep gathered value rows in L1 with evict-last priority
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t@p ld.global.nc.L1::evict_last.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+        : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
+        : "l"(p), "r"(static_cast<int>(pred)));
+    return v;
+#endif
     asm("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t@p ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
         : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
         : "l"(p), "r"(static_cast<int>(pred)));
@@ -109,7 +115,13 @@ __device__ __forceinline__ float4 mul4(float c, const float4& g) {
         : "f"(c), "f"(g.x), "f"(g.y), "f"(g.z), "f"(g.w));
     return r;
 }
-__device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4(float* p, const float4& v) {
+#ifdef CAPE_EXP_STREAM_STORE   // profiling variant: streaming (evict-first) output stores
+    asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    return;
+#endif
+    *reinterpret_cast<float4*>(p) = v;
+}
 __device__ __forceinline__ void st4(__nv_bfloat16* p, const float4& v) {
     const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
     uint2 r;

@@ -315,11 +315,16 @@ def test_reference_checkpoint_keys_load_into_the_mirror():
 def test_real_reference_state_dict_loads_into_the_mirror():
     """The reference's own RoomFormerV2 (stub backbone, oracle/make_golden.py) after `_setup_caches` — i.e. with the leaked
     KV / V cache buffers of Appendix A.2 in its state dict — loads into the mirror with nothing missing or unexpected."""
+    import sys
     from oracle import make_golden
     syn = make_golden.load_synthetic()
     shapes = ((8, 12), (4, 6), (2, 3), (1, 2))
     feats = [torch.zeros(2, 256, h, w) for h, w in shapes]
-    model, tokenizer, _ = make_golden.build_reference_model(syn, 20, 6, feats, None, 31)
+    saved_path = list(sys.path)
+    try:
+        model, tokenizer, _ = make_golden.build_reference_model(syn, 20, 6, feats, None, 31)
+    finally:
+        sys.path[:] = saved_path          # make_golden puts the reference checkout (with its own `tests/`) in front
     model._setup_caches(2, sum(h * w for h, w in shapes))
     state = model.state_dict()
     assert any(".kv_cache." in k for k in state)                                  # the leak is real

@@ -194,8 +194,13 @@ def test_real_training_loop_data_parallel_equals_single_process():
     q = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_dp_engine_worker, args=(r, 2, port, q)) for r in range(2)]
-    for p in procs:
-        p.start()
+    saved_path = list(sys.path)
+    sys.path.insert(0, REPO)      # spawn hands sys.path to the children: `tests` must resolve to THIS repo's package even
+    try:                          # if an earlier test left the reference checkout (which has its own `tests/`) in front
+        for p in procs:
+            p.start()
+    finally:
+        sys.path[:] = saved_path
     results = sorted((q.get(timeout=240) for _ in procs), key=lambda r: r[0])
     for p in procs:
         p.join(60)

@@ -183,6 +183,36 @@ __global__ void red_global_scalar(float* __restrict__ table, const int* __restri
     }
 }
 
+
+// bulk reductions through the TMA unit: every lane group stages its 128 B row in shared memory (STS.128) and one lane per row
+// issues cp.reduce.async.bulk (UBLKRED) to the row's global address; kStages commit groups in flight per warp
+constexpr int kBulkStages = 8;
+__global__ void red_bulk_tma(float* __restrict__ table, const int* __restrict__ idx, int rows_per_cta_window, int window_stride) {
+    extern __shared__ __align__(128) float4 ring[];           // [warp][stage][4 rows][8 float4]
+    const int lane = threadIdx.x & 31, slot = lane >> 3, k = lane & 7, warp = threadIdx.x >> 5;
+    const int* my = idx + ((size_t)blockIdx.x * (kThreads / 32) + warp) * kIters * 4;
+    float* base = table + (size_t)(blockIdx.x % window_stride) * rows_per_cta_window * 32;
+    float4* mine = ring + (size_t)warp * kBulkStages * 32;
+    for (int i = 0; i < kIters; ++i) {
+        const int r = __ldg(my + i * 4 + slot);
+        float4* stage = mine + (i % kBulkStages) * 32;
+        if (i >= kBulkStages) {                                  // the stage's previous bulk op must have read its rows
+            if (k == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kBulkStages - 1) : "memory");
+            __syncwarp();
+        }
+        stage[slot * 8 + k] = make_float4(1.f, 2.f, 3.f, 4.f);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (k == 0) {
+            const unsigned src = (unsigned)__cvta_generic_to_shared(stage + slot * 8);
+            float* dst = base + (size_t)r * 32;
+            asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], 128;" ::"l"(dst), "r"(src) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    if (k == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 template <typename F>
 float time_ms(F launch, int reps = 5) {
     cudaEvent_t a, b;
@@ -246,6 +276,7 @@ int main() {
         report("gather bf16 LDG.64 (4 rows/instr)", time_ms([&] { gather_bf16_v2<<<grid, kThreads>>>((const uint2*)table, idx, (uint2*)out, c.rows, c.windows); }), 64);
         report("red.global.add.v4.f32 (4 rows/instr)", time_ms([&] { red_global_v4<<<grid, kThreads>>>(table, idx, c.rows, c.windows); }), 128);
         report("atomicAdd f32 scalar (1 row/instr)", time_ms([&] { red_global_scalar<<<grid, kThreads>>>(table, idx, c.rows, c.windows); }), 128);
+        report("cp.reduce.async.bulk add.f32 128 B rows", time_ms([&] { red_bulk_tma<<<grid, kThreads, (kThreads / 32) * kBulkStages * 512>>>(table, idx, c.rows, c.windows); }), 128);
     }
     // shared-memory cases: 512 rows of 128 B = 64 KB per CTA (3 CTAs/SM)
     {
