@@ -15,8 +15,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcape_msda.so")
-SOURCES = ["cape_abi.cu", "msda_forward.cu", "msda_forward_staged.cu", "msda_backward.cu", "msda_backward_staged.cu", "msda_variants.cu", "seq_tokens.cu", "decode_step.cu", "linear_tf32x3.cu"]
-HEADERS = ["msda_common.cuh", "msda_launch.h", "async_copy.cuh", os.path.join("..", "..", "include", "cape_msda.h")]
+SOURCES = ["cape_abi.cu", "msda_forward.cu", "msda_forward_staged.cu", "msda_backward.cu", "msda_backward_staged.cu", "msda_backward_tc.cu", "msda_variants.cu", "seq_tokens.cu", "decode_step.cu", "linear_tf32x3.cu"]
+HEADERS = ["msda_common.cuh", "msda_launch.h", "async_copy.cuh", "umma_tf32.cuh", os.path.join("..", "..", "include", "cape_msda.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -48,7 +48,8 @@ def build(force: bool = False, verbose: bool = False, variant: str = "") -> str:
     extra = []
     if variant:
         extra = {"nored": ["-DCAPE_EXP_NO_RED"], "noload": ["-DCAPE_EXP_NO_LOAD"], "t896": ["-DCAPE_BS_THREADS=896"],
-                 "t768": ["-DCAPE_BS_THREADS=768"], "nocoarsered": ["-DCAPE_EXP_NO_COARSE_RED"], "evictlast": ["-DCAPE_EXP_EVICT_LAST"],
+                 "t768": ["-DCAPE_BS_THREADS=768"], "nocoarsered": ["-DCAPE_EXP_NO_COARSE_RED=12"], "nored0": ["-DCAPE_EXP_NO_COARSE_RED=1"], "nored1": ["-DCAPE_EXP_NO_COARSE_RED=2"],
+                 "nored2": ["-DCAPE_EXP_NO_COARSE_RED=4"], "nored3": ["-DCAPE_EXP_NO_COARSE_RED=8"], "nored01": ["-DCAPE_EXP_NO_COARSE_RED=3"], "evictlast": ["-DCAPE_EXP_EVICT_LAST"],
                  "streamstore": ["-DCAPE_EXP_STREAM_STORE"]}[variant]
         lib = os.path.join(os.path.dirname(HERE), "tools", f"libcape_msda_{variant}.so")
         return _compile(lib, extra, verbose, os.path.join(HERE, "build", variant))

@@ -82,7 +82,8 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 namespace {
 const char* const kTuneNames[kTuneCount] = {"FWD_THREADS", "FWD_QPC", "FWD_POINT_MAX_QM", "FWD_STAGED", "FWD_STAGED_MIN_QM",
-                                            "FWD_STAGED_KB", "BWD_THREADS", "BWD_QPC", "BWD_MODE", "BWD_STAGED_KB", "PROFILE"};
+                                            "FWD_STAGED_KB", "BWD_THREADS", "BWD_QPC", "BWD_MODE", "BWD_STAGED_KB", "PROFILE",
+                                            "BWD_TC_MIN_QM"};
 std::atomic<int> g_tune[kTuneCount];
 std::once_flag g_tune_once;
 

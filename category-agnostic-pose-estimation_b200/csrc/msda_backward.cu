@@ -184,8 +184,8 @@ msda_bwd_fast_kernel(const VT* __restrict__ gout, const VT* __restrict__ value, 
             const float py = __shfl_sync(kFullMask, locv, l * 8 + p * 2 + 1);
             const float a = __shfl_sync(kFullMask, attnv, l * 4 + p);
             float ga, gx, gy;
-#ifdef CAPE_EXP_NO_COARSE_RED   // profiling-only variant (tools/, never shipped): levels >= 2 gather but do not scatter
-            scatter_level(vbase, l >= 2 ? nullptr : gbase, rowStride, lv.off[l], lv.H[l], lv.W[l], px, py, a, g, ga, gx, gy);
+#ifdef CAPE_EXP_NO_COARSE_RED   // profiling-only variant (tools/, never shipped): levels in the mask gather but do not scatter
+            scatter_level(vbase, ((CAPE_EXP_NO_COARSE_RED >> l) & 1) ? nullptr : gbase, rowStride, lv.off[l], lv.H[l], lv.W[l], px, py, a, g, ga, gx, gy);
 #else
             scatter_level(vbase, gbase, rowStride, lv.off[l], lv.H[l], lv.W[l], px, py, a, g, ga, gx, gy);
 #endif
@@ -356,6 +356,11 @@ cudaError_t launch_backward(const BwdArgs& a, cudaStream_t stream) {
     const int mode = tuning(kTuneBwdMode, 1);      // 1: L1 kernel + REDs; 2: staged rows + tensor-core scatter; 3: staged rows
     if (mode == 2 || mode == 3 || mode == 4) {   // 4: profiling only (results invalid), see msda_backward_staged.cu
         const cudaError_t e = launch_backward_staged(a, mode, stream);
+        if (e == cudaSuccess) count_launch();
+        if (e != cudaErrorNotSupported) return e;
+    }
+    if (mode == 5) {   // small CTAs + tensor-core scatter of the coarsest level (msda_backward_tc.cu)
+        const cudaError_t e = launch_backward_tc(a, stream);
         if (e == cudaSuccess) count_launch();
         if (e != cudaErrorNotSupported) return e;
     }

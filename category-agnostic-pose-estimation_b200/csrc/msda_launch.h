@@ -70,6 +70,8 @@ cudaError_t launch_backward(const BwdArgs& a, cudaStream_t stream);
 // shared-memory staged variants (persistent, TMA): return cudaErrorNotSupported for configurations they do not cover
 cudaError_t launch_forward_staged(const FwdArgs& a, cudaStream_t stream);
 cudaError_t launch_backward_staged(const BwdArgs& a, int mode, cudaStream_t stream);   // mode 2: + tensor-core scatter, 3: staged only
+// small CTAs, coarsest level scattered by tcgen05 (msda_backward_tc.cu); cudaErrorNotSupported outside its configurations
+cudaError_t launch_backward_tc(const BwdArgs& a, cudaStream_t stream);
 cudaError_t read_backward_staged_cycles(long long* out16, bool reset);   // PROFILE knob: cycle counters of CTA 0
 cudaError_t launch_query_pool_forward(const FwdArgs& a, cudaStream_t stream);     // fp32 only
 cudaError_t launch_query_pool_backward(const BwdArgs& a, cudaStream_t stream);    // fp32 only
@@ -141,7 +143,7 @@ inline int balanced_q_per_cta(int64_t nm, int lq, int q_default, int slots, int 
 // time through cape_set_tuning() (tools/tune.py).  Values <= 0 mean "default".
 enum Tune {
     kTuneFwdThreads, kTuneFwdQpc, kTuneFwdPointMaxQm, kTuneFwdStaged, kTuneFwdStagedMinQm, kTuneFwdStagedKb,
-    kTuneBwdThreads, kTuneBwdQpc, kTuneBwdMode, kTuneBwdStagedKb, kTuneProfile, kTuneCount
+    kTuneBwdThreads, kTuneBwdQpc, kTuneBwdMode, kTuneBwdStagedKb, kTuneProfile, kTuneBwdTcMinQm, kTuneCount
 };
 int tuning(Tune knob, int fallback);
 

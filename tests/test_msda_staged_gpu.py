@@ -19,9 +19,10 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture
 def staged():
     """Force the staged kernels for any size; restore the defaults afterwards."""
-    knobs = ("FWD_STAGED", "FWD_STAGED_MIN_QM", "FWD_STAGED_KB", "BWD_MODE", "BWD_STAGED_KB")
+    knobs = ("FWD_STAGED", "FWD_STAGED_MIN_QM", "FWD_STAGED_KB", "BWD_MODE", "BWD_STAGED_KB", "BWD_TC_MIN_QM")
     _lib.set_tuning("FWD_STAGED", 1)
     _lib.set_tuning("FWD_STAGED_MIN_QM", 1)
+    _lib.set_tuning("BWD_TC_MIN_QM", 1)
     yield _lib.set_tuning
     for k in knobs:
         _lib.set_tuning(k, 0)
@@ -141,7 +142,9 @@ def _fwd_bwd(inp, dtype=torch.float32, aux=None):
     return tuple(t.detach().float().cpu().numpy() for t in (gv, gl, ga))
 
 
-@pytest.mark.parametrize("mode", [2, 3])                       # 2: + tensor-core scatter; 3: staged rows, all REDs
+# 2: staged rows + tensor-core scatter of the two coarse levels; 3: staged rows, all REDs; 5: small CTAs, tensor-core scatter of
+# the coarsest level (csrc/msda_backward_tc.cu)
+@pytest.mark.parametrize("mode", [2, 3, 5])
 @pytest.mark.parametrize("dist", ["encoder", "uniform"])
 @pytest.mark.parametrize("n,lq", [(2, 700), (3, 129), (1, 5440), (2, 31)])
 def test_backward_staged_fp32_vs_c_oracle(staged, mode, dist, n, lq):
@@ -159,32 +162,35 @@ def test_backward_staged_fp32_vs_c_oracle(staged, mode, dist, n, lq):
 
 @pytest.mark.parametrize("shapes,m", [(synthetic.CAPE_PYRAMID_512, 8), (((16, 12), (8, 6), (4, 3), (2, 2)), 3),
                                       (((40, 40), (3, 50), (7, 7), (1, 1)), 5), (((30, 30), (20, 20), (25, 20), (4, 4)), 2)])
-def test_backward_tensor_core_scatter_other_pyramids(staged, shapes, m):
+@pytest.mark.parametrize("mode", [2, 5])
+def test_backward_tensor_core_scatter_other_pyramids(staged, shapes, m, mode):
     """Small pyramids (two covered levels in one 128-row tile), non-square levels, M != 8, and a pyramid whose level 2
     (500 pixels) does not fit the 384 covered rows (only the last level goes to the tensor cores)."""
     inp = synthetic.make_inputs(2, 333, shapes, n_heads=m, dist="uniform", seed=m)
     want = msda_c.msda_backward(inp["grad_output"].numpy(), *_oracle_args(inp), dtype=np.float32)
-    staged("BWD_MODE", 2)
+    staged("BWD_MODE", mode)
     gv, gl, ga = _fwd_bwd(inp)
     for got, w in zip((gv, gl, ga), want):
         assert rel_err(got, w) < 1e-4
 
 
+@pytest.mark.parametrize("mode", [2, 5])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
-def test_backward_tensor_core_scatter_half_precision(staged, dtype):
+def test_backward_tensor_core_scatter_half_precision(staged, dtype, mode):
     inp = synthetic.make_inputs(2, 600, dist="encoder", seed=21)
     rounded = dict(inp)
     rounded["value"] = inp["value"].to(dtype).float()
     rounded["grad_output"] = inp["grad_output"].to(dtype).float()
     want = msda_c.msda_backward(rounded["grad_output"].numpy(), *_oracle_args(rounded), dtype=np.float32)
-    staged("BWD_MODE", 2)
+    staged("BWD_MODE", mode)
     gv, gl, ga = _fwd_bwd(inp, dtype, torch.float32)
     for got, w in zip((gv, gl, ga), want):
         assert rel_err(got, w) < 2e-2
 
 
-def test_fused_backward_tensor_core_scatter(staged):
-    """cape::ms_deform_attn_fused_backward (softmax / location prologue inside the kernel) in mode 2 vs the L1 kernel."""
+@pytest.mark.parametrize("mode", [2, 5])
+def test_fused_backward_tensor_core_scatter(staged, mode):
+    """cape::ms_deform_attn_fused_backward (softmax / location prologue inside the kernel) in modes 2 / 5 vs the L1 kernel."""
     g = torch.Generator().manual_seed(4)
     n, lq, m, l, p = 2, 450, 8, 4, 4
     inp = synthetic.make_inputs(n, lq, dist="encoder", seed=5)
@@ -202,7 +208,7 @@ def test_fused_backward_tensor_core_scatter(staged):
         return res
     staged("BWD_MODE", 1)
     want = run()
-    staged("BWD_MODE", 2)
+    staged("BWD_MODE", mode)
     got = run()
     for a, b in zip(got, want):
         assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < 1e-4

@@ -54,5 +54,11 @@ for dist in ("encoder", "uniform"):
         if which in ("bwd", "both"):
             for mode in (int(m) for m in os.environ.get("TUNE_BWD_MODES", "1,2").split(",")):
                 _lib.set_tuning("BWD_MODE", mode)
-                print(f"{dist:8s} {name:4s} bwd mode {mode} (memset incl.) {timeit(bwd):8.1f} us", flush=True)
+                for prof in (int(x) for x in os.environ.get("TUNE_PROFILE", "0").split(",")) if mode == 5 else (0,):
+                    _lib.set_tuning("PROFILE", prof)
+                    for qpc in (int(x) for x in os.environ.get("TUNE_QPC", "0").split(",")) if mode == 5 else (0,):
+                        _lib.set_tuning("BWD_QPC", qpc)
+                        print(f"{dist:8s} {name:4s} bwd mode {mode} prof {prof} qpc {qpc:4d} (memset incl.) {timeit(bwd):8.1f} us", flush=True)
+                _lib.set_tuning("PROFILE", 0)
+                _lib.set_tuning("BWD_QPC", 0)
             _lib.set_tuning("BWD_MODE", 0)
