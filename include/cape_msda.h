@@ -321,6 +321,9 @@ CAPE_API uint64_t cape_launch_count(void);
  * from the environment variable of the same name (CAPE_FWD_THREADS, CAPE_FWD_QPC, CAPE_FWD_POINT_MAX_QM, CAPE_FWD_STAGED,
  * CAPE_BWD_THREADS, CAPE_BWD_QPC, CAPE_BWD_MODE ...); this call changes it at run time (value <= 0: back to the
  * default).  Returns 0, or CAPE_ERR_BAD_DIMS for an unknown name.  Not part of the reference-facing interface.
+ * BWD_MODE: 1 (default) small CTAs, vector REDs for every level; 2 persistent CTAs, TMA-staged coarse rows + tcgen05 scatter of
+ * the two coarse levels; 3 staged rows only; 5 small CTAs + tcgen05 scatter of the coarsest level (4 is a profiling aid with
+ * invalid results).  PROFILE is read by modes 2-5 only and must stay 0 outside timing experiments.
  */
 CAPE_API int cape_set_tuning(const char* name, int value);
 CAPE_API int cape_get_tuning(const char* name);
