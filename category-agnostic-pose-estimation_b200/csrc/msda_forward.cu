@@ -86,6 +86,48 @@ __device__ __forceinline__ void gather_level(const VT* __restrict__ img, int lev
     fma4(aly * lx, v11, acc);
 }
 
+// Build variant `--variant=fwdtable` (-DCAPE_FWD_TABLE=1): every lane converts its own two samples once and the group reads
+// 16-byte records from a per-warp shared-memory table instead of 3 shuffles + the floor / bounds arithmetic per sample.
+// Parity-green and 35 % fewer instructions, but SLOWER in fp32 (357 vs 313 us; bf16 294 vs 298): a 16-byte read by four
+// query groups costs 4 wavefronts on the LSU pipe that bounds this kernel, the 3 shuffles cost 3
+// (profiles/r02_forward_sample_table.txt).  Default stays the shuffle form.
+#ifndef CAPE_FWD_TABLE
+#define CAPE_FWD_TABLE 0
+#endif
+
+// Sample record written once per sample by the lane that owns it and read by the 8 lanes of its query group:
+// (a, lx, ly, off | valid) — off = element offset of corner (y0, x0) inside the (n, m, quad) image, a multiple of
+// rowStride >= 32, so its 4 low bits carry the in-bounds flags of the 4 corners.
+__device__ __forceinline__ float4 make_sample_record(float px, float py, float a, int H, int W, int levelOff, int rowStride) {
+    const float xf = floorf(px), yf = floorf(py);
+    const int x0 = static_cast<int>(xf), y0 = static_cast<int>(yf);
+    const unsigned x0ok = static_cast<unsigned>(x0) < static_cast<unsigned>(W);
+    const unsigned x1ok = static_cast<unsigned>(x0 + 1) < static_cast<unsigned>(W);
+    const unsigned y0ok = static_cast<unsigned>(y0) < static_cast<unsigned>(H);
+    const unsigned y1ok = static_cast<unsigned>(y0 + 1) < static_cast<unsigned>(H);
+    const int off = levelOff + (y0 * W + x0) * rowStride;
+    const unsigned bits = (y0ok & x0ok) | ((y0ok & x1ok) << 1) | ((y1ok & x0ok) << 2) | ((y1ok & x1ok) << 3);
+    return make_float4(a, px - xf, py - yf, __int_as_float(off | static_cast<int>(bits)));
+}
+
+template <typename VT>
+__device__ __forceinline__ void gather_record(const VT* __restrict__ img, const float4& r, int rowStride, int downStride,
+                                              float4& acc) {
+    const int w = __float_as_int(r.w);
+    const VT* p00 = img + (w & ~15);
+    const VT* p10 = p00 + downStride;
+    const float a = r.x, lx = r.y, ly = r.z;
+    const float ahy = a * (1.f - ly), aly = a * ly, hx = 1.f - lx;
+    const float4 v00 = ld4_or_zero(p00, w & 1);
+    const float4 v01 = ld4_or_zero(p00 + rowStride, w & 2);
+    const float4 v10 = ld4_or_zero(p10, w & 4);
+    const float4 v11 = ld4_or_zero(p10 + rowStride, w & 8);
+    fma4(ahy * hx, v00, acc);
+    fma4(ahy * lx, v01, acc);
+    fma4(aly * hx, v10, acc);
+    fma4(aly * lx, v11, acc);
+}
+
 // The sample table of one (q, m), spread over the 8 lanes of the query's group: lane k holds location floats
 // 4k .. 4k+3 (= samples 2k and 2k+1, both of level k >> 1) and weights 2k, 2k+1.
 struct RawSamples {
@@ -135,12 +177,21 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
     lv.load(shapes, starts, value + (static_cast<int64_t>(n) * S * M + m) * D + k * 4, rowStride, S);
     // dimensions of the level whose samples this lane converts (level k >> 1)
     float ownW = 1.f, ownH = 1.f;
+    int ownWi = 0, ownHi = 0, ownOff = 0;
 #pragma unroll
     for (int l = 0; l < L; ++l)
         if ((k >> 1) == l) {
             ownW = static_cast<float>(lv.W[l]);
             ownH = static_cast<float>(lv.H[l]);
+            ownWi = lv.W[l];
+            ownHi = lv.H[l];
+            ownOff = lv.off[l];
         }
+#if CAPE_FWD_TABLE
+    // per-warp sample records: [sample 0..15][query slot g] x 16 B, so that the 4 groups' reads of one sample are 64 contiguous bytes
+    __shared__ float4 sample_table[kFwdMaxThreads / 32][16][4];
+    float4(*table)[4] = sample_table[warp];
+#endif
     const LT* loc_t = static_cast<const LT*>(locp);
     const LT* attn_t = static_cast<const LT*>(attnp);
     const int q_end = min(Lq, (qt + 1) * q_per_cta);
@@ -178,6 +229,22 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
         const float px0 = on ? pixel_coord(cur.loc.x, ownW) : -4.f, py0 = on ? pixel_coord(cur.loc.y, ownH) : -4.f;
         const float px1 = on ? pixel_coord(cur.loc.z, ownW) : -4.f, py1 = on ? pixel_coord(cur.loc.w, ownH) : -4.f;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#if CAPE_FWD_TABLE
+        // every lane converts its own two samples once (floor, bounds, offset) instead of all 8 lanes of the group
+        // repeating it for all 16; the group then reads one 16-byte record per sample
+        __syncwarp();                                    // the previous quad's records have been read
+        if (k < 2 * L) {
+            table[2 * k][g] = make_sample_record(px0, py0, cur.attn.x, ownHi, ownWi, ownOff, rowStride);
+            table[2 * k + 1][g] = make_sample_record(px1, py1, cur.attn.y, ownHi, ownWi, ownOff, rowStride);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+            const int downStride = lv.W[l] * rowStride;
+#pragma unroll
+            for (int p = 0; p < 4; ++p) gather_record(lv.img, table[l * 4 + p][g], rowStride, downStride, acc);
+        }
+#else
 #pragma unroll
         for (int l = 0; l < L; ++l) {
 #pragma unroll
@@ -189,6 +256,7 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
                 gather_level(lv.img, lv.off[l], rowStride, lv.H[l], lv.W[l], px, py, a, acc);
             }
         }
+#endif
         if (on) st4(out + (nq * M + m) * D + k * 4, acc);
     }
 }
