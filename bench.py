@@ -341,7 +341,7 @@ def _force_coordinate_tokens(model):
             head.bias.copy_(torch.tensor([50.0, 0.0, 0.0], device=head.bias.device))
 
 
-def cape_train_step(dev, rank, world, steps=2, with_reference=False, amp=False, tensor_core=False):
+def cape_train_step(dev, rank, world, steps=3, with_reference=False, amp=False, tensor_core=False):
     """BASELINE.json configs[2] / [4]: CAPE 5-shot episodic training, batch 10 episodes x 2 queries (N = 20) per GPU,
     accumulation 4, AdamW with the reference's two parameter groups, clip 0.1 — the UNMODIFIED reference model
     (ResNet-50 + input_proj + 6 + 6 deformable transformer layers + geometric/GCN support encoder + heads), its own
@@ -397,14 +397,17 @@ def cape_train_step(dev, rank, world, steps=2, with_reference=False, amp=False, 
         launches0 = cape_b200.launch_count()
         epoch(1, patched, buckets, opt, scaler)
         per_step = cape_b200.launch_count() - launches0
-        cdist.barrier(dev)
-        torch.cuda.synchronize(dev)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        stats = epoch(steps, patched, buckets, opt, scaler)
-        e1.record()
-        torch.cuda.synchronize(dev)
-        ms = cdist.max_over_ranks(e0.elapsed_time(e1), dev) / steps
+        times = []                      # every optimizer step timed on its own (device events, max over ranks); median reported:
+        for _ in range(steps):          # single steps on a shared host vary by +-25 % now and then (tools/arm_variance.py)
+            cdist.barrier(dev)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            stats = epoch(1, patched, buckets, opt, scaler)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            times.append(cdist.max_over_ranks(e0.elapsed_time(e1), dev))
+        ms = sorted(times)[len(times) // 2]
         buckets.remove()
         for p in model.parameters():
             p.grad = None
@@ -462,21 +465,25 @@ def cape_inference(dev, rank, world, episodes=64, keypoints=100, with_reference=
         return out["coordinates"].float().sum().item(), out["logits"].shape[1]      # D2H read of the result
 
     def timed(reps):
+        """Median over `reps` batches (each timed on its own after a barrier; max over ranks): single batches on a shared host
+        vary by +-25 % now and then (tools/arm_variance.py)."""
         run()
-        cdist.barrier(dev)
-        torch.cuda.synchronize(dev)
-        t0 = time.perf_counter()
+        times = []
         for _ in range(reps):
+            cdist.barrier(dev)
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
             _, steps = run()
-        torch.cuda.synchronize(dev)
-        return cdist.max_over_ranks((time.perf_counter() - t0) / reps, dev), steps
+            torch.cuda.synchronize(dev)
+            times.append(cdist.max_over_ranks(time.perf_counter() - t0, dev))
+        return sorted(times)[len(times) // 2], steps
 
     mod_name = "models.deformable_transformer"
     cape_b200.patch_reference(sys.modules[mod_name], swap_forward_inference=True)
     try:
         launches0 = cape_b200.launch_count()
-        t_fast, steps = timed(2)
-        launches = (cape_b200.launch_count() - launches0) // 3
+        t_fast, steps = timed(3)
+        launches = (cape_b200.launch_count() - launches0) // 4
     finally:
         cape_b200.unpatch_reference()
     out = {"episodes_per_s": round(world * episodes / t_fast, 2), "s_per_batch": round(t_fast, 4),
@@ -488,7 +495,7 @@ def cape_inference(dev, rank, world, episodes=64, keypoints=100, with_reference=
     cape_b200.patch_reference(sys.modules[mod_name], swap_forward_inference=True)
     cape_b200.set_linear_mode("tf32x3")
     try:
-        t_tc, _ = timed(2)
+        t_tc, _ = timed(3)
         out["tensor_core_linears"] = {"episodes_per_s": round(world * episodes / t_tc, 2), "s_per_batch": round(t_tc, 4)}
     except Exception as exc:                                       # noqa: BLE001
         out["tensor_core_linears"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
@@ -841,14 +848,14 @@ def generation(dev, episodes=64, keypoints=100):
             gen_tc = cape_b200.AutoregressiveGenerator(tr, spec, n, dev)
             run_tc = lambda: gen_tc.generate(feats, masks, pos, query_embed, sup, sup_mask, enc_cache=enc_tc)
             run_tc()
-            t_dec_tc, _ = timed(run_tc)
+            t_dec_tc, _ = min((timed(run_tc) for _ in range(3)), key=lambda r: r[0])
         del gen_tc, enc_tc
     finally:
         cape_b200.set_linear_mode("fp32")
     gen = cape_b200.AutoregressiveGenerator(tr, spec, n, dev)
     run = lambda: gen.generate(feats, masks, pos, query_embed, sup, sup_mask, enc_cache=enc_cache)
     run()                                                    # captures the graph
-    t_dec, out = timed(run)
+    t_dec, out = min((timed(run) for _ in range(3)), key=lambda r: r[0])       # best of 3, like the encoder pass above
     steps = out["steps"]
     gen.state.reset()                                        # the token step alone: replays of the captured graph
     t_rep, _ = timed(lambda: [gen.graph.replay() for _ in range(50)])
