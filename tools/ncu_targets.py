@@ -1,6 +1,7 @@
 """One launch of each sampling-kernel variant at the bench shape (N=20, Lq=S=5440, fp32, encoder-like) for ncu:
 forward L1 kernel, forward staged (200 KB), backward L1 kernel (mode 1), backward staged + tensor-core scatter (mode 2),
-backward staged with the covered levels' REDs dropped (mode 4, timing floor only).  Prints CUDA-event times when run plain."""
+backward staged with the covered levels' REDs dropped (mode 4, timing floor only), backward small CTAs + tcgen05 scatter of
+the coarsest level (mode 5).  Prints CUDA-event times when run plain."""
 import ctypes
 import os
 import sys
@@ -45,7 +46,8 @@ run("forward  staged, levels 1-3 in shared memory", fwd)
 _lib.set_tuning("FWD_STAGED", 0)
 gv.zero_()
 run("backward L1 kernel + REDs (default, mode 1)", bwd)
-for mode, label in ((2, "backward staged + tensor-core scatter (mode 2)"), (4, "backward staged, coarse REDs dropped (mode 4)")):
+for mode, label in ((2, "backward staged + tensor-core scatter (mode 2)"), (4, "backward staged, coarse REDs dropped (mode 4)"),
+                    (5, "backward small CTAs + tensor-core scatter of the 8x8 level (mode 5)")):
     _lib.set_tuning("BWD_MODE", mode)
     run(label, bwd)
 _lib.set_tuning("BWD_MODE", 0)
