@@ -83,7 +83,7 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 namespace {
 const char* const kTuneNames[kTuneCount] = {"FWD_THREADS", "FWD_QPC", "FWD_POINT_MAX_QM", "FWD_STAGED", "FWD_STAGED_MIN_QM",
                                             "FWD_STAGED_KB", "BWD_THREADS", "BWD_QPC", "BWD_MODE", "BWD_STAGED_KB", "PROFILE",
-                                            "BWD_TC_MIN_QM"};
+                                            "BWD_TC_MIN_QM", "HOST_CHUNKS"};
 std::atomic<int> g_tune[kTuneCount];
 std::once_flag g_tune_once;
 
@@ -758,8 +758,10 @@ int cape_msda_forward_backward_host(const float* value_host, const int64_t* spat
     // (PCIe is full duplex).  Copies ride on two library-owned helper streams forked from / joined to `stream` with
     // events; kernels stay on the caller's stream.
     const size_t bytes_in = static_cast<size_t>(d.N) * (ev + 3 * ea + (bwd ? eo : 0));
-    constexpr int kMaxChunks = 8;
-    int chunks = bytes_in > (static_cast<size_t>(32) << 20) ? (d.N < kMaxChunks ? d.N : kMaxChunks) : 1;
+    constexpr int kMaxChunks = 32;
+    int want = cape::tuning(cape::kTuneHostChunks, kMaxChunks);   // N = 20: 20 chunks of one image 9.67 ms, 8 chunks 10.23 ms (tools/host_chunks_time.py)
+    if (want > kMaxChunks) want = kMaxChunks;
+    int chunks = bytes_in > (static_cast<size_t>(32) << 20) ? (d.N < want ? d.N : want) : 1;
     HelperStreams hs;
     if (chunks > 1 && !get_helper_streams(&hs)) chunks = 1;
     // Events are owned by a guard so that every exit path (including the CAPE_TRY early returns) destroys them and joins

@@ -143,7 +143,7 @@ inline int balanced_q_per_cta(int64_t nm, int lq, int q_default, int slots, int 
 // time through cape_set_tuning() (tools/tune.py).  Values <= 0 mean "default".
 enum Tune {
     kTuneFwdThreads, kTuneFwdQpc, kTuneFwdPointMaxQm, kTuneFwdStaged, kTuneFwdStagedMinQm, kTuneFwdStagedKb,
-    kTuneBwdThreads, kTuneBwdQpc, kTuneBwdMode, kTuneBwdStagedKb, kTuneProfile, kTuneBwdTcMinQm, kTuneCount
+    kTuneBwdThreads, kTuneBwdQpc, kTuneBwdMode, kTuneBwdStagedKb, kTuneProfile, kTuneBwdTcMinQm, kTuneHostChunks, kTuneCount
 };
 int tuning(Tune knob, int fallback);
 
