@@ -869,7 +869,7 @@ def generation(dev, episodes=64, keypoints=100):
     total = t_enc + t_dec
     return {"episodes": episodes, "queries_per_episode": 2, "tokens": steps, "encoder_layers": 6, "decoder_layers": 6,
             "encoder_s": round(t_enc, 4), "decode_s": round(t_dec, 4), "value_projection_s": round(t_reset, 4),
-            "us_per_token_step": round(t_rep / 50 * 1e6, 1), "launches_per_token_step": 6 * 16 + 6,
+            "us_per_token_step": round(t_rep / 50 * 1e6, 1), "launches_per_token_step": 6 * 15 + 6,
             "episodes_per_s": round(episodes / total, 2), "tokens_per_s": round(n * steps / t_dec, 1),
             "tensor_core_linears": {"encoder_s": round(t_enc_tc, 4), "decode_s": round(t_dec_tc, 4),
                                     "episodes_per_s": round(episodes / (t_enc_tc + t_dec_tc), 2),

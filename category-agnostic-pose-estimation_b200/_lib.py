@@ -71,6 +71,7 @@ _SIGNATURES = {
     "cape_decode_attention": (_i, [_vp, _i, _vp, _vp, _i] + [_vp] * 5 + [_i] * 4 + [_vp]),
     "cape_skinny_linear": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, ctypes.c_float, _vp, _vp, _i, _i, _i, _i, _i,
                                 _vp]),
+    "cape_msda_output_proj": (_i, [_vp] * 6 + [ctypes.POINTER(Dims)] + [_vp, _vp, _vp, _i, _vp, _vp, ctypes.c_float, _vp, _i, _i, _vp]),
     "cape_skinny_linear_split": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp]),
     "cape_coord_head_refine": (_i, [_vp, _i] + [_vp] * 8 + [_i] * 4 + [_vp]),
     "cape_tiny_linear": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),

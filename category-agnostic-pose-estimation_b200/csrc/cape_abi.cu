@@ -558,6 +558,42 @@ int cape_skinny_linear(const float* x, int x_stride, const float* x2, int x2_str
     return e == cudaSuccess ? 0 : fail_cuda(e, "cape_skinny_linear launch");
 }
 
+int cape_msda_output_proj(const float* value_cache, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                          const float* reference_points, const float* sampling_offsets, const float* attention_logits,
+                          const cape_msda_dims* dims, const float* wt, const float* bias, const float* residual,
+                          int residual_stride, const float* gamma, const float* beta, float eps, float* y, int y_stride,
+                          int n_out, void* stream) {
+    int rc;
+    if ((rc = check_dims(dims))) return rc;
+    const cape_msda_dims& d = *dims;
+    if (d.D != 32 || d.P != 4 || d.L != 4 || d.M < 1 || d.M * 32 > 2048 || (d.M * 32) % 16 != 0)
+        return fail(CAPE_ERR_BAD_DIMS, "cape_msda_output_proj needs D = 32, P = 4, L = 4 (got D=%d P=%d L=%d M=%d)", d.D, d.P, d.L, d.M);
+    if (n_out <= 0 || n_out > 256 || n_out % 4 != 0 || !gamma || !beta)
+        return fail(CAPE_ERR_BAD_DIMS, "the LayerNorm epilogue needs 0 < N <= 256, N %% 4 == 0 (got %d) and gamma / beta", n_out);
+    const long long rows64 = static_cast<long long>(d.N) * d.Lq;
+    if (rows64 > 0x7fffffffLL) return fail(CAPE_ERR_BAD_DIMS, "too many rows");
+    const int rows = static_cast<int>(rows64);
+    const bool empty = rows == 0;
+    if ((rc = check_ptr(value_cache, "value_cache", empty)) || (rc = check_ptr(spatial_shapes, "spatial_shapes", false, 8)) ||
+        (rc = check_ptr(level_start_index, "level_start_index", false, 8)) ||
+        (rc = check_ptr(reference_points, "reference_points", empty, 4)) ||
+        (rc = check_ptr(sampling_offsets, "sampling_offsets", empty, 4)) ||
+        (rc = check_ptr(attention_logits, "attention_logits", empty, 4)) || (rc = check_ptr(wt, "wt", false)) ||
+        (rc = check_ptr(bias, "bias", true, 4)) || (rc = check_ptr(residual, "residual", true, 4)) ||
+        (rc = check_ptr(gamma, "gamma", false, 4)) || (rc = check_ptr(beta, "beta", false, 4)) || (rc = check_ptr(y, "y", empty, 4)))
+        return rc;
+    SkinnyArgs a{};
+    a.wt = wt, a.bias = bias, a.res = residual, a.gamma = gamma, a.beta = beta, a.y = y;
+    a.rows = rows, a.K = d.M * 32, a.N = n_out;
+    a.res_stride = residual_stride, a.y_stride = y_stride;
+    a.eps = eps;
+    a.msda_value = value_cache, a.msda_shapes = spatial_shapes, a.msda_starts = level_start_index;
+    a.msda_ref = reference_points, a.msda_off = sampling_offsets, a.msda_logits = attention_logits;
+    a.msda_S = d.S, a.msda_M = d.M, a.msda_Lq = d.Lq;
+    const cudaError_t e = launch_skinny_linear(a, 2, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? 0 : fail_cuda(e, "cape_msda_output_proj launch");
+}
+
 int cape_skinny_linear_split(const float* x, int x_stride, const float* x2, int x2_stride, const float* wt,
                              const float* bias, float* y, int y_stride, float* y2, int y2_stride, int split, int rows, int K,
                              int N, void* stream) {

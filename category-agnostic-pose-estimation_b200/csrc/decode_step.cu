@@ -20,6 +20,7 @@
 
 #include "msda_common.cuh"
 #include "msda_launch.h"
+#include "msda_point.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -201,8 +202,31 @@ skinny_linear_kernel(SkinnyArgs a) {
     for (int j = 0; j < kSkBatch; ++j)
         w[j] = (col_live && j < kper) ? __ldg(reinterpret_cast<const float4*>(wp + static_cast<int64_t>(j) * a.N))
                                       : make_float4(0.f, 0.f, 0.f, 0.f);
-    // stage the input rows (optionally x + x2, or the sine embedding of the reference points)
-    if (a.sine_dim_t) {   // K = 256: [coordinate 0: sin, cos interleaved over 128 | coordinate 1: same]  (:1013-1017)
+    // stage the input rows (optionally x + x2, the sine embedding of the reference points, or — output_proj of the decode
+    // step's MSDeformAttn, deformable_transformer.py:112-113 — the sampled rows themselves)
+    if (EPI == 2 && a.msda_value) {
+        // The CTAs of a row tile (one cluster) share the sampling: CTA `rank` takes every peers-th (row, head) pair, one warp
+        // per pair with all 16 corner loads in flight (sample_point), and writes the 32 channels into the input tile of
+        // EVERY CTA of the cluster through distributed shared memory; same arithmetic as cape_msda_decode.
+        cg::cluster_group cluster = cg::this_cluster();
+        const unsigned peers = cluster.num_blocks(), rank = cluster.block_rank();
+        const int lane = tid & 31, warp = tid >> 5;
+        const int M = a.msda_M;
+        cluster.sync();                                     // every peer's shared memory exists before anybody writes into it
+        for (int i = static_cast<int>(rank) + static_cast<int>(peers) * warp; i < kSkRows * M; i += static_cast<int>(peers) * (kThreads >> 5)) {
+            const int r = i / M, m = i - r * M;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < rows) {
+                const int64_t nq = r0 + r, qm = nq * M + m;
+                acc = sample_point<float, float, 4, true>(a.msda_value, a.msda_shapes, a.msda_starts, a.msda_off, a.msda_logits,
+                                                          a.msda_ref, qm, nq / a.msda_Lq, m, nq, a.msda_S, M, lane);
+            }
+            if (lane < 8)
+                for (unsigned p = 0; p < peers; ++p)
+                    *reinterpret_cast<float4*>(cluster.map_shared_rank(xs, p) + r * a.K + m * 32 + lane * 4) = acc;
+        }
+        cluster.sync();                                     // all peers' channels have landed
+    } else if (a.sine_dim_t) {   // K = 256: [coordinate 0: sin, cos interleaved over 128 | coordinate 1: same]  (:1013-1017)
         for (int i = tid; i < kSkRows * 256; i += kThreads) {
             const int r = i >> 8, k = i & 255;
             float v = 0.f;

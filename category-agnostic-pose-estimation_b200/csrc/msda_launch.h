@@ -102,6 +102,15 @@ struct SkinnyArgs {
     float* ref_out;            // (rows, 2)
     float* ref_levels;         // (rows, n_levels, 2)
     int n_levels;
+    // input = MSDeformAttn sampling (fused softmax / location prologue) on a projected-value cache instead of x: row r of the
+    // input is the sampled (M x 32)-vector of query r.  LayerNorm epilogue only; K = msda_M * 32, 4 levels x 4 points.
+    const float* msda_value;   // (B, S, M, 32) fp32
+    const int64_t* msda_shapes;
+    const int64_t* msda_starts;
+    const float* msda_ref;     // (rows, L, 2)
+    const float* msda_off;     // (rows, M, L, P, 2) raw offsets
+    const float* msda_logits;  // (rows, M, L * P) raw logits
+    int msda_S, msda_M, msda_Lq;
 };
 
 cudaError_t launch_decode_attention(const float* q, const float* k_new, const float* v_new, float* k_cache, float* v_cache,

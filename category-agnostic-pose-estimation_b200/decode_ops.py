@@ -6,6 +6,7 @@ functions over fp32 CUDA tensors, no autograd.  CUDA only, no fallback.
 """
 from __future__ import annotations
 
+import ctypes
 from typing import Optional
 
 import torch
@@ -93,6 +94,35 @@ def skinny_linear_split(x, wt, bias, split: int, *, x2=None):
                                           _stream(x.device))
     _lib.check(rc, "cape_skinny_linear_split")
     return y, y2
+
+
+def msda_output_proj(value_cache, spatial_shapes, level_start_index, reference_points, offsets, logits, wt, bias, *,
+                     residual, gamma, beta, eps: float = 1e-5):
+    """MSDeformAttn sampling on the projected-value cache + output projection + residual + LayerNorm in one launch
+    (``cape_msda_output_proj``): ``LayerNorm(residual + sample(...) @ wt + bias)``.  ``value_cache`` (B, S, M, 32) fp32,
+    ``reference_points`` (B, Lq, L, 2), ``offsets`` (B, Lq, M, L, P, 2), ``logits`` (B, Lq, M, L * P), ``wt`` (M * 32, N)."""
+    lib = _lib.load()
+    b, s_len, m, d = value_cache.shape
+    lq, lv, pts = offsets.shape[1], offsets.shape[3], offsets.shape[4]
+    k, n = wt.shape
+    if value_cache.dtype != torch.float32 or not value_cache.is_contiguous():
+        raise ValueError("value_cache must be a contiguous fp32 (B, S, M, 32) tensor")
+    if k != m * d or not wt.is_contiguous() or wt.dtype != torch.float32:
+        raise ValueError(f"wt must be a contiguous fp32 ({m * d}, N) tensor")
+    ref = reference_points.contiguous().float()
+    off = offsets.contiguous().float()
+    lg = logits.contiguous().float()
+    residual = _rows2d(residual, "residual")
+    if residual.shape[0] != b * lq:
+        raise ValueError(f"residual has {residual.shape[0]} rows, expected {b * lq}")
+    dims = _lib.Dims(b, s_len, m, d, lq, lv, pts)
+    y = torch.empty(b * lq, n, dtype=torch.float32, device=value_cache.device)
+    with torch.cuda.device(value_cache.device):
+        rc = lib.cape_msda_output_proj(_ptr(value_cache), _ptr(spatial_shapes), _ptr(level_start_index), _ptr(ref), _ptr(off),
+                                       _ptr(lg), ctypes.byref(dims), _ptr(wt), _p(bias), _ptr(residual), residual.stride(0),
+                                       _ptr(gamma), _ptr(beta), eps, _ptr(y), n, n, _stream(value_cache.device))
+    _lib.check(rc, "cape_msda_output_proj")
+    return y
 
 
 def coord_head_refine(x, wt, bias, w3, b3, ref, valid_ratios):

@@ -350,6 +350,9 @@ class AutoregressiveGenerator(IncrementalDecoder):
             raise NotImplementedError("the fused decode step needs d_model 256, head dim 32, q/k/v projections, ReLU and "
                                       "sine query positions (the CAPE configuration)")
         self.fused = can_fuse if fused is None else fused
+        # MSDeformAttn sampling + output_proj + residual + norm1 as ONE launch (cape_msda_output_proj: 15 launches per layer);
+        # False: the sampling op followed by the skinny linear (16 launches, identical results)
+        self.fuse_output_proj = True
         self._fprep = None
 
     def invalidate(self):
@@ -386,7 +389,7 @@ class AutoregressiveGenerator(IncrementalDecoder):
                 "w_cls": dec.class_embed[-1].weight.detach().contiguous(), "b_cls": dec.class_embed[-1].bias}
 
     def _run_fused(self):
-        """One token through every decoder layer with the hand-written step kernels: 16 launches per layer, no library
+        """One token through every decoder layer with the hand-written step kernels: 15 launches per layer, no library
         GEMM / attention call.  Same arithmetic as :meth:`_run` (fp32 FMA; only the summation order differs)."""
         from . import decode_ops as K
         dec, st = self.transformer.decoder, self.state
@@ -417,12 +420,17 @@ class AutoregressiveGenerator(IncrementalDecoder):
                 x = K.skinny_linear(xs, w["wt_so"], w["b_so"], residual=x, gamma=g, beta=b_, eps=eps)
             # MSDeformAttn on the cached projected value (:360-363)
             offsets, logits = K.skinny_linear_split(x, w["wt_ol"], w["b_ol"], w["n_off"], x2=qpos)   # :99-100
-            sampled = torch.ops.cape.ms_deform_attn_decode(
-                self.values[lid], shapes, starts, ref_levels.view(n, 1, ca.n_levels, 2),
-                offsets.view(n, 1, ca.n_heads, ca.n_levels, ca.n_points, 2),
-                logits.view(n, 1, ca.n_heads, ca.n_levels * ca.n_points)).view(n, -1)
             g, b_, eps = w["n1"]
-            x = K.skinny_linear(sampled, w["wt_out"], w["b_out"], residual=x, gamma=g, beta=b_, eps=eps)
+            off6 = offsets.view(n, 1, ca.n_heads, ca.n_levels, ca.n_points, 2)
+            lg4 = logits.view(n, 1, ca.n_heads, ca.n_levels * ca.n_points)
+            if self.fuse_output_proj and self.values[lid].dtype == torch.float32 and ca.n_levels == 4 and ca.n_points == 4:
+                # sampling + output_proj + residual + norm1 in one launch: the sampled rows never leave the SM (:112-113)
+                x = K.msda_output_proj(self.values[lid], shapes, starts, ref_levels.view(n, 1, ca.n_levels, 2), off6, lg4,
+                                       w["wt_out"], w["b_out"], residual=x, gamma=g, beta=b_, eps=eps)
+            else:
+                sampled = torch.ops.cape.ms_deform_attn_decode(
+                    self.values[lid], shapes, starts, ref_levels.view(n, 1, ca.n_levels, 2), off6, lg4).view(n, -1)
+                x = K.skinny_linear(sampled, w["wt_out"], w["b_out"], residual=x, gamma=g, beta=b_, eps=eps)
             hidden = K.skinny_linear(x, w["wt_f1"], w["b_f1"], relu=True)                      # FFN (:366-368)
             g, b_, eps = w["n3"]
             x = K.skinny_linear(hidden, w["wt_f2"], w["b_f2"], residual=x, gamma=g, beta=b_, eps=eps)

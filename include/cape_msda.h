@@ -271,6 +271,19 @@ CAPE_API int cape_coord_head_refine(const float* x, int x_stride, const float* w
                                     float* ref_levels, int rows, int K, int N, int n_levels, void* stream);
 CAPE_API int cape_tiny_linear(const float* x, int x_stride, const float* w, const float* bias, const float* refine_ref,
                               float* y, int rows, int K, int N, void* stream);
+/*
+ * cape_msda_output_proj — MSDeformAttn's sampling AND its output projection, residual and LayerNorm in one launch
+ *   (MSDeformAttn.forward, models/deformable_transformer.py:99-113, followed by the decoder layer's norm1,
+ *   deformable_transformer_v2.py:360-364):  y = LayerNorm_N(residual + sample(value_cache, ...) wt + bias) * gamma + beta.
+ *   The sampled (N * Lq, M * 32) rows are the input tile of the linear and never exist in HBM; arguments and arithmetic of
+ *   the sampling are those of cape_msda_decode (fp32 value cache, raw offsets and logits, reference points), of the linear
+ *   those of cape_skinny_linear with epilogue 2 (wt (M * 32, n_out) transposed weight, n_out <= 256).  D = 32, P = 4, L = 4.
+ */
+CAPE_API int cape_msda_output_proj(const float* value_cache, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                                   const float* reference_points, const float* sampling_offsets,
+                                   const float* attention_logits, const cape_msda_dims* dims, const float* wt,
+                                   const float* bias, const float* residual, int residual_stride, const float* gamma,
+                                   const float* beta, float eps, float* y, int y_stride, int n_out, void* stream);
 
 /*
  * fp32-accurate linear layer on the tensor cores ("3xTF32", tcgen05.mma.kind::tf32 with TMA-fed operands) for the

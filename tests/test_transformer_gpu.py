@@ -327,6 +327,42 @@ def test_split_linear_and_coordinate_head_fusions_vs_torch():
         assert rel_err(got_levels.cpu(), (want_ref[:, None, :] * valid).cpu()) < FWD_TOL_F32
 
 
+@pytest.mark.parametrize("rows,lq,m", [(1, 1, 8), (6, 1, 8), (128, 1, 8), (3, 5, 8), (7, 1, 4)])
+def test_sampling_fused_into_the_output_projection_equals_the_two_launch_path(rows, lq, m):
+    """cape_msda_output_proj (MSDeformAttn sampling as the input stage of output_proj + residual + norm1, one launch,
+    deformable_transformer.py:99-113 + deformable_transformer_v2.py:360-364) against cape::ms_deform_attn_decode followed by
+    the skinny linear — the same device code in the same order, so bit-identical — and against plain torch."""
+    from cape_b200 import decode_ops as K
+    g = torch.Generator().manual_seed(rows * 10 + lq)
+    shapes = torch.tensor(synthetic.CAPE_PYRAMID)
+    starts = cape_b200.level_start_index_from_shapes(shapes)
+    s_len = int((shapes[:, 0] * shapes[:, 1]).sum())
+    n_out = 32 * m
+    value = torch.randn(rows, s_len, m, 32, generator=g).cuda()
+    ref = torch.rand(rows, lq, 4, 2, generator=g).cuda()
+    off = (torch.randn(rows, lq, m, 4, 4, 2, generator=g) * 3).cuda()
+    logits = torch.randn(rows, lq, m, 16, generator=g).cuda()
+    lin = torch.nn.Linear(32 * m, n_out).cuda()
+    ln = torch.nn.LayerNorm(n_out).cuda()
+    with torch.no_grad():
+        ln.weight.uniform_(0.5, 1.5)
+        ln.bias.uniform_(-0.5, 0.5)
+    res = torch.randn(rows * lq, n_out, generator=g).cuda()
+    wt = lin.weight.detach().t().contiguous()
+    shapes_d, starts_d = shapes.cuda(), starts.cuda()
+    with torch.no_grad():
+        sampled = torch.ops.cape.ms_deform_attn_decode(value, shapes_d, starts_d, ref, off, logits).view(rows * lq, -1)
+        two = K.skinny_linear(sampled, wt, lin.bias, residual=res, gamma=ln.weight, beta=ln.bias, eps=ln.eps)
+        before = cape_b200.launch_count()
+        one = K.msda_output_proj(value, shapes_d, starts_d, ref, off, logits, wt, lin.bias, residual=res, gamma=ln.weight,
+                                 beta=ln.bias, eps=ln.eps)
+        assert cape_b200.launch_count() == before + 1
+        want = ln(res + lin(sampled))
+    torch.cuda.synchronize()
+    assert torch.equal(one, two)
+    assert rel_err(one.cpu(), want.cpu()) < FWD_TOL_F32
+
+
 # ---- 3xTF32 tensor-core linear (csrc/linear_tf32x3.cu) ---------------------------------------------------------------
 @pytest.mark.parametrize("m,n,k", [(128, 128, 32), (1, 128, 64), (300, 256, 256), (4099, 1024, 256), (1000, 256, 1024),
                                     (129, 384, 96)])

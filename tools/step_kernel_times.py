@@ -52,6 +52,8 @@ cases = {
     "attention self (51 keys)": lambda: K.decode_attention(qkv[:, :256], kc, vc, qkv[:, 256:512], qkv[:, 512:], pos),
     "attention support (17 keys)": lambda: K.decode_attention(x, sk, sv, key_bias=bias),
     "msda decode": lambda: torch.ops.cape.ms_deform_attn_decode(value, shapes, starts, refl, off, logits),
+    "msda decode + output_proj + res + LN (one launch)": lambda: K.msda_output_proj(value, shapes, starts, refl, off, logits, w256, b256,
+                                                                                   residual=x2, gamma=g, beta=be),
     "torch add (baseline launch)": lambda: torch.add(x, x2),
 }
 reps = 100
