@@ -83,7 +83,7 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 namespace {
 const char* const kTuneNames[kTuneCount] = {"FWD_THREADS", "FWD_QPC", "FWD_POINT_MAX_QM", "FWD_STAGED", "FWD_STAGED_MIN_QM",
                                             "FWD_STAGED_KB", "BWD_THREADS", "BWD_QPC", "BWD_MODE", "BWD_STAGED_KB", "PROFILE",
-                                            "BWD_TC_MIN_QM", "HOST_CHUNKS"};
+                                            "BWD_TC_MIN_QM", "HOST_CHUNKS", "WGRAD_TRANSPOSE"};
 std::atomic<int> g_tune[kTuneCount];
 std::once_flag g_tune_once;
 
@@ -676,14 +676,19 @@ int cape_linear_tf32x3(const float* x, const float* w, const float* w_lo, const 
 
 int cape_linear_tf32x3_wgrad(const float* grad_out, const float* x, float* grad_w, float* workspace, int rows, int N, int K,
                              void* stream) {
-    if (rows <= 0 || N <= 0 || K <= 0 || rows % 32 != 0 || N % 32 != 0 || K % 128 != 0)
-        return fail(CAPE_ERR_BAD_DIMS, "bad weight-gradient dimensions (rows=%d N=%d K=%d; rows %% 32 == 0, K %% 128 == 0)", rows, N, K);
+    const bool transposed = cape::tuning(cape::kTuneWgradTranspose, 0) == 1;
+    if (rows <= 0 || N <= 0 || K <= 0 || N % 32 != 0 || K % 128 != 0 || (transposed && rows % 32 != 0))
+        return fail(CAPE_ERR_BAD_DIMS, "bad weight-gradient dimensions (rows=%d N=%d K=%d; N %% 32 == 0, K %% 128 == 0)", rows, N, K);
     int rc;
     if ((rc = check_ptr(grad_out, "grad_out", false)) || (rc = check_ptr(x, "x", false)) || (rc = check_ptr(grad_w, "grad_w", false)) ||
-        (rc = check_ptr(workspace, "workspace", false)))
+        (rc = check_ptr(workspace, "workspace", !transposed)))
         return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    // workspace: g^T (N, rows) | x^T (K, rows) | lo(x^T) (K, rows)
+    if (!transposed) {   // default: operands read in place (MN-major tiles), no transposed copies
+        const cudaError_t e0 = launch_wgrad_tf32x3(grad_out, x, grad_w, rows, N, K, s);
+        return e0 == cudaSuccess ? 0 : fail_cuda(e0, "cape_linear_tf32x3_wgrad launch");
+    }
+    // WGRAD_TRANSPOSE=1 (the earlier formulation, kept for A/B runs): workspace = g^T (N, rows) | x^T (K, rows) | lo(x^T) (K, rows)
     float* gt = workspace;
     float* xt = gt + static_cast<size_t>(N) * rows;
     float* xt_lo = xt + static_cast<size_t>(K) * rows;

@@ -19,7 +19,12 @@
 //   * mbarriers: full (TMA bytes landed), conv (x_lo in tensor memory), empty (tcgen05.commit: the MMAs that read the
 //     stage are done), tmem_full / tmem_empty (accumulator complete / drained);
 //   * split-K mode for weight gradients (tiny output, reduction over ~10^5 rows): work item = (tile, K slice of <= 1024),
-//     partial tiles are ADDED into y by the TMA (cp.reduce.async.bulk.tensor ... add).
+//     partial tiles are ADDED into y by the TMA (cp.reduce.async.bulk.tensor ... add);
+//   * MNMAJOR variant for those weight gradients, grad_w = g^T x: g (rows, N) and x (rows, K) are read where they are — the
+//     reduction index is the slow one in memory, so both operands are MN-major tiles (128-byte swizzle with 32-byte atoms,
+//     four TMA boxes of 32 rows x 32 columns per operand and stage) and both lo tiles are split in shared memory by the
+//     converter warps; no transposed copies (they were 6.7 % of a training step): 96 us instead of 232 us for
+//     108 800 x 256 x 256, 355 instead of 700 us for 108 800 x 1024 x 256 (cuBLAS fp32: 388 / 1130 us).
 // What bounds it (ncu): tensor pipe ~58 % active; per tile the SM takes in 384 KB of operand tiles (2/3 of it the W tiles
 // every CTA re-reads from L2), ~31 B/clk/SM — the L2 -> shared-memory ingress of one SM, not the stage count (3 -> 4
 // stages gained 3 %).  A 256-row tile per CTA (two MMAs per W tile) is the next step.
@@ -94,15 +99,29 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
     return (static_cast<uint64_t>(hi) << 32) | lo;
 }
 
+// MN-major operand tile (the contraction index is the SLOW one in memory: weight gradients read grad_out / x as they are).
+// For 32-bit MN-major operands the tensor core accepts one shared-memory layout only, the 128-byte swizzle with 32-byte
+// atoms (cute::UMMA::Layout_MN_SW128_32B_Atom, layout type SWIZZLE_128B_BASE32B; the TMA writes it with
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): rows of 128 B = 32 consecutive M (or N) indices of one k, the 32-byte chunks of a
+// row XOR-ed with k % 4; 4 k-rows per 512-byte atom, the next 4 k's 512 B further (stride byte offset), the next 32 M
+// indices 4096 B further (leading byte offset) — ((8,n),(4,k)):((1,LBO),(8,SBO)) in 16-byte units.
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t smem_addr) {
+    const uint32_t lo = ((smem_addr >> 4) & 0x3fffu) | ((4096u >> 4) << 16);
+    const uint32_t hi = (512u >> 4) | (1u << 14) | (1u << 29);
+    return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
 // cute::UMMA::InstrDescriptor for kind::tf32, fp32 accumulate, both operands K-major, M = 128, N = 128.
 constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((kBN >> 3) << 17) | ((kBM >> 4) << 24);
+constexpr uint32_t kInstrDescMN = kInstrDesc | (1u << 15) | (1u << 16);     // a_major = b_major = MN
 
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate) {
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate,
+                                          uint32_t idesc = kInstrDesc) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(kInstrDesc), "r"(accumulate)
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 // same MMA with the A operand read from tensor memory (128 lanes = rows, 8 columns = one K step of tf32 values)
@@ -118,12 +137,18 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-template <int ACT>   // 0 none, 1 ReLU
+// MNMAJOR (weight gradients, y (M, N) = a^T b with a (K, M) and b (K, N) row-major, i.e. both operands MN-major): map_x = a,
+// map_wh = b, map_wl unused; a stage is four tiles [a | a_lo | b | b_lo] (three stages), both lo tiles are produced in
+// shared memory by the converter warps (an elementwise pass over the landed tiles: the layout is kept), no tensor-memory
+// operand.  K is then the number of ROWS of a / b and may end inside a block (the TMA zero-fills).
+template <int ACT, bool MNMAJOR = false>   // ACT: 0 none, 1 ReLU
 __global__ void __launch_bounds__(kGemmThreads, 1)
 linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_wh,
                      const __grid_constant__ CUtensorMap map_wl, const __grid_constant__ CUtensorMap map_y,
                      const float* __restrict__ bias, int M, int N, int K, int splits) {
     extern __shared__ uint8_t smem_raw[];
+    constexpr int kStages = MNMAJOR ? 3 : cape::kStages;                  // shadows the file-level constants inside this kernel
+    constexpr int kStageBytes = (MNMAJOR ? 4 : 3) * kTileBytes;           // (3 x 64 KB = 4 x 48 KB)
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // swizzle atoms need 1024-byte alignment
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
     // barriers: full[S], conv[S], empty[S], tmem_full[2], tmem_empty[2]; then the tensor-memory base address
@@ -137,7 +162,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // Work item t = (output tile, K split): with splits > 1 (weight gradients: tiny output, reduction over all rows)
     // every item covers a slice of the reduction dimension and the epilogue ADDS its partial tile to y (TMA reduce).
-    const int k_blocks_all = K / kBK;
+    const int k_blocks_all = MNMAJOR ? (K + kBK - 1) / kBK : K / kBK;
     const int kb_per = (k_blocks_all + splits - 1) / splits;
     const int n_tiles = N / kBN;
     const int tiles = n_tiles * ((M + kBM - 1) / kBM) * splits;            // persistent: item t = blockIdx.x, += gridDim.x
@@ -180,6 +205,15 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                     const int s = it % kStages;
                     mbar_wait(empty(s), ((it / kStages) & 1) ^ 1);
                     const uint32_t st = base + s * kStageBytes;
+                    if (MNMAJOR) {   // four boxes of 32 k-rows x 32 columns per operand: one per 32-wide M / N block
+                        mbar_arrive_expect_tx(full(s), 2 * kTileBytes);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            tma_load_2d(st + j * 4096, &map_x, full(s), m0 + 32 * j, kb * kBK);
+                            tma_load_2d(st + 2 * kTileBytes + j * 4096, &map_wh, full(s), n0 + 32 * j, kb * kBK);
+                        }
+                        continue;
+                    }
                     mbar_arrive_expect_tx(full(s), 3 * kTileBytes);
                     tma_load_2d(st, &map_x, full(s), kb * kBK, m0);
                     tma_load_2d(st + kTileBytes, &map_wh, full(s), kb * kBK, n0);
@@ -204,6 +238,19 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                     mbar_wait(conv(s), parity);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t st = base + s * kStageBytes;
+                    if (MNMAJOR) {
+                        const uint64_t d_a = umma_desc_mn(st), d_alo = umma_desc_mn(st + kTileBytes);
+                        const uint64_t d_b = umma_desc_mn(st + 2 * kTileBytes), d_blo = umma_desc_mn(st + 3 * kTileBytes);
+#pragma unroll
+                        for (int k = 0; k < kBK / 8; ++k) {   // 8 k-rows (two 512-byte atoms, 1024 B) per UMMA_K step
+                            const uint64_t adv = static_cast<uint64_t>(k * (1024 >> 4));
+                            umma_tf32(tmem_acc, d_alo + adv, d_b + adv, (kb != kb0) | (k != 0), kInstrDescMN);
+                            umma_tf32(tmem_acc, d_a + adv, d_blo + adv, 1, kInstrDescMN);
+                            umma_tf32(tmem_acc, d_a + adv, d_b + adv, 1, kInstrDescMN);
+                        }
+                        umma_commit(empty(s));
+                        continue;
+                    }
                     const uint64_t d_x = umma_desc(st);
                     const uint64_t d_wh = umma_desc(st + kTileBytes), d_wl = umma_desc(st + 2 * kTileBytes);
                     const uint32_t t_xlo = tmem_base + kALoCol + s * kBK;
@@ -230,6 +277,24 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             for (int kb = kb0; kb < kb1; ++kb, ++it) {
                 const int s = it % kStages;
                 mbar_wait(full(s), (it / kStages) & 1);
+                if (MNMAJOR) {   // lo tiles of both operands, written next to them in the same (swizzled) layout
+                    uint8_t* st_ptr = base_ptr + s * kStageBytes;
+                    const int t128 = (warp - 2) * 32 + lane;
+#pragma unroll
+                    for (int tile = 0; tile < 2; ++tile) {
+                        const uint8_t* hi = st_ptr + tile * 2 * kTileBytes;
+#pragma unroll
+                        for (int i = 0; i < kTileBytes / (16 * kConvThreads); ++i) {
+                            const int o = (i * kConvThreads + t128) * 16;
+                            const float4 v = *reinterpret_cast<const float4*>(hi + o);
+                            *reinterpret_cast<float4*>(const_cast<uint8_t*>(hi) + kTileBytes + o) =
+                                make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+                        }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_arrive(conv(s));
+                    continue;
+                }
                 const uint8_t* src = base_ptr + s * kStageBytes + row * 128;
                 uint32_t r[32];
 #pragma unroll
@@ -372,7 +437,8 @@ EncodeTiledFn encode_tiled() {
 
 // (rows, K) row-major fp32 -> boxes of box_rows rows x 32 columns, 128-byte swizzle; out-of-range rows read as zeros /
 // are not written.
-bool make_map(CUtensorMap* map, const float* ptr, int rows, int K, int box_rows = kBM) {
+bool make_map(CUtensorMap* map, const float* ptr, int rows, int K, int box_rows = kBM,
+              CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn fn = encode_tiled();
     if (!fn) return false;
     const cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
@@ -380,7 +446,7 @@ bool make_map(CUtensorMap* map, const float* ptr, int rows, int K, int box_rows 
     const cuuint32_t box[2] = {kBK, static_cast<cuuint32_t>(box_rows)};
     const cuuint32_t elem[2] = {1, 1};
     return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, elem,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -446,6 +512,41 @@ cudaError_t launch_linear_tf32x3(const float* x, const float* w, const float* w_
         linear_tf32x3_kernel<1><<<grid, kGemmThreads, kGemmSmem, stream>>>(map_x, map_wh, map_wl, map_y, bias, M, N, K, splits);
     else
         linear_tf32x3_kernel<0><<<grid, kGemmThreads, kGemmSmem, stream>>>(map_x, map_wh, map_wl, map_y, bias, M, N, K, splits);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// grad_w (N, K) = grad_out^T . x for grad_out (rows, N) and x (rows, K), both row-major: the operands are read where they
+// are (MN-major tiles), no transposed copies; rows are split into chains of <= 1024 whose partial tiles the TMA adds into
+// grad_w (zero-filled first).  N % 32 == 0, K % 128 == 0.
+cudaError_t launch_wgrad_tf32x3(const float* grad_out, const float* x, float* grad_w, int rows, int N, int K, cudaStream_t stream) {
+    if (rows == 0) return cudaMemsetAsync(grad_w, 0, static_cast<size_t>(N) * K * sizeof(float), stream);
+    CUtensorMap map_g, map_x, map_y;
+    // boxes of 32 rows (reduction index) x 32 columns of the row-major operands
+    if (!make_map(&map_g, grad_out, rows, N, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
+        !make_map(&map_x, x, rows, K, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) || !make_map(&map_y, grad_w, N, K, 32))
+        return cudaErrorNotSupported;
+    static unsigned long long configured = 0;
+    if (first_use_on_device(&configured))
+        cudaFuncSetAttribute(linear_tf32x3_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmem));
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int out_tiles = (K / kBN) * ((N + kBM - 1) / kBM);
+    constexpr int kMaxChain = 32;                      // see launch_linear_tf32x3
+    const int k_blocks = (rows + kBK - 1) / kBK;
+    int splits = out_tiles < sms ? sms / out_tiles : 1;
+    if (splits * kMaxChain < k_blocks) splits = (k_blocks + kMaxChain - 1) / kMaxChain;
+    if (splits > k_blocks) splits = k_blocks;
+    if (splits < 1) splits = 1;
+    const int per = (k_blocks + splits - 1) / splits;
+    splits = (k_blocks + per - 1) / per;
+    if (splits > 1) {
+        const cudaError_t e = cudaMemsetAsync(grad_w, 0, static_cast<size_t>(N) * K * sizeof(float), stream);
+        if (e != cudaSuccess) return e;
+    }
+    const int tiles = out_tiles * splits;
+    const dim3 grid(tiles < sms ? tiles : sms);
+    linear_tf32x3_kernel<0, true><<<grid, kGemmThreads, kGemmSmem, stream>>>(map_g, map_x, map_x, map_y, nullptr, N, K, rows, splits);
     count_launch();
     return cudaGetLastError();
 }

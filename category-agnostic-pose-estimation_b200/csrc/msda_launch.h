@@ -122,6 +122,7 @@ cudaError_t launch_tiny_linear(const float* x, int x_stride, const float* w, con
 cudaError_t launch_tf32_split_lo(const float* x, float* lo, int64_t n, cudaStream_t stream);
 cudaError_t launch_linear_tf32x3(const float* x, const float* w, const float* w_lo, const float* bias, float* y, int M, int N,
                                  int K, int act, int split_k, cudaStream_t stream);
+cudaError_t launch_wgrad_tf32x3(const float* grad_out, const float* x, float* grad_w, int rows, int N, int K, cudaStream_t stream);
 cudaError_t launch_transpose_lo(const float* in, float* out, float* out_lo, int R, int C, cudaStream_t stream);
 cudaError_t launch_seq_embed_forward(const SeqEmbedArgs& a, cudaStream_t stream);
 cudaError_t launch_seq_embed_backward(const SeqEmbedArgs& a, cudaStream_t stream);
@@ -152,7 +153,7 @@ inline int balanced_q_per_cta(int64_t nm, int lq, int q_default, int slots, int 
 // time through cape_set_tuning() (tools/tune.py).  Values <= 0 mean "default".
 enum Tune {
     kTuneFwdThreads, kTuneFwdQpc, kTuneFwdPointMaxQm, kTuneFwdStaged, kTuneFwdStagedMinQm, kTuneFwdStagedKb,
-    kTuneBwdThreads, kTuneBwdQpc, kTuneBwdMode, kTuneBwdStagedKb, kTuneProfile, kTuneBwdTcMinQm, kTuneHostChunks, kTuneCount
+    kTuneBwdThreads, kTuneBwdQpc, kTuneBwdMode, kTuneBwdStagedKb, kTuneProfile, kTuneBwdTcMinQm, kTuneHostChunks, kTuneWgradTranspose, kTuneCount
 };
 int tuning(Tune knob, int fallback);
 

@@ -133,27 +133,32 @@ def _workspace(numel: int, device) -> torch.Tensor:
 def wgrad_supported(g2: torch.Tensor, x2: torch.Tensor) -> bool:
     rows, n = g2.shape
     k = x2.shape[1]
-    return (g2.is_cuda and g2.dtype == torch.float32 and x2.dtype == torch.float32 and rows % 32 == 0 and rows >= 1024
+    return (g2.is_cuda and g2.dtype == torch.float32 and x2.dtype == torch.float32 and rows >= 1024
             and n % 128 == 0 and k % 128 == 0)
 
 
 def linear_tf32x3_wgrad(grad_out: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
-    """grad_w (N, K) = grad_out (rows, N)^T @ x (rows, K) through the 3xTF32 kernel (split over the SMs along the rows)."""
+    """grad_w (N, K) = grad_out (rows, N)^T @ x (rows, K) through the 3xTF32 kernel: both operands are read where they are
+    (MN-major tiles, lo parts split in shared memory), the rows are split over the SMs in chains of <= 1024 whose partial tiles
+    the TMA adds into grad_w.  (Tuning knob WGRAD_TRANSPOSE=1: the earlier form on transposed copies, kept for A/B runs.)"""
     lib = _lib.load()
     g2, x2 = grad_out.detach().contiguous(), x.detach().contiguous()
     rows, n = g2.shape
     k = x2.shape[1]
     grad_w = torch.empty(n, k, dtype=torch.float32, device=g2.device)
-    workspace = _workspace((n + 2 * k) * rows, g2.device)
+    transposed = lib.cape_get_tuning(b"WGRAD_TRANSPOSE") == 1
+    workspace = _workspace((n + 2 * k) * rows, g2.device) if transposed else None
     with torch.cuda.device(g2.device):
-        rc = lib.cape_linear_tf32x3_wgrad(_ptr(g2), _ptr(x2), _ptr(grad_w), _ptr(workspace), rows, n, k, _stream(g2.device))
+        rc = lib.cape_linear_tf32x3_wgrad(_ptr(g2), _ptr(x2), _ptr(grad_w), None if workspace is None else _ptr(workspace),
+                                          rows, n, k, _stream(g2.device))
     _lib.check(rc, "cape_linear_tf32x3_wgrad")
     return grad_w
 
 
 class _LinearTF32x3(torch.autograd.Function):
     """Training form: forward, the input gradient (g . W, the same K-major GEMM with W^T as the weight) and the weight
-    gradient (g^T . x on transposed operands, reduction split over the SMs) all run on the 3xTF32 kernel."""
+    gradient (g^T . x with both operands read in place as MN-major tiles, reduction split over the SMs) all run on the 3xTF32
+    kernel."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):

@@ -297,10 +297,13 @@ CAPE_API int cape_tf32_split_lo(const float* x, float* lo, int64_t n, void* stre
 CAPE_API int cape_linear_tf32x3(const float* x, const float* w, const float* w_lo, const float* bias, float* y, int M, int N,
                                 int K, int act, void* stream);
 /*
- * Weight gradient of that layer, grad_w (N, K) = grad_out (rows, N)^T . x (rows, K), on the same kernel: the operands are
- * transposed into `workspace` ((N + 2 K) * rows floats: grad_out^T, x^T and the lo part of x^T) so that the row index is the
- * contiguous reduction dimension, the reduction is split over the SMs and the partial tiles are added into grad_w by the
- * TMA (cp.reduce.async.bulk.tensor ... add); grad_w is zero-filled by the call.  rows % 32 == 0, N % 32 == 0, K % 128 == 0.
+ * Weight gradient of that layer, grad_w (N, K) = grad_out (rows, N)^T . x (rows, K), on the same kernel: both operands are
+ * read where they are as MN-major tiles (the row index is the reduction dimension; 128-byte swizzle with 32-byte atoms, the
+ * one layout the tensor core takes for 32-bit MN-major operands), their lo parts are split in shared memory, the reduction
+ * is cut into chains of <= 1024 rows spread over the SMs and the partial tiles are added into grad_w by the TMA
+ * (cp.reduce.async.bulk.tensor ... add); grad_w is zero-filled by the call.  N % 32 == 0, K % 128 == 0; `workspace` may be
+ * NULL.  (Tuning knob WGRAD_TRANSPOSE=1 selects the earlier form on transposed copies: workspace of (N + 2 K) * rows floats,
+ * rows % 32 == 0.)
  */
 CAPE_API int cape_linear_tf32x3_wgrad(const float* grad_out, const float* x, float* grad_w, float* workspace, int rows, int N,
                                       int K, void* stream);
