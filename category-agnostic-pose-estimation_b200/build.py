@@ -48,7 +48,7 @@ def build(force: bool = False, verbose: bool = False, variant: str = "") -> str:
     extra = []
     if variant:
         extra = {"nored": ["-DCAPE_EXP_NO_RED"], "noload": ["-DCAPE_EXP_NO_LOAD"], "t896": ["-DCAPE_BS_THREADS=896"],
-                 "t768": ["-DCAPE_BS_THREADS=768"], "nocoarsered": ["-DCAPE_EXP_NO_COARSE_RED=12"], "fwdtable": ["-DCAPE_FWD_TABLE=1"], "nored0": ["-DCAPE_EXP_NO_COARSE_RED=1"], "nored1": ["-DCAPE_EXP_NO_COARSE_RED=2"],
+                 "t768": ["-DCAPE_BS_THREADS=768"], "nocoarsered": ["-DCAPE_EXP_NO_COARSE_RED=12"], "fwdtable": ["-DCAPE_FWD_TABLE=1"], "redcta": ["-DCAPE_EXP_RED_CTA_SCOPE"], "nored0": ["-DCAPE_EXP_NO_COARSE_RED=1"], "nored1": ["-DCAPE_EXP_NO_COARSE_RED=2"],
                  "nored2": ["-DCAPE_EXP_NO_COARSE_RED=4"], "nored3": ["-DCAPE_EXP_NO_COARSE_RED=8"], "nored01": ["-DCAPE_EXP_NO_COARSE_RED=3"], "evictlast": ["-DCAPE_EXP_EVICT_LAST"],
                  "streamstore": ["-DCAPE_EXP_STREAM_STORE"]}[variant]
         lib = os.path.join(os.path.dirname(HERE), "tools", f"libcape_msda_{variant}.so")

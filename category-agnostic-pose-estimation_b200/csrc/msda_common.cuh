@@ -148,6 +148,11 @@ template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return
 // fp32 vector reduction into global memory (REDG.E.ADD.F32x4 on sm_90+; p must be 16-byte aligned), executed only when
 // `pred`: the predicate rides on the REDG itself, no branch in the source.
 __device__ __forceinline__ void red_add4_if(float* p, bool pred, float x, float y, float z, float w) {
+#ifdef CAPE_EXP_RED_CTA_SCOPE   // profiling variant: CTA-scope reduction (does the scope change where the add happens?)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t@p red.relaxed.cta.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n\t}"
+                 ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(w), "r"(static_cast<int>(pred)) : "memory");
+    return;
+#endif
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t@p red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n\t}"
                  ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(w), "r"(static_cast<int>(pred)) : "memory");
 }
