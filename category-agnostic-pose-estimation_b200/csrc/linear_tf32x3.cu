@@ -24,7 +24,8 @@
 //     reduction index is the slow one in memory, so both operands are MN-major tiles (128-byte swizzle with 32-byte atoms,
 //     four TMA boxes of 32 rows x 32 columns per operand and stage) and both lo tiles are split in shared memory by the
 //     converter warps; no transposed copies (they were 6.7 % of a training step): 96 us instead of 232 us for
-//     108 800 x 256 x 256, 355 instead of 700 us for 108 800 x 1024 x 256 (cuBLAS fp32: 388 / 1130 us).
+//     108 800 x 256 x 256, 312 instead of 680 us for 108 800 x 1024 x 256 (cuBLAS fp32: 390 / 1130 us).  Work items run
+//     output-tile-fastest so that concurrent CTAs share a row slice's operand tiles in L2.
 // What bounds it (ncu): tensor pipe ~58 % active; per tile the SM takes in 384 KB of operand tiles (2/3 of it the W tiles
 // every CTA re-reads from L2), ~31 B/clk/SM — the L2 -> shared-memory ingress of one SM, not the stage count (3 -> 4
 // stages gained 3 %).  A 256-row tile per CTA (two MMAs per W tile) is the next step.
@@ -166,8 +167,12 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     const int kb_per = (k_blocks_all + splits - 1) / splits;
     const int n_tiles = N / kBN;
     const int tiles = n_tiles * ((M + kBM - 1) / kBM) * splits;            // persistent: item t = blockIdx.x, += gridDim.x
+    const int out_tiles = n_tiles * ((M + kBM - 1) / kBM);
     const auto item = [&](int t, int& m0, int& n0, int& kb0, int& kb1) {
-        const int sp = t % splits, tile = t / splits;
+        // weight gradients: the output tile is the FAST index, so the CTAs running at the same time work on the same slice of
+        // rows and share its operand tiles through L2 (every operand tile is needed by all tiles of the other dimension:
+        // with the slice as the fast index DRAM read 1.63 GB for 108 800 x 1024 x 256, 2.9x the operands)
+        const int sp = MNMAJOR ? t / out_tiles : t % splits, tile = MNMAJOR ? t % out_tiles : t / splits;
         m0 = (tile / n_tiles) * kBM;
         n0 = (tile % n_tiles) * kBN;
         kb0 = sp * kb_per;
