@@ -52,7 +52,8 @@ def build(force: bool = False, verbose: bool = False, variant: str = "") -> str:
                  "nored2": ["-DCAPE_EXP_NO_COARSE_RED=4"], "nored3": ["-DCAPE_EXP_NO_COARSE_RED=8"], "nored01": ["-DCAPE_EXP_NO_COARSE_RED=3"], "evictlast": ["-DCAPE_EXP_EVICT_LAST"],
                  "streamstore": ["-DCAPE_EXP_STREAM_STORE"]}[variant]
         lib = os.path.join(os.path.dirname(HERE), "tools", f"libcape_msda_{variant}.so")
-        return _compile(lib, extra, verbose, os.path.join(HERE, "build", variant))
+        import tempfile   # objects of profiling variants stay out of the tree (the tree travels to the GPU box)
+        return _compile(lib, extra, verbose, os.path.join(tempfile.gettempdir(), "cape_msda_build", variant))
     if not force and not _stale():
         return LIB
     return _compile(LIB, extra, verbose, os.path.join(HERE, "build"))
