@@ -75,7 +75,7 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index = index
-        self.samples, self.reasons = [], set()
+        self.samples, self.reasons, self.power = [], set(), []
         self.max_mhz = None
         self._stop = threading.Event()
         self._thread = None
@@ -94,6 +94,10 @@ class ClockSampler:
         while not self._stop.is_set():
             try:
                 self.samples.append(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM))
+                try:
+                    self.power.append(n.nvmlDeviceGetPowerUsage(self._h) / 1000.0)
+                except Exception:
+                    pass
                 try:
                     mask = n.nvmlDeviceGetCurrentClocksEventReasons(self._h)
                 except Exception:
@@ -131,8 +135,12 @@ class ClockSampler:
         if self._thread:
             self._thread.join(timeout=10)
         s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(s)}
+        out = {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+               "samples": len(s)}
+        if self.power:
+            pw = sorted(self.power)
+            out["power_w_median"], out["power_w_max"] = round(pw[len(pw) // 2], 1), round(pw[-1], 1)
+        return out
 
 
 # ---- CPU arm: the reference's own function (staged in baseline/_ref), else the oracle port ------------------------------
@@ -397,6 +405,8 @@ def cape_train_step(dev, rank, world, steps=3, with_reference=False, amp=False, 
         launches0 = cape_b200.launch_count()
         epoch(1, patched, buckets, opt, scaler)
         per_step = cape_b200.launch_count() - launches0
+        sampler = ClockSampler(dev.index if dev.index is not None else 0)     # this rank's GPU, during the timed steps
+        sampler.start()
         times = []                      # every optimizer step timed on its own (device events, max over ranks); median reported:
         for _ in range(steps):          # single steps on a shared host vary by +-25 % now and then (tools/arm_variance.py)
             cdist.barrier(dev)
@@ -408,13 +418,16 @@ def cape_train_step(dev, rank, world, steps=3, with_reference=False, amp=False, 
             torch.cuda.synchronize(dev)
             times.append(cdist.max_over_ranks(e0.elapsed_time(e1), dev))
         ms = sorted(times)[len(times) // 2]
+        clocks.update(sampler.stop())
         buckets.remove()
         for p in model.parameters():
             p.grad = None
         return ms, per_step, stats, len(buckets.buckets)
 
+    clocks = {}
     ms, launches, stats, n_buckets = measure(True)
     out = {"episodes_per_s": round(world * accumulation * episodes / (ms * 1e-3), 2), "ms_per_optimizer_step": round(ms, 2),
+           "clocks_rank0": dict(clocks),
            "episodes_per_step": world * accumulation * episodes, "accumulation": accumulation,
            "micro_batch": f"{episodes} episodes x {k} queries (N={episodes * k}), {shots}-shot, {kpts} keypoints, 512x512",
            "trainable_params": n_params, "allreduce_mb": round(n_params * 4 / 2 ** 20, 1), "allreduce_buckets": n_buckets,
