@@ -174,6 +174,21 @@ def test_backward_tensor_core_scatter_other_pyramids(staged, shapes, m, mode):
         assert rel_err(got, w) < 1e-4
 
 
+@pytest.mark.parametrize("shapes", [((20, 24), (10, 12), (5, 6)), ((12, 12), (8, 8)), ((9, 9), (16, 16), (4, 4), (7, 9)),
+                                    ((16, 16), (12, 12))])
+def test_small_cta_tensor_core_scatter_with_fewer_levels(staged, shapes):
+    """BWD_MODE=5 with 3 and 2 pyramid levels, a last level of exactly 64 pixels / of 63 pixels, and a last level too large
+    for the 64-row tile (144 pixels: it keeps its REDs, the tiles stay unused)."""
+    inp = synthetic.make_inputs(2, 301, shapes, n_heads=4, dist="uniform", seed=len(shapes))
+    want = msda_c.msda_backward(inp["grad_output"].numpy(), *_oracle_args(inp), dtype=np.float32)
+    staged("BWD_MODE", 5)
+    before = cape_b200.launch_count()
+    gv, gl, ga = _fwd_bwd(inp)
+    assert cape_b200.launch_count() == before + 2
+    for got, w in zip((gv, gl, ga), want):
+        assert rel_err(got, w) < 1e-4
+
+
 @pytest.mark.parametrize("mode", [2, 5])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 def test_backward_tensor_core_scatter_half_precision(staged, dtype, mode):

@@ -363,6 +363,36 @@ def test_sampling_fused_into_the_output_projection_equals_the_two_launch_path(ro
     assert rel_err(one.cpu(), want.cpu()) < FWD_TOL_F32
 
 
+def test_fused_output_projection_rejects_what_it_does_not_cover():
+    """cape_msda_output_proj: error codes instead of launches for dimensions outside D = 32 / P = 4 / L = 4, N > 256, missing
+    LayerNorm parameters; zero rows is a no-op."""
+    import ctypes
+    from cape_b200 import _lib
+    lib = _lib.load()
+    dev = "cuda"
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    value = torch.zeros(2, 5440, 8, 32, device=dev)
+    shapes = torch.tensor(synthetic.CAPE_PYRAMID, device=dev)
+    starts = cape_b200.level_start_index_from_shapes(shapes.cpu()).to(dev)
+    ref, off, lg = torch.zeros(2, 1, 4, 2, device=dev), torch.zeros(2, 1, 8, 4, 4, 2, device=dev), torch.zeros(2, 1, 8, 16, device=dev)
+    wt, vec, y = torch.zeros(256, 256, device=dev), torch.zeros(512, device=dev), torch.zeros(2, 512, device=dev)
+
+    def call(dims, n_out=256, gamma=vec):
+        return lib.cape_msda_output_proj(p(value), p(shapes), p(starts), p(ref), p(off), p(lg), ctypes.byref(dims), p(wt), p(vec),
+                                         p(y), 512, None if gamma is None else p(gamma), p(vec), 1e-5, p(y), 512, n_out, None)
+    before = cape_b200.launch_count()
+    assert call(_lib.Dims(2, 5440, 8, 32, 1, 4, 4)) == 0
+    assert cape_b200.launch_count() == before + 1
+    assert call(_lib.Dims(2, 5440, 8, 32, 1, 4, 2)) == -1            # P != 4
+    assert call(_lib.Dims(2, 5440, 8, 16, 1, 4, 4)) == -1            # D != 32
+    assert call(_lib.Dims(2, 5440, 8, 32, 1, 3, 4)) == -1            # L != 4
+    assert call(_lib.Dims(2, 5440, 8, 32, 1, 4, 4), n_out=512) == -1  # LayerNorm epilogue: N <= 256
+    assert call(_lib.Dims(2, 5440, 8, 32, 1, 4, 4), gamma=None) == -1
+    assert call(_lib.Dims(0, 5440, 8, 32, 1, 4, 4)) == 0             # no rows: nothing launched
+    assert cape_b200.launch_count() == before + 1
+    torch.cuda.synchronize()
+
+
 # ---- 3xTF32 tensor-core linear (csrc/linear_tf32x3.cu) ---------------------------------------------------------------
 @pytest.mark.parametrize("m,n,k", [(128, 128, 32), (1, 128, 64), (300, 256, 256), (4099, 1024, 256), (1000, 256, 1024),
                                     (129, 384, 96)])
