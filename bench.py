@@ -15,9 +15,10 @@ value   = sum over ranks of algorithmic bytes (A_fwd + A_bwd, each tensor once) 
 e2e     = same metric through the C-ABI host entry point (cape_msda_forward_backward_host): pinned HOST buffers in,
           results back on the host, copies inside the timed region.
 roofline= the dominant kernel (backward) against the measured HBM copy peak in MEASURED_PEAKS.json.
-cpu_baseline = the oracle port of the reference path (oracle/msda_torch.py: the same per-level grid_sample
-          formulation on ATen's CPU kernels) timed on this box's host cores on a bounded sample.
---impl reference times that CPU port alone, same metric/unit/config, rank 0 only.
+cpu_baseline = the reference's own ms_deform_attn_core_pytorch + autograd (staged unmodified in baseline/_ref by
+          tools/stage_reference.py; the oracle port oracle/msda_torch.py only where the reference is not staged) timed on
+          this box's host cores at the full N = 20.
+--impl reference times that CPU function alone, same metric/unit/config, rank 0 only.
 """
 from __future__ import annotations
 
@@ -150,20 +151,34 @@ def _stage_reference_module():
     return stage_reference
 
 
+_REFERENCE_DT = []
+
+
+def reference_dt_module():
+    """(module, path) of the UNMODIFIED reference's models/deformable_transformer.py loaded from baseline/_ref (or
+    /root/reference in the build container) by file location — it needs only ``util.misc`` — or (None, None)."""
+    if not _REFERENCE_DT:
+        sr = _stage_reference_module()
+        root = sr.root()
+        mod = path = None
+        if root is not None:
+            import importlib.util
+            if root not in sys.path:
+                sys.path.insert(0, root)
+            path = os.path.join(root, "models", "deformable_transformer.py")
+            spec = importlib.util.spec_from_file_location("cape_reference_deformable_transformer", path)
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            path = os.path.relpath(path, REPO) if path.startswith(REPO) else path
+        _REFERENCE_DT.append((mod, path))
+    return _REFERENCE_DT[0]
+
+
 def reference_core():
-    """(fn, kind, what): ``ms_deform_attn_core_pytorch`` of the UNMODIFIED reference loaded from baseline/_ref (or
-    /root/reference in the build container) by file location — it needs only ``util.misc`` — else the oracle port."""
-    sr = _stage_reference_module()
-    root = sr.root()
-    if root is not None:
-        import importlib.util
-        if root not in sys.path:
-            sys.path.insert(0, root)
-        path = os.path.join(root, "models", "deformable_transformer.py")
-        spec = importlib.util.spec_from_file_location("cape_reference_deformable_transformer", path)
-        mod = importlib.util.module_from_spec(spec)
-        spec.loader.exec_module(mod)
-        rel = os.path.relpath(path, REPO) if path.startswith(REPO) else path
+    """(fn, kind, what): ``ms_deform_attn_core_pytorch`` of the unmodified reference, else the oracle port (CPU baseline leg
+    only: nothing under oracle/ is executed on a box where the reference is staged)."""
+    mod, rel = reference_dt_module()
+    if mod is not None:
         return mod.ms_deform_attn_core_pytorch, "reference", f"{rel}: ms_deform_attn_core_pytorch + autograd backward"
     from oracle import msda_torch
     return msda_torch.msda_core, "port", "oracle/msda_torch.py (reference not staged on this box)"
@@ -668,10 +683,9 @@ def module_step(dev):
     """one MSDeformAttn MODULE call of the encoder at the training shape (N=20, Lq=S=5440),
     forward + backward: the mirror with the fused prologue, the mirror materialising sampling_locations /
     attention_weights like the reference (our core op, torch prologue), and the reference's formulation run eagerly on
-    this GPU (oracle/msda_torch.py — baseline only)."""
+    this GPU (the reference's own MSDeformAttn class from baseline/_ref with the same weights — baseline only)."""
     import torch
     import cape_b200
-    from oracle import msda_torch
     w = WORKLOAD
     torch.manual_seed(0)
     mod = cape_b200.MSDeformAttn(256, 4, 8, 4).to(dev)
@@ -685,15 +699,13 @@ def module_step(dev):
     ref = cape_b200.synthetic.pyramid_reference_points(cape_b200.synthetic.CAPE_PYRAMID, w["Lq"]).to(dev)
     ref = ref[None, :, None, :].expand(w["N"], w["Lq"], 4, 2).contiguous()
     gout = torch.randn(w["N"], w["Lq"], 256, device=dev)
-    weights = {k: v.detach() for k, v in mod.state_dict().items()}
-    shapes_l = shapes.tolist()
 
-    def run(fn):
+    def run(fn, module=None):
         def step():
             out = fn()
             out.backward(gout)
             src.grad = None
-            mod.zero_grad(set_to_none=True)
+            (module or mod).zero_grad(set_to_none=True)
         return _time_us(step, 10) / 1e3
 
     mod.fuse_prologue = True
@@ -706,12 +718,17 @@ def module_step(dev):
         fused_tc = run(lambda: mod(src + pos, ref, src, shapes, starts, None))
     finally:
         cape_b200.set_linear_mode("fp32")
-    wreq = {k: v.clone().requires_grad_(True) for k, v in weights.items()}
-    eager = run(lambda: msda_torch.msda_module_forward(wreq, src + pos, ref, src, shapes_l, None))
+    ref_dt, _ = reference_dt_module()
+    eager = None
+    if ref_dt is not None:                         # the unmodified reference module, unpatched, same weights
+        ref_mod = ref_dt.MSDeformAttn(256, 4, 8, 4).to(dev)
+        ref_mod.load_state_dict(mod.state_dict())
+        eager = run(lambda: ref_mod(src + pos, ref, src, shapes, starts, None), ref_mod)
+        del ref_mod
     return {"N": w["N"], "Lq": w["Lq"], "fwd_bwd_ms": {"mirror_fused_prologue": round(fused, 3),
                                                          "mirror_fused_prologue_tensor_core_linears": round(fused_tc, 3),
                                                          "mirror_materialised_prologue": round(unfused, 3),
-                                                         "reference_formulation_eager_gpu": round(eager, 3)},
+                                                         "reference_module_eager_gpu": None if eager is None else round(eager, 3)},
             "note": "includes the four nn.Linear projections and their backward (cuBLAS fp32, or the opt-in 3xTF32 kernel)"}
 
 
@@ -897,25 +914,31 @@ def generation(dev, episodes=64, keypoints=100):
 
 
 def gpu_eager_baseline(dev, alg_bytes):
-    """The reference's formulation (oracle/msda_torch.py: per-level grid_sample, stack, multiply, sum) run eagerly on this
-    GPU through ATen's CUDA kernels — what a user of the reference sees on the same box.  Baseline only."""
+    """The reference's own function (baseline/_ref: per-level grid_sample, stack, multiply, sum) run eagerly on this GPU through
+    ATen's CUDA kernels — what a user of the reference sees on the same box.  Baseline only."""
     import torch
     import cape_b200
-    from oracle import msda_torch
+    ref_dt, rel = reference_dt_module()
+    if ref_dt is None:
+        return {"unavailable": "reference not staged (baseline/_ref)"}
+    core = ref_dt.ms_deform_attn_core_pytorch
     w = WORKLOAD
     inp = cape_b200.synthetic.make_inputs(w["N"], w["Lq"], dist="encoder", seed=0, device=dev)
-    shapes = inp["spatial_shapes"].tolist()
+    shapes = inp["spatial_shapes"]
     torch.cuda.reset_peak_memory_stats(dev)
     base = torch.cuda.memory_allocated(dev)
 
     def step():
-        msda_torch.msda_core_fwd_bwd(inp["value"], shapes, inp["sampling_locations"], inp["attention_weights"],
-                                     inp["grad_output"])
+        v = inp["value"].detach().requires_grad_(True)
+        loc = inp["sampling_locations"].detach().requires_grad_(True)
+        a = inp["attention_weights"].detach().requires_grad_(True)
+        torch.autograd.grad(core(v, shapes, loc, a), (v, loc, a), inp["grad_output"])
     t = _time_us(step, 5)
     peak = torch.cuda.max_memory_allocated(dev) - base
     return {"value": round(alg_bytes / t / 1e3, 2), "unit": UNIT, "ms_per_step": round(t / 1e3, 3),
-            "peak_extra_memory_mb": round(peak / 2 ** 20), "kind": "port",
-            "sample": "oracle/msda_torch.py on the same B200 (ATen grid_sampler_2d CUDA kernels), full N=20 workload, fp32"}
+            "peak_extra_memory_mb": round(peak / 2 ** 20), "kind": "reference",
+            "sample": f"{rel}: ms_deform_attn_core_pytorch + autograd on the same B200 (ATen grid_sampler_2d CUDA kernels), "
+                      "full N=20 workload, fp32"}
 
 
 def copy_probe(dev, rank, world, mb=256, reps=4):
